@@ -1,0 +1,187 @@
+/*
+ * nbg_b200.h -- C ABI of the B200-native numbagg hot path (libnbg_b200.so).
+ *
+ * Drop-in boundary.  numbagg has no native code: its native boundary is the NumPy gufunc
+ * inner loop that numba emits for each decorated body,
+ *     void loop(char **args, npy_intp *dims, npy_intp *steps, void *data)
+ * (numba/np/ufunc/wrappers.py:334-343), built at numbagg/decorators.py:151-162 (move / exp),
+ * :427-463 (fill) and :533-556 (grouped).  Each entry point below replaces one family of
+ * those loops: `dims[0]` (outer-loop count) and the core dimension become explicit
+ * (outer, n, inner) sizes, `steps` are implied by C-contiguity, scalars are passed by value
+ * and operands are DEVICE pointers.  INTEGRATION.md shows the ctypes binding a numbagg
+ * maintainer would add in decorators.py.
+ *
+ * Conventions
+ *  - All data pointers are device pointers (cudaMalloc / torch CUDA tensors), never host.
+ *  - Every array operand is the C-contiguous 3-D view (outer, n, inner) of the caller's
+ *    array with the core axis in the middle; axis=-1 of a C-contiguous array is inner == 1,
+ *    any other axis of a C-contiguous array is inner > 1 -- no copy is ever needed for a
+ *    C- or F-contiguous input.  Output has the same view.
+ *  - Calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *    stream).  No allocation, no host synchronisation; the caller owns every buffer and
+ *    the kernels write every output element (outputs may be uninitialised on entry).
+ *  - Return value: NBG_OK or a negative nbg_status; hot-path kernels never raise on data
+ *    (NaN, inf, /0 are values).  nbg_last_error() gives a thread-local message.
+ *  - No CPU fallback exists: without a CUDA device every compute entry point fails.
+ */
+#ifndef NBG_B200_H
+#define NBG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBG_ABI_VERSION 1
+
+typedef enum {
+    NBG_OK = 0,
+    NBG_ERR_BAD_DTYPE = -1,
+    NBG_ERR_BAD_OP = -2,
+    NBG_ERR_BAD_ARG = -3,
+    NBG_ERR_UNSUPPORTED = -4, /* legal in numbagg but not built yet (see message) */
+    NBG_ERR_CUDA = -5,        /* launch / runtime failure: see nbg_last_error() */
+    NBG_ERR_WORKSPACE = -6    /* workspace too small */
+} nbg_status;
+
+typedef enum { NBG_F32 = 0, NBG_F64 = 1, NBG_I32 = 2, NBG_I64 = 3 } nbg_dtype;
+
+/* numbagg/moving.py:12-275 */
+typedef enum {
+    NBG_MOVE_MEAN = 0,
+    NBG_MOVE_SUM = 1,
+    NBG_MOVE_STD = 2,
+    NBG_MOVE_VAR = 3,
+    NBG_MOVE_COV = 4, /* two inputs */
+    NBG_MOVE_CORR = 5 /* two inputs */
+} nbg_move_op;
+
+/* numbagg/moving_exp.py:12-335 */
+typedef enum {
+    NBG_EXP_NANCOUNT = 0,
+    NBG_EXP_NANMEAN = 1,
+    NBG_EXP_NANSUM = 2,
+    NBG_EXP_NANVAR = 3,
+    NBG_EXP_NANSTD = 4,
+    NBG_EXP_NANCOV = 5, /* two inputs */
+    NBG_EXP_NANCORR = 6 /* two inputs */
+} nbg_exp_op;
+
+/* numbagg/funcs.py:294-326 */
+typedef enum { NBG_FFILL = 0, NBG_BFILL = 1 } nbg_fill_dir;
+
+/* numbagg/grouped.py:7-270 */
+typedef enum {
+    NBG_GROUP_NANMEAN = 0,
+    NBG_GROUP_NANSUM = 1,
+    NBG_GROUP_NANCOUNT = 2,
+    NBG_GROUP_NANARGMAX = 3,
+    NBG_GROUP_NANARGMIN = 4,
+    NBG_GROUP_NANFIRST = 5,
+    NBG_GROUP_NANLAST = 6,
+    NBG_GROUP_NANPROD = 7,
+    NBG_GROUP_NANSUM_OF_SQUARES = 8,
+    NBG_GROUP_NANVAR = 9,
+    NBG_GROUP_NANSTD = 10,
+    NBG_GROUP_NANMIN = 11,
+    NBG_GROUP_NANMAX = 12,
+    NBG_GROUP_NANANY = 13,
+    NBG_GROUP_NANALL = 14
+} nbg_group_op;
+
+int nbg_abi_version(void);
+const char *nbg_last_error(void);
+/* Number of kernels this library has launched in the calling process (all families). */
+int64_t nbg_launch_count(void);
+
+/*
+ * Moving-window functions.  Replaces the gufunc loops "(a),(),()->(a)" /
+ * "(a),(a),(),()->(a)" built by ndmove (numbagg/decorators.py:275-341) over the bodies in
+ * numbagg/moving.py.  dtype: NBG_F32 | NBG_F64 (accumulation is always double, like the
+ * reference).  b: second input for COV/CORR, else NULL.  Requires 0 < window; min_count >= 0
+ * (the per-op max(min_count, 1|2) clamp of moving.py:18,127,158,193,232 is applied inside).
+ *
+ * Core-axis sharding (multi-GPU): when this call covers only positions [g0, g0+n) of a
+ * longer core axis, pass in a_halo/b_halo the `halo_len` elements that precede the shard
+ * (view (outer, halo_len, inner), normally halo_len = min(window, g0)); NULL / 0 otherwise.
+ */
+int nbg_move(int op, int dtype, const void *a, const void *b, void *out, int64_t outer,
+             int64_t n, int64_t inner, int64_t window, int64_t min_count, const void *a_halo,
+             const void *b_halo, int64_t halo_len, void *stream);
+
+/*
+ * Exponential moving functions.  Replaces the loops "(a),(a),()->(a)" /
+ * "(a),(a),(a),()->(a)" built by ndmoveexp (numbagg/decorators.py:344-414) over
+ * numbagg/moving_exp.py.  alpha: device array of the SAME dtype as the data, either 1-D of
+ * length n shared by every slice (alpha_nd == 0) or the full (outer, n, inner) view
+ * (alpha_nd == 1); alpha == NULL means the scalar `alpha_scalar` for every position
+ * (decorators.py:398-400 broadcasts it; here it costs no memory traffic).
+ *
+ * State exchange for core-axis sharding: NBG_EXP_STATE doubles per slice,
+ *   [0]=prod(decay) [1]=prod(decay^2) [2..9]=channel values [10]=seen-any-valid flag.
+ * carry_in  (nullable): state at the start of this shard (only [2..10] are read).
+ * agg_out   (nullable): this shard's aggregate computed from a ZERO carry; composing
+ *           aggregates left to right with s' = D*s + U gives the carry of the next shard.
+ * out may be NULL when only agg_out is wanted (aggregate-only pass, no output traffic).
+ */
+#define NBG_EXP_STATE 11
+int nbg_move_exp(int op, int dtype, const void *a1, const void *a2, const void *alpha,
+                 int alpha_nd, double alpha_scalar, double min_weight, void *out,
+                 int64_t outer, int64_t n, int64_t inner, const double *carry_in,
+                 double *agg_out, void *workspace, size_t workspace_bytes, void *stream);
+size_t nbg_move_exp_workspace_bytes(int op, int dtype, int64_t outer, int64_t n, int64_t inner);
+
+/*
+ * ffill / bfill.  Replaces the loop "(n),()->(n)" built by ndfill
+ * (numbagg/decorators.py:417-487) over numbagg/funcs.py:294-326.  itemsize: 4 or 8 bytes of
+ * an IEEE float dtype (integers have no NaN: the caller copies them).  limit >= 0.
+ * State exchange for core-axis sharding: NBG_FILL_STATE int64 words per slice,
+ *   [0]=has_valid [1]=raw bits of the last valid value [2]=distance from that value to the
+ *   end of the shard (= shard length when has_valid == 0).  Same carry_in / agg_out / out
+ *   rules as nbg_move_exp; for bfill "start" and "end" are mirrored.
+ */
+#define NBG_FILL_STATE 3
+int nbg_fill(int dir, int itemsize, const void *a, void *out, int64_t outer, int64_t n,
+             int64_t inner, int64_t limit, const int64_t *carry_in, int64_t *agg_out,
+             void *workspace, size_t workspace_bytes, void *stream);
+size_t nbg_fill_workspace_bytes(int itemsize, int64_t outer, int64_t n, int64_t inner);
+
+/*
+ * Grouped reductions.  Replaces the loops "(a..),(a..),(z)" / "(a..),(a..),(),(z)" built by
+ * groupndreduce (numbagg/decorators.py:490-674) over numbagg/grouped.py.  values is the
+ * (rows, n) C-contiguous matrix obtained after the dispatcher's moveaxis (decorators.py:639,
+ * 653) with the core dims flattened in C order; labels is (n,) shared by every row
+ * (labels_per_row == 0) or (rows, n); out is (rows, num_labels) in the values dtype.
+ * label < 0 or label >= num_labels => element skipped (the reference corrupts memory on
+ * the latter; we guard).  vdtype: any nbg_dtype (NANMEAN/NANVAR/NANSTD floats only -- the
+ * dispatcher casts integers to float64 first, decorators.py:613-619); ldtype: NBG_I32|I64.
+ *
+ * Three-step form for element-sharded inputs (multi-GPU): init -> accumulate (any number
+ * of shards, `index_offset` = flat index of the shard's first element) -> [caller combines
+ * workspaces across devices] -> finalize.  nbg_group() runs the three steps on one device.
+ * The workspace holds, per (row, label), NBG_GROUP_WS_CHANNELS 8-byte slots whose meaning
+ * is listed in DESIGN.md ("group workspace"); nbg_group_workspace_bytes() sizes it.
+ */
+#define NBG_GROUP_WS_CHANNELS 3
+size_t nbg_group_workspace_bytes(int op, int vdtype, int64_t rows, int64_t num_labels);
+int nbg_group_init(int op, int vdtype, void *workspace, int64_t rows, int64_t num_labels,
+                   void *stream);
+int nbg_group_accumulate(int op, int vdtype, int ldtype, const void *values,
+                         const void *labels, int labels_per_row, void *workspace, int64_t rows,
+                         int64_t n, int64_t num_labels, int64_t index_offset, void *stream);
+/* Merge workspace `other` (accumulated over LATER elements) into `accum`; order matters for
+ * first/last and for arg* ties.  Used to fold all-gathered per-device partials. */
+int nbg_group_combine(int op, int vdtype, void *accum, const void *other, int64_t rows,
+                      int64_t num_labels, void *stream);
+int nbg_group_finalize(int op, int vdtype, const void *workspace, void *out, int64_t rows,
+                       int64_t num_labels, int64_t ddof, void *stream);
+int nbg_group(int op, int vdtype, int ldtype, const void *values, const void *labels,
+              int labels_per_row, void *out, int64_t rows, int64_t n, int64_t num_labels,
+              int64_t ddof, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBG_B200_H */

@@ -1,0 +1,413 @@
+"""Host-side mirror of numbagg's dispatch decorators for the hot path.
+
+Same class names, call signatures (keyword-only scalars), defaults, validation order and
+exception types/messages as numbagg/decorators.py -- ``ndmove`` (:275-341), ``ndmoveexp``
+(:344-414), ``ndfill`` (:417-487), ``groupndreduce`` (:490-674) -- but instead of building a
+Numba gufunc each ``__call__`` hands device pointers to libnbg_b200.so (include/nbg_b200.h).
+There is no CPU path: numpy inputs are copied to the GPU and the result is copied back;
+CUDA ``torch.Tensor`` inputs are used in place and a CUDA tensor is returned.
+"""
+
+from __future__ import annotations
+
+import inspect
+import logging
+import math
+from typing import Any, Callable
+
+import numpy as np
+import torch
+
+from . import _device as dev
+from . import _lib
+
+logger = logging.getLogger(__name__)
+
+_F32 = np.dtype(np.float32)
+_F64 = np.dtype(np.float64)
+_NBG_DTYPE = {
+    _F32: _lib.NBG_F32,
+    _F64: _lib.NBG_F64,
+    np.dtype(np.int32): _lib.NBG_I32,
+    np.dtype(np.int64): _lib.NBG_I64,
+}
+
+
+def _float_loop_dtype(*dtypes: np.dtype) -> np.dtype:
+    """Loop selection NumPy performs over the (float32, float64) gufunc loops the reference
+    registers: float32/float16 -> float32 loop, anything else -> float64."""
+    dt = np.result_type(*dtypes)
+    return _F32 if dt in (_F32, np.dtype(np.float16)) else _F64
+
+
+def _is_int(x) -> bool:
+    return isinstance(x, (int, np.integer)) and not isinstance(x, (bool, np.bool_))
+
+
+def _wants_tensor(*xs) -> bool:
+    return any(dev.is_tensor(x) for x in xs)
+
+
+def _finish(result: torch.Tensor, as_tensor: bool, out=None):
+    """Return a tensor to tensor callers and a numpy array to numpy callers."""
+    if out is not None:
+        if dev.is_tensor(out):
+            out.copy_(result)
+            return out
+        return dev.to_host(result, out)
+    if as_tensor:
+        return result
+    return dev.to_host(result)
+
+
+class NumbaBase:
+    """Counterpart of numbagg.decorators.NumbaBase (:103-162): carries the function's
+    name/doc, ``repr`` and public signature.  ``target`` is always "cuda"."""
+
+    def __init__(self, name: str, doc: str | None = None) -> None:
+        self.__name__ = name
+        self.__qualname__ = name
+        self.__doc__ = doc
+        self.__signature__ = inspect.signature(self.__call__)
+        self.supports_parallel = True
+
+    def __repr__(self) -> str:
+        return f"numbagg.{self.__name__}"
+
+    @property
+    def target(self) -> str:
+        return "cuda"
+
+    def __call__(self, *args, **kwargs):
+        raise NotImplementedError
+
+
+# ------------------------------------------------------------------------------- moving
+def run_move(name: str, arrs: list[torch.Tensor], window: int, min_count: int, axis: int,
+             halos: list[torch.Tensor] | None = None) -> torch.Tensor:
+    """Device-level entry (CUDA tensors of one float dtype, same shape) -> CUDA tensor."""
+    view = dev.CoreView(arrs[0], axis)
+    ts = [view.t] + [view.like(a) for a in arrs[1:]]
+    out = torch.empty_like(view.t)
+    halo_len = 0
+    hs = [None, None]
+    if halos:
+        hv = [view.like(h) for h in halos]
+        halo_len = hv[0].shape[view.axis]
+        hs[: len(hv)] = hv
+    rc = _lib.lib().nbg_move(
+        _lib.MOVE_OPS[name], _NBG_DTYPE[dev.np_dtype_of(view.t)],
+        dev.ptr(ts[0]), dev.ptr(ts[1]) if len(ts) > 1 else None, dev.ptr(out),
+        view.outer, view.n, view.inner, int(window), int(min_count),
+        dev.ptr(hs[0]), dev.ptr(hs[1]), halo_len, dev.stream_ptr(),
+    )
+    _lib.check(rc, f"nbg_move({name})")
+    return view.restore(out)
+
+
+class ndmove(NumbaBase):
+    """N-dimensional moving-window function along one axis (numbagg ``ndmove``)."""
+
+    def __init__(self, name: str, n_inputs: int = 1, doc: str | None = None):
+        self.n_inputs = n_inputs
+        super().__init__(name, doc)
+
+    def __call__(self, *arr, window: int, min_count: int | None = None,
+                 axis: int | tuple[int, ...] = -1, **kwargs):
+        out = kwargs.pop("out", None)
+        if kwargs:
+            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        if len(arr) != self.n_inputs:
+            raise TypeError(f"{self.__name__}() takes {self.n_inputs} array argument(s), got {len(arr)}")
+        if min_count is None:
+            min_count = window
+        elif min_count < 0:
+            raise ValueError(f"min_count must be positive: {min_count}")
+        if isinstance(axis, tuple):
+            if axis == ():
+                if len(arr) > 1:
+                    raise ValueError(
+                        "`axis` cannot be an empty tuple when passing more than one array; since we default to returning the input."
+                    )
+                return arr[0]
+            elif len(axis) > 1:
+                raise ValueError(f"only one axis can be passed to {self.__name__}; got {axis}")
+            (axis,) = axis
+        as_tensor = _wants_tensor(*arr)
+        arr = tuple(a if dev.is_tensor(a) else np.asarray(a) for a in arr)
+        if not 0 < window <= arr[0].shape[axis]:
+            raise ValueError(f"window not in valid range: {window}")
+        if not _is_int(window) or not _is_int(min_count):
+            # NumPy refuses to cast a float window/min_count to the int64 loop operand
+            raise TypeError(f"window and min_count must be integers: {window!r}, {min_count!r}")
+        dt = _float_loop_dtype(*[dev.np_dtype_of(a) for a in arr])
+        ts = [dev.to_device(a, dt) for a in arr]
+        if len(ts) > 1 and any(t.shape != ts[0].shape for t in ts):
+            ts = [t.contiguous() for t in torch.broadcast_tensors(*ts)]
+        res = run_move(self.__name__, ts, window, min_count, axis)
+        return _finish(res, as_tensor, out)
+
+
+# --------------------------------------------------------------------------- exp moving
+def run_move_exp(name: str, arrs: list[torch.Tensor], alpha, min_weight: float, axis: int,
+                 carry_in: torch.Tensor | None = None, want_agg: bool = False,
+                 want_out: bool = True):
+    """Device-level entry.  `alpha`: python float (scalar path) or a CUDA tensor that is 1-D
+    of length n or has the data's shape.  Returns (out | None, agg | None)."""
+    view = dev.CoreView(arrs[0], axis)
+    ts = [view.t] + [view.like(a) for a in arrs[1:]]
+    alpha_t, alpha_nd, alpha_scalar = None, 0, 0.0
+    if dev.is_tensor(alpha):
+        if alpha.dim() <= 1:
+            alpha_t = alpha.contiguous()
+        else:
+            alpha_t, alpha_nd = view.like(alpha), 1
+    else:
+        alpha_scalar = float(alpha)
+    L = _lib.lib()
+    code = _lib.EXP_OPS[name]
+    dcode = _NBG_DTYPE[dev.np_dtype_of(view.t)]
+    out = torch.empty_like(view.t) if want_out else None
+    slices = view.outer * view.inner
+    agg = torch.empty((slices, _lib.NBG_EXP_STATE), dtype=torch.float64, device=view.t.device) if want_agg else None
+    ws_bytes = L.nbg_move_exp_workspace_bytes(code, dcode, view.outer, view.n, view.inner)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=view.t.device)
+    rc = L.nbg_move_exp(
+        code, dcode, dev.ptr(ts[0]), dev.ptr(ts[1]) if len(ts) > 1 else None, dev.ptr(alpha_t),
+        alpha_nd, alpha_scalar, float(min_weight), dev.ptr(out) if out is not None else None,
+        view.outer, view.n, view.inner, dev.ptr(carry_in), dev.ptr(agg), ws.data_ptr(), ws_bytes,
+        dev.stream_ptr(),
+    )
+    _lib.check(rc, f"nbg_move_exp({name})")
+    return (view.restore(out) if out is not None else None), agg
+
+
+class ndmoveexp(NumbaBase):
+    """Exponentially-weighted moving function (numbagg ``ndmoveexp``).  ``alpha`` is a
+    scalar, a 1-D array over the core axis, or an array with the data's shape."""
+
+    def __init__(self, name: str, n_inputs: int = 1, doc: str | None = None):
+        self.n_inputs = n_inputs
+        super().__init__(name, doc)
+
+    def __call__(self, *arr, alpha, min_weight: float = 0,
+                 axis: int | tuple[int, ...] = -1, **kwargs):
+        out = kwargs.pop("out", None)
+        if kwargs:
+            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        if len(arr) != self.n_inputs:
+            raise TypeError(f"{self.__name__}() takes {self.n_inputs} array argument(s), got {len(arr)}")
+        if isinstance(axis, tuple):
+            if axis == ():
+                if len(arr) > 1:
+                    raise ValueError(
+                        "`axis` cannot be an empty tuple when passing more than one array; since we default to returning the input."
+                    )
+                return arr[0]
+            if len(axis) > 1:
+                raise ValueError(f"Only one axis can be passed to {self.__name__}; got {axis}")
+            (axis,) = axis
+        as_tensor = _wants_tensor(*arr)
+        arr = tuple(a if dev.is_tensor(a) else np.asarray(a) for a in arr)
+        n = arr[0].shape[axis]
+        alpha_is_array = isinstance(alpha, np.ndarray) or dev.is_tensor(alpha)
+        if alpha_is_array:
+            alpha_dtype = dev.np_dtype_of(alpha)
+            if alpha.ndim == 0:
+                alpha_is_array = False
+                alpha = alpha.item() if alpha_dtype != _F32 else np.float32(alpha.item())
+        if not alpha_is_array:
+            # np.broadcast_to(alpha, n) in the reference: the scalar's own dtype takes part in
+            # loop selection (python float -> float64, np.float32 -> float32)
+            alpha_dtype = np.asarray(alpha).dtype
+        dt = _float_loop_dtype(*[dev.np_dtype_of(a) for a in arr], alpha_dtype)
+        ts = [dev.to_device(a, dt) for a in arr]
+        if len(ts) > 1 and any(t.shape != ts[0].shape for t in ts):
+            ts = [t.contiguous() for t in torch.broadcast_tensors(*ts)]
+        if alpha_is_array:
+            if alpha.ndim == 1:
+                if alpha.shape[0] != n:
+                    raise ValueError(
+                        f"alpha has length {alpha.shape[0]} but the core axis has length {n}"
+                    )
+                alpha_dev = dev.to_device(alpha, dt)
+            else:
+                alpha_dev = dev.to_device(alpha, dt)
+                if alpha_dev.shape != ts[0].shape:
+                    alpha_dev = alpha_dev.broadcast_to(ts[0].shape).contiguous()
+        else:
+            # the loop sees alpha rounded to the loop dtype
+            alpha_dev = float(np.float32(alpha)) if dt == _F32 else float(alpha)
+        mw = float(np.float32(min_weight)) if dt == _F32 else float(min_weight)
+        res, _ = run_move_exp(self.__name__, ts, alpha_dev, mw, axis)
+        return _finish(res, as_tensor, out)
+
+
+# -------------------------------------------------------------------------------- fills
+def run_fill(name: str, t: torch.Tensor, limit: int, axis: int,
+             carry_in: torch.Tensor | None = None, want_agg: bool = False, want_out: bool = True):
+    """Device-level entry for ffill/bfill on a float32/float64 CUDA tensor."""
+    view = dev.CoreView(t, axis)
+    L = _lib.lib()
+    itemsize = view.t.element_size()
+    out = torch.empty_like(view.t) if want_out else None
+    slices = view.outer * view.inner
+    agg = torch.empty((slices, _lib.NBG_FILL_STATE), dtype=torch.int64, device=t.device) if want_agg else None
+    ws_bytes = L.nbg_fill_workspace_bytes(itemsize, view.outer, view.n, view.inner)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=t.device)
+    rc = L.nbg_fill(
+        _lib.FILL_DIRS[name], itemsize, dev.ptr(view.t), dev.ptr(out) if out is not None else None,
+        view.outer, view.n, view.inner, int(limit), dev.ptr(carry_in), dev.ptr(agg),
+        ws.data_ptr(), ws_bytes, dev.stream_ptr(),
+    )
+    _lib.check(rc, f"nbg_fill({name})")
+    return (view.restore(out) if out is not None else None), agg
+
+
+class ndfill(NumbaBase):
+    """Forward/backward fill along one axis (numbagg ``ndfill``)."""
+
+    def __call__(self, arr, *, limit: None | int = None, axis: int = -1, **kwargs):
+        out = kwargs.pop("out", None)
+        if kwargs:
+            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        as_tensor = dev.is_tensor(arr)
+        if not as_tensor:
+            arr = np.asarray(arr)
+        if limit is None:
+            limit = arr.shape[axis]
+        if limit < 0:
+            raise ValueError(f"`limit` must be positive: {limit}")
+        dt = dev.np_dtype_of(arr)
+        if not np.issubdtype(dt, np.number):
+            raise TypeError(f"Unsupported dtype for fill operation: {dt}")
+        if dt.kind in "iu":
+            # np.isnan is constant-false for integers (funcs.py:303,319): the loop is a copy
+            res = arr.clone() if as_tensor else arr.copy()
+            if out is not None:
+                out[...] = res
+                return out
+            return res
+        if dt.kind == "c":
+            raise TypeError(f"Unsupported dtype for fill operation: {dt}")
+        work = _F32 if dt == np.dtype(np.float16) else dt  # float16 <-> float32 is exact
+        t = dev.to_device(arr, work)
+        if t.dim() == 0:
+            raise ValueError("ffill/bfill need at least one dimension")
+        res, _ = run_fill(self.__name__, t, limit, axis)
+        if work != dt:
+            res = res.to(dev._NP_TO_TORCH[dt])
+        return _finish(res, as_tensor, out)
+
+
+# ------------------------------------------------------------------------------ grouped
+def run_group(name: str, values: torch.Tensor, labels: torch.Tensor, num_labels: int, ddof: int,
+              labels_per_row: bool = False) -> torch.Tensor:
+    """Device-level entry: values (rows, n) contiguous, labels (n,) or (rows, n), both CUDA;
+    values dtype in {f32, f64, i32, i64}, labels in {i32, i64} -> (rows, num_labels)."""
+    L = _lib.lib()
+    code = _lib.GROUP_OPS[name]
+    vcode = _NBG_DTYPE[dev.np_dtype_of(values)]
+    lcode = _NBG_DTYPE[dev.np_dtype_of(labels)]
+    rows, n = values.shape
+    out = torch.empty((rows, num_labels), dtype=values.dtype, device=values.device)
+    ws_bytes = L.nbg_group_workspace_bytes(code, vcode, rows, num_labels)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=values.device)
+    rc = L.nbg_group(
+        code, vcode, lcode, dev.ptr(values), dev.ptr(labels), int(labels_per_row), dev.ptr(out),
+        rows, n, int(num_labels), int(ddof), ws.data_ptr(), ws_bytes, dev.stream_ptr(),
+    )
+    _lib.check(rc, f"nbg_group({name})")
+    return out
+
+
+class groupndreduce(NumbaBase):
+    """N-dimensional grouped aggregation (numbagg ``groupndreduce``): ``axis=int`` (labels
+    1-D along that axis), ``axis=tuple`` (labels shaped like those axes) or ``axis=None``
+    (labels shaped like values).  The group axis is the LAST axis of the result."""
+
+    def __init__(self, name: str, *, supports_ddof: bool = False, supports_bool: bool = True,
+                 supports_ints: bool = True, doc: str | None = None) -> None:
+        self.supports_bool = supports_bool
+        self.supports_ints = supports_ints
+        self.supports_ddof = supports_ddof
+        super().__init__(name, doc)
+
+    def __call__(self, values, labels, *, ddof: int = 1, num_labels: int | None = None,
+                 axis: int | tuple[int, ...] | None = None):
+        as_tensor = _wants_tensor(values, labels)
+        if not dev.is_tensor(values):
+            values = np.asarray(values)
+        if not dev.is_tensor(labels):
+            labels = np.asarray(labels)
+        vdt = dev.np_dtype_of(values)
+        ldt = dev.np_dtype_of(labels)
+        if ldt.kind not in "i":
+            raise TypeError(
+                "labels must be an integer array; it's expected to have already been factorized with a function such as `pd.factorize`"
+            )
+        vsize = math.prod(values.shape)
+        # The reference widens labels so that a per-group count cannot overflow
+        # (decorators.py:581-596).  Counts here are always 64-bit; labels only need a dtype
+        # the kernels read (int32/int64).
+        if vdt == np.bool_:
+            if not self.supports_bool:
+                raise TypeError(
+                    f"{self.__name__} does not support boolean input. Convert to a numeric type first."
+                )
+            vdt = np.dtype(np.int32)
+        if num_labels is None:
+            # `int` so that a label at the dtype's maximum doesn't overflow the add.
+            num_labels = int(labels.max()) + 1
+        if not self.supports_ints and np.issubdtype(vdt, np.integer):
+            work_dt = result_dt = _F64
+        else:
+            result_dt = vdt
+            if vdt in _NBG_DTYPE:
+                work_dt = vdt
+            elif vdt.kind in "iu":
+                work_dt = np.dtype(np.int64)  # narrow ints: wrap back to result_dt at the end
+            elif vdt == np.dtype(np.float16):
+                work_dt = result_dt = _F32
+            else:
+                raise TypeError(f"unsupported values dtype {vdt}")
+
+        vshape = tuple(values.shape)
+        lshape = tuple(labels.shape)
+        nd = len(vshape)
+        if axis is None:
+            if vshape != lshape:
+                raise ValueError(
+                    "axis required if values and labels have different "
+                    f"shapes: {vshape} vs {lshape}"
+                )
+            core_axes = tuple(range(nd))
+        elif isinstance(axis, (int, np.integer)):
+            if lshape != (vshape[axis],):
+                raise ValueError(
+                    "values must have same shape along axis as labels: "
+                    f"{(vshape[axis],)} vs {lshape}"
+                )
+            core_axes = (int(axis) % nd,)
+        else:
+            values_shape = tuple(vshape[ax] for ax in axis)
+            if lshape != values_shape:
+                raise ValueError(
+                    "values must have same shape along axis as labels: "
+                    f"{values_shape} vs {lshape}"
+                )
+            core_axes = tuple(int(ax) % nd for ax in axis)
+
+        v = dev.to_device(values, work_dt)
+        lab = dev.to_device(labels, np.dtype(np.int64) if ldt.itemsize > 4 else np.dtype(np.int32))
+        if len(core_axes) and core_axes != tuple(range(nd - len(core_axes), nd)):
+            v = torch.movedim(v, core_axes, tuple(range(nd - len(core_axes), nd)))
+        bshape = tuple(v.shape[: nd - len(core_axes)])
+        n = math.prod(v.shape[nd - len(core_axes):])
+        v2 = v.reshape(-1, n) if v.is_contiguous() else v.contiguous().reshape(-1, n)
+        res = run_group(self.__name__, v2, lab.reshape(-1).contiguous(), num_labels,
+                        ddof if self.supports_ddof else 1)
+        res = res.reshape(bshape + (num_labels,))
+        if work_dt != result_dt:
+            res = res.to(dev._NP_TO_TORCH[result_dt])
+        return _finish(res, as_tensor)
