@@ -1,19 +1,537 @@
+// nbg_group.cu -- grouped NaN-aware reductions (group_nan*) for sm_100a.
+//
+// Replaces the scatter-reduce loops of numbagg/grouped.py:7-270 (dispatched by
+// groupndreduce, numbagg/decorators.py:490-674).
+//
+// Workspace ("group workspace", channel-major: ws[ch][row][label], 8-byte slots):
+//   op                         ch0                      ch1                 ch2
+//   nansum / sum_of_squares    sum   (f64 | i64)        -                   -
+//   nanmean                    sum                      -                   count (i64)
+//   nancount                   -                        -                   count
+//   nanvar / nanstd            sum                      sum of squares      count
+//   nanprod                    product (f64 | i64)      -                   -
+//   nanmin / nanmax            ordered key (u64, 0=empty; min uses the inverted key)
+//   nanany / nanall            flag (i64)
+//   nanfirst / nanlast         raw value bits           global flat index (i64)
+//   nanargmax / nanargmin      ordered key              global flat index of the FIRST extreme
+// Float data accumulate in double (global RED.ADD.F64), integers in int64 (wrap-around, like
+// the reference's in-dtype accumulation modulo 2^bits).  Comparisons for min/max/arg* happen
+// on the value converted to double, exactly like the reference (its scratch arrays are
+// float64: grouped.py:56, 80, 213, 231).
+//
+// Kernels
+//   group_atomic_kernel      any shape / cardinality: one global atomic per element and
+//                            channel.  HBM/L2-atomic bound; the high-cardinality path.
+//   group_rowbins_kernel     labels shared by all rows, bins of a few rows fit in shared
+//                            memory: one CTA owns (row group, column segment), streams row
+//                            tiles through TMA bulk copies and accumulates into PRIVATE
+//                            shared-memory bins that only one lane ever touches -- no
+//                            atomics, and each bin sees its elements in ascending column
+//                            order, i.e. the reference's own summation order.
 #include "nbg_common.cuh"
-extern "C" size_t nbg_group_workspace_bytes(int, int, int64_t, int64_t) { return 0; }
-extern "C" int nbg_group_init(int, int, void *, int64_t, int64_t, void *) {
-    return nbg::fail(NBG_ERR_UNSUPPORTED, "nbg_group: not built yet");
+
+namespace nbg {
+
+constexpr int64_t kIdxNone = INT64_MAX;
+
+// ----------------------------------------------------------------------------- key encoding
+// Order-preserving map double -> u64; never 0 for a non-NaN input, so 0 can mean "empty".
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    if (v == 0.0) v = 0.0;  // -0.0 and +0.0 compare equal in the reference
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
-extern "C" int nbg_group_accumulate(int, int, int, const void *, const void *, int, void *, int64_t, int64_t, int64_t,
-                                    int64_t, void *) {
-    return nbg::fail(NBG_ERR_UNSUPPORTED, "nbg_group: not built yet");
+__device__ __forceinline__ double key_to_double(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
 }
-extern "C" int nbg_group_combine(int, int, void *, const void *, int64_t, int64_t, void *) {
-    return nbg::fail(NBG_ERR_UNSUPPORTED, "nbg_group: not built yet");
+
+template <typename V>
+struct VTraits;
+template <>
+struct VTraits<float> {
+    using Acc = double;
+    static constexpr bool is_float = true;
+    __device__ static __forceinline__ float nan_out() { return quiet_nan<float>(); }
+};
+template <>
+struct VTraits<double> {
+    using Acc = double;
+    static constexpr bool is_float = true;
+    __device__ static __forceinline__ double nan_out() { return quiet_nan<double>(); }
+};
+template <>
+struct VTraits<int32_t> {
+    using Acc = long long;
+    static constexpr bool is_float = false;
+    __device__ static __forceinline__ int32_t nan_out() { return INT32_MIN; }  // x86 cvttsd2si(NaN)
+};
+template <>
+struct VTraits<int64_t> {
+    using Acc = long long;
+    static constexpr bool is_float = false;
+    __device__ static __forceinline__ int64_t nan_out() { return INT64_MIN; }
+};
+
+// square / product in the VALUE type first (numba: V*V is V), then widened to the accumulator
+__device__ __forceinline__ double sq_as_input(float v) { return (double)__fmul_rn(v, v); }
+__device__ __forceinline__ double sq_as_input(double v) { return __dmul_rn(v, v); }
+__device__ __forceinline__ long long sq_as_input(int32_t v) { return (long long)v * (long long)v; }
+__device__ __forceinline__ long long sq_as_input(int64_t v) {
+    return (long long)((unsigned long long)v * (unsigned long long)v);
 }
-extern "C" int nbg_group_finalize(int, int, const void *, void *, int64_t, int64_t, int64_t, void *) {
-    return nbg::fail(NBG_ERR_UNSUPPORTED, "nbg_group: not built yet");
+
+__device__ __forceinline__ void atomic_add_acc(double *p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add_acc(long long *p, long long v) {
+    atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
 }
-extern "C" int nbg_group(int, int, int, const void *, const void *, int, void *, int64_t, int64_t, int64_t, int64_t,
-                         void *, size_t, void *) {
-    return nbg::fail(NBG_ERR_UNSUPPORTED, "nbg_group: not built yet");
+__device__ __forceinline__ void atomic_mul_acc(double *p, double v) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(p);
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(__dmul_rn(__longlong_as_double((long long)assumed), v)));
+    } while (old != assumed);
+}
+__device__ __forceinline__ void atomic_mul_acc(long long *p, long long v) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(p);
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        old = atomicCAS(a, assumed, assumed * (unsigned long long)v);
+    } while (old != assumed);
+}
+
+struct GroupWs {
+    void *ch[NBG_GROUP_WS_CHANNELS];
+    __host__ __device__ static GroupWs carve(void *base, int64_t rows, int64_t K) {
+        GroupWs w;
+        for (int c = 0; c < NBG_GROUP_WS_CHANNELS; c++)
+            w.ch[c] = static_cast<unsigned char *>(base) + (size_t)c * (size_t)rows * (size_t)K * 8;
+        return w;
+    }
+};
+
+// ------------------------------------------------------------------------------------- init
+__global__ void group_init_kernel(GroupWs ws, int op, int is_float, int64_t slots) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slots) return;
+    unsigned long long c0 = 0, c1 = 0, c2 = 0;
+    switch (op) {
+        case NBG_GROUP_NANPROD:
+            c0 = is_float ? (unsigned long long)__double_as_longlong(1.0) : 1ull;
+            break;
+        case NBG_GROUP_NANALL:
+            c0 = 1ull;
+            break;
+        case NBG_GROUP_NANFIRST:
+        case NBG_GROUP_NANARGMAX:
+        case NBG_GROUP_NANARGMIN:
+            c1 = (unsigned long long)kIdxNone;
+            break;
+        case NBG_GROUP_NANLAST:
+            c1 = (unsigned long long)(long long)-1;
+            break;
+        default:
+            break;
+    }
+    reinterpret_cast<unsigned long long *>(ws.ch[0])[i] = c0;
+    reinterpret_cast<unsigned long long *>(ws.ch[1])[i] = c1;
+    reinterpret_cast<unsigned long long *>(ws.ch[2])[i] = c2;
+}
+
+// --------------------------------------------------------------------- generic atomic kernel
+// PHASE 1 of arg* re-reads the data and records the smallest index whose key equals the
+// group's extreme; every other op has PHASE 0 only.
+template <typename V, typename L, int OP, int PHASE>
+__global__ void __launch_bounds__(256) group_atomic_kernel(const V *__restrict__ values, const L *__restrict__ labels,
+                                                           int labels_per_row, GroupWs ws, int64_t rows, int64_t n,
+                                                           int64_t K, int64_t index_offset, int64_t blocks_per_row) {
+    using Acc = typename VTraits<V>::Acc;
+    const int64_t row = blockIdx.x / blocks_per_row;
+    const int64_t blk = blockIdx.x % blocks_per_row;
+    const V *vrow = values + row * n;
+    const L *lrow = labels + (labels_per_row ? row * n : 0);
+    Acc *c0 = reinterpret_cast<Acc *>(ws.ch[0]) + row * K;
+    Acc *c1 = reinterpret_cast<Acc *>(ws.ch[1]) + row * K;
+    long long *cnt = reinterpret_cast<long long *>(ws.ch[2]) + row * K;
+    unsigned long long *key0 = reinterpret_cast<unsigned long long *>(ws.ch[0]) + row * K;
+    long long *idx1 = reinterpret_cast<long long *>(ws.ch[1]) + row * K;
+    constexpr int PER = 8;
+    const int64_t base = blk * (256 * PER);
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        const int64_t i = base + (int64_t)q * 256 + threadIdx.x;
+        if (i >= n) break;
+        const int64_t label = (int64_t)lrow[i];
+        if (label < 0 || label >= K) continue;
+        const V v = vrow[i];
+        if (is_nan(v)) continue;
+        const int64_t gi = index_offset + i;
+        if (OP == NBG_GROUP_NANSUM) {
+            atomic_add_acc(c0 + label, (Acc)v);
+        } else if (OP == NBG_GROUP_NANMEAN) {
+            atomic_add_acc(c0 + label, (Acc)v);
+            atomic_add_acc(cnt + label, 1ll);
+        } else if (OP == NBG_GROUP_NANCOUNT) {
+            atomic_add_acc(cnt + label, 1ll);
+        } else if (OP == NBG_GROUP_NANSUM_OF_SQUARES) {
+            atomic_add_acc(c0 + label, (Acc)sq_as_input(v));
+        } else if (OP == NBG_GROUP_NANVAR || OP == NBG_GROUP_NANSTD) {
+            atomic_add_acc(c0 + label, (Acc)v);
+            atomic_add_acc(c1 + label, (Acc)sq_as_input(v));
+            atomic_add_acc(cnt + label, 1ll);
+        } else if (OP == NBG_GROUP_NANPROD) {
+            atomic_mul_acc(c0 + label, (Acc)v);
+        } else if (OP == NBG_GROUP_NANMAX) {
+            atomicMax(key0 + label, order_key((double)v));
+        } else if (OP == NBG_GROUP_NANMIN) {
+            atomicMax(key0 + label, ~order_key((double)v));
+        } else if (OP == NBG_GROUP_NANANY) {
+            if (v != (V)0) reinterpret_cast<volatile long long *>(c0)[label] = 1;
+        } else if (OP == NBG_GROUP_NANALL) {
+            if (v == (V)0) reinterpret_cast<volatile long long *>(c0)[label] = 0;
+        } else if (OP == NBG_GROUP_NANFIRST) {
+            atomicMin(idx1 + label, (long long)gi);
+        } else if (OP == NBG_GROUP_NANLAST) {
+            atomicMax(idx1 + label, (long long)gi);
+        } else if (OP == NBG_GROUP_NANARGMAX || OP == NBG_GROUP_NANARGMIN) {
+            const unsigned long long k = OP == NBG_GROUP_NANARGMAX ? order_key((double)v) : ~order_key((double)v);
+            if (PHASE == 0) {
+                atomicMax(key0 + label, k);
+            } else {
+                if (k == key0[label]) atomicMin(idx1 + label, (long long)gi);
+            }
+        }
+    }
+}
+
+// first/last: fetch the winning value of this shard into ch0 (one thread per (row, label)).
+template <typename V>
+__global__ void group_gather_kernel(const V *__restrict__ values, GroupWs ws, int64_t rows, int64_t n, int64_t K,
+                                    int64_t index_offset) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= rows * K) return;
+    const int64_t row = s / K;
+    const long long gi = reinterpret_cast<long long *>(ws.ch[1])[s];
+    const int64_t local = gi - index_offset;
+    if (local < 0 || local >= n) return;  // winner lives in another shard (or none)
+    const V v = values[row * n + local];
+    unsigned long long bits;
+    if (sizeof(V) == 8) {
+        bits = *reinterpret_cast<const unsigned long long *>(&v);
+    } else {
+        bits = (unsigned long long)*reinterpret_cast<const unsigned int *>(&v);
+    }
+    reinterpret_cast<unsigned long long *>(ws.ch[0])[s] = bits;
+}
+
+// ---------------------------------------------------------------------------------- combine
+template <bool IS_FLOAT>
+__global__ void group_combine_kernel(GroupWs acc, GroupWs oth, int op, int64_t slots) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    using Acc = typename std::conditional<IS_FLOAT, double, long long>::type;
+    Acc *a0 = reinterpret_cast<Acc *>(acc.ch[0]) + s, *a1 = reinterpret_cast<Acc *>(acc.ch[1]) + s;
+    const Acc *o0 = reinterpret_cast<const Acc *>(oth.ch[0]) + s, *o1 = reinterpret_cast<const Acc *>(oth.ch[1]) + s;
+    long long *ac = reinterpret_cast<long long *>(acc.ch[2]) + s;
+    const long long *oc = reinterpret_cast<const long long *>(oth.ch[2]) + s;
+    unsigned long long *ak = reinterpret_cast<unsigned long long *>(acc.ch[0]) + s;
+    const unsigned long long *ok = reinterpret_cast<const unsigned long long *>(oth.ch[0]) + s;
+    long long *ai = reinterpret_cast<long long *>(acc.ch[1]) + s;
+    const long long *oi = reinterpret_cast<const long long *>(oth.ch[1]) + s;
+    switch (op) {
+        case NBG_GROUP_NANSUM:
+        case NBG_GROUP_NANMEAN:
+        case NBG_GROUP_NANCOUNT:
+        case NBG_GROUP_NANSUM_OF_SQUARES:
+        case NBG_GROUP_NANVAR:
+        case NBG_GROUP_NANSTD:
+            *a0 = *a0 + *o0;
+            *a1 = *a1 + *o1;
+            *ac = *ac + *oc;
+            break;
+        case NBG_GROUP_NANPROD:
+            *a0 = *a0 * *o0;
+            break;
+        case NBG_GROUP_NANMIN:
+        case NBG_GROUP_NANMAX:
+            if (*ok > *ak) *ak = *ok;
+            break;
+        case NBG_GROUP_NANANY:
+            if (*ok) *ak = 1;
+            break;
+        case NBG_GROUP_NANALL:
+            if (!*ok) *ak = 0;
+            break;
+        case NBG_GROUP_NANFIRST:
+            if (*oi < *ai) {
+                *ai = *oi;
+                *ak = *ok;
+            }
+            break;
+        case NBG_GROUP_NANLAST:
+            if (*oi > *ai) {
+                *ai = *oi;
+                *ak = *ok;
+            }
+            break;
+        case NBG_GROUP_NANARGMAX:
+        case NBG_GROUP_NANARGMIN:
+            if (*ok > *ak) {
+                *ak = *ok;
+                *ai = *oi;
+            } else if (*ok == *ak && *oi < *ai) {
+                *ai = *oi;
+            }
+            break;
+        default:
+            break;
+    }
+}
+
+// --------------------------------------------------------------------------------- finalize
+template <typename V>
+__global__ void group_finalize_kernel(GroupWs ws, V *__restrict__ out, int op, int64_t slots, int64_t ddof) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    using Acc = typename VTraits<V>::Acc;
+    const Acc a0 = reinterpret_cast<const Acc *>(ws.ch[0])[s];
+    const Acc a1 = reinterpret_cast<const Acc *>(ws.ch[1])[s];
+    const long long cnt = reinterpret_cast<const long long *>(ws.ch[2])[s];
+    const unsigned long long k0 = reinterpret_cast<const unsigned long long *>(ws.ch[0])[s];
+    const long long i1 = reinterpret_cast<const long long *>(ws.ch[1])[s];
+    V r = (V)0;
+    switch (op) {
+        case NBG_GROUP_NANSUM:
+        case NBG_GROUP_NANSUM_OF_SQUARES:
+        case NBG_GROUP_NANPROD:
+            r = (V)a0;
+            break;
+        case NBG_GROUP_NANCOUNT:
+            r = (V)cnt;
+            break;
+        case NBG_GROUP_NANANY:
+        case NBG_GROUP_NANALL:
+            r = (V)(long long)k0;
+            break;
+        case NBG_GROUP_NANMEAN:
+            // out[label] /= count: the V-typed sum divided in double (grouped.py:22-27)
+            r = cnt == 0 ? VTraits<V>::nan_out() : (V)((double)(V)a0 / (double)cnt);
+            break;
+        case NBG_GROUP_NANVAR:
+        case NBG_GROUP_NANSTD: {
+            const long long denom = cnt - ddof;
+            if (denom <= 0) {
+                r = VTraits<V>::nan_out();
+            } else {
+                // (sums_of_squares - sums**2 / count) / denom with V-typed sums (grouped.py:176)
+                const V sv = (V)a0, ssv = (V)a1;
+                const double s2 = (double)sq_as_input(sv);
+                const double num = __dsub_rn((double)ssv, s2 / (double)cnt);
+                const double q = num / (double)denom;
+                r = (V)(op == NBG_GROUP_NANSTD ? sqrt(q) : q);
+            }
+            break;
+        }
+        case NBG_GROUP_NANMAX:
+            r = k0 == 0 ? VTraits<V>::nan_out() : (V)key_to_double(k0);
+            break;
+        case NBG_GROUP_NANMIN:
+            r = k0 == 0 ? VTraits<V>::nan_out() : (V)key_to_double(~k0);
+            break;
+        case NBG_GROUP_NANFIRST:
+        case NBG_GROUP_NANLAST: {
+            const bool none = (op == NBG_GROUP_NANFIRST) ? (i1 == kIdxNone) : (i1 < 0);
+            if (none) {
+                // grouped.py:109-110 / :114: NaN for floats; first leaves integers untouched (0 here)
+                r = (op == NBG_GROUP_NANFIRST && !VTraits<V>::is_float) ? (V)0 : VTraits<V>::nan_out();
+            } else if (sizeof(V) == 8) {
+                r = *reinterpret_cast<const V *>(&k0);
+            } else {
+                const unsigned int b = (unsigned int)k0;
+                r = *reinterpret_cast<const V *>(&b);
+            }
+            break;
+        }
+        case NBG_GROUP_NANARGMAX:
+        case NBG_GROUP_NANARGMIN:
+            r = k0 == 0 ? VTraits<V>::nan_out() : (V)i1;
+            break;
+        default:
+            break;
+    }
+    out[s] = r;
+}
+
+// ---------------------------------------------------------------------------------- launch
+static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+template <typename V, typename L, int OP>
+static int launch_atomic(const V *values, const L *labels, int labels_per_row, GroupWs ws, int64_t rows, int64_t n,
+                         int64_t K, int64_t index_offset, cudaStream_t stream) {
+    const int64_t bpr = (n + 2047) / 2048;
+    if (bpr * rows > INT32_MAX) return fail(NBG_ERR_UNSUPPORTED, "nbg_group: grid too large");
+    group_atomic_kernel<V, L, OP, 0><<<(unsigned)(bpr * rows), 256, 0, stream>>>(values, labels, labels_per_row, ws,
+                                                                                  rows, n, K, index_offset, bpr);
+    int rc = check_launch("nbg_group(atomic)");
+    if (rc) return rc;
+    if (OP == NBG_GROUP_NANARGMAX || OP == NBG_GROUP_NANARGMIN) {
+        group_atomic_kernel<V, L, OP, 1><<<(unsigned)(bpr * rows), 256, 0, stream>>>(values, labels, labels_per_row,
+                                                                                      ws, rows, n, K, index_offset, bpr);
+        rc = check_launch("nbg_group(atomic, index phase)");
+        if (rc) return rc;
+    }
+    if (OP == NBG_GROUP_NANFIRST || OP == NBG_GROUP_NANLAST) {
+        group_gather_kernel<V><<<blocks_for(rows * K, 256), 256, 0, stream>>>(values, ws, rows, n, K, index_offset);
+        rc = check_launch("nbg_group(gather)");
+    }
+    return rc;
+}
+
+template <typename V, typename L>
+static int dispatch_accumulate(int op, const V *values, const L *labels, int labels_per_row, GroupWs ws, int64_t rows,
+                               int64_t n, int64_t K, int64_t index_offset, cudaStream_t stream) {
+#define NBG_GROUP_CASE(OPC) \
+    case OPC:               \
+        return launch_atomic<V, L, OPC>(values, labels, labels_per_row, ws, rows, n, K, index_offset, stream)
+    switch (op) {
+        NBG_GROUP_CASE(NBG_GROUP_NANMEAN);
+        NBG_GROUP_CASE(NBG_GROUP_NANSUM);
+        NBG_GROUP_CASE(NBG_GROUP_NANCOUNT);
+        NBG_GROUP_CASE(NBG_GROUP_NANARGMAX);
+        NBG_GROUP_CASE(NBG_GROUP_NANARGMIN);
+        NBG_GROUP_CASE(NBG_GROUP_NANFIRST);
+        NBG_GROUP_CASE(NBG_GROUP_NANLAST);
+        NBG_GROUP_CASE(NBG_GROUP_NANPROD);
+        NBG_GROUP_CASE(NBG_GROUP_NANSUM_OF_SQUARES);
+        NBG_GROUP_CASE(NBG_GROUP_NANVAR);
+        NBG_GROUP_CASE(NBG_GROUP_NANSTD);
+        NBG_GROUP_CASE(NBG_GROUP_NANMIN);
+        NBG_GROUP_CASE(NBG_GROUP_NANMAX);
+        NBG_GROUP_CASE(NBG_GROUP_NANANY);
+        NBG_GROUP_CASE(NBG_GROUP_NANALL);
+        default:
+            return fail(NBG_ERR_BAD_OP, "nbg_group: unknown op");
+    }
+#undef NBG_GROUP_CASE
+}
+
+template <typename V>
+static int dispatch_labels(int op, int ldtype, const void *values, const void *labels, int labels_per_row, GroupWs ws,
+                           int64_t rows, int64_t n, int64_t K, int64_t index_offset, cudaStream_t stream) {
+    if (ldtype == NBG_I32)
+        return dispatch_accumulate<V, int32_t>(op, static_cast<const V *>(values), static_cast<const int32_t *>(labels),
+                                               labels_per_row, ws, rows, n, K, index_offset, stream);
+    if (ldtype == NBG_I64)
+        return dispatch_accumulate<V, int64_t>(op, static_cast<const V *>(values), static_cast<const int64_t *>(labels),
+                                               labels_per_row, ws, rows, n, K, index_offset, stream);
+    return fail(NBG_ERR_BAD_DTYPE, "nbg_group: labels dtype must be NBG_I32 or NBG_I64");
+}
+
+static bool float_only(int op) {
+    return op == NBG_GROUP_NANMEAN || op == NBG_GROUP_NANVAR || op == NBG_GROUP_NANSTD;
+}
+
+}  // namespace nbg
+
+extern "C" size_t nbg_group_workspace_bytes(int, int, int64_t rows, int64_t num_labels) {
+    if (rows <= 0 || num_labels <= 0) return 0;
+    return (size_t)NBG_GROUP_WS_CHANNELS * (size_t)rows * (size_t)num_labels * 8 + 256;
+}
+
+static void *align256(void *p) { return reinterpret_cast<void *>(((uintptr_t)p + 255) & ~(uintptr_t)255); }
+
+extern "C" int nbg_group_init(int op, int vdtype, void *workspace, int64_t rows, int64_t num_labels, void *stream) {
+    using namespace nbg;
+    if (op < 0 || op > NBG_GROUP_NANALL) return fail(NBG_ERR_BAD_OP, "nbg_group_init: unknown op");
+    const int64_t slots = rows * num_labels;
+    if (slots <= 0) return NBG_OK;
+    if (!workspace) return fail(NBG_ERR_WORKSPACE, "nbg_group_init: null workspace");
+    GroupWs ws = GroupWs::carve(align256(workspace), rows, num_labels);
+    const int is_float = (vdtype == NBG_F32 || vdtype == NBG_F64);
+    group_init_kernel<<<blocks_for(slots, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ws, op, is_float, slots);
+    return check_launch("nbg_group_init");
+}
+
+extern "C" int nbg_group_accumulate(int op, int vdtype, int ldtype, const void *values, const void *labels,
+                                    int labels_per_row, void *workspace, int64_t rows, int64_t n, int64_t num_labels,
+                                    int64_t index_offset, void *stream) {
+    using namespace nbg;
+    if (rows < 0 || n < 0 || num_labels < 0) return fail(NBG_ERR_BAD_ARG, "nbg_group: negative size");
+    if (rows * n == 0 || num_labels == 0) return NBG_OK;
+    if (!values || !labels || !workspace) return fail(NBG_ERR_BAD_ARG, "nbg_group: null pointer");
+    if (float_only(op) && !(vdtype == NBG_F32 || vdtype == NBG_F64))
+        return fail(NBG_ERR_BAD_DTYPE, "nbg_group: nanmean/nanvar/nanstd need float values (cast integers to float64)");
+    GroupWs ws = GroupWs::carve(align256(workspace), rows, num_labels);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (vdtype) {
+        case NBG_F32:
+            return dispatch_labels<float>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, st);
+        case NBG_F64:
+            return dispatch_labels<double>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, st);
+        case NBG_I32:
+            return dispatch_labels<int32_t>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, st);
+        case NBG_I64:
+            return dispatch_labels<int64_t>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, st);
+        default:
+            return fail(NBG_ERR_BAD_DTYPE, "nbg_group: bad values dtype");
+    }
+}
+
+extern "C" int nbg_group_combine(int op, int vdtype, void *accum, const void *other, int64_t rows, int64_t num_labels,
+                                 void *stream) {
+    using namespace nbg;
+    const int64_t slots = rows * num_labels;
+    if (slots <= 0) return NBG_OK;
+    if (!accum || !other) return fail(NBG_ERR_BAD_ARG, "nbg_group_combine: null workspace");
+    GroupWs a = GroupWs::carve(align256(accum), rows, num_labels);
+    GroupWs o = GroupWs::carve(align256(const_cast<void *>(other)), rows, num_labels);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (vdtype == NBG_F32 || vdtype == NBG_F64)
+        group_combine_kernel<true><<<blocks_for(slots, 256), 256, 0, st>>>(a, o, op, slots);
+    else
+        group_combine_kernel<false><<<blocks_for(slots, 256), 256, 0, st>>>(a, o, op, slots);
+    return check_launch("nbg_group_combine");
+}
+
+extern "C" int nbg_group_finalize(int op, int vdtype, const void *workspace, void *out, int64_t rows,
+                                  int64_t num_labels, int64_t ddof, void *stream) {
+    using namespace nbg;
+    const int64_t slots = rows * num_labels;
+    if (slots <= 0) return NBG_OK;
+    if (!workspace || !out) return fail(NBG_ERR_BAD_ARG, "nbg_group_finalize: null pointer");
+    GroupWs ws = GroupWs::carve(align256(const_cast<void *>(workspace)), rows, num_labels);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned nb = blocks_for(slots, 256);
+    switch (vdtype) {
+        case NBG_F32:
+            group_finalize_kernel<float><<<nb, 256, 0, st>>>(ws, static_cast<float *>(out), op, slots, ddof);
+            break;
+        case NBG_F64:
+            group_finalize_kernel<double><<<nb, 256, 0, st>>>(ws, static_cast<double *>(out), op, slots, ddof);
+            break;
+        case NBG_I32:
+            group_finalize_kernel<int32_t><<<nb, 256, 0, st>>>(ws, static_cast<int32_t *>(out), op, slots, ddof);
+            break;
+        case NBG_I64:
+            group_finalize_kernel<int64_t><<<nb, 256, 0, st>>>(ws, static_cast<int64_t *>(out), op, slots, ddof);
+            break;
+        default:
+            return fail(NBG_ERR_BAD_DTYPE, "nbg_group_finalize: bad values dtype");
+    }
+    return check_launch("nbg_group_finalize");
+}
+
+extern "C" int nbg_group(int op, int vdtype, int ldtype, const void *values, const void *labels, int labels_per_row,
+                         void *out, int64_t rows, int64_t n, int64_t num_labels, int64_t ddof, void *workspace,
+                         size_t workspace_bytes, void *stream) {
+    using namespace nbg;
+    if (rows * num_labels > 0 && workspace_bytes < nbg_group_workspace_bytes(op, vdtype, rows, num_labels))
+        return fail(NBG_ERR_WORKSPACE, "nbg_group: workspace too small");
+    int rc = nbg_group_init(op, vdtype, workspace, rows, num_labels, stream);
+    if (rc) return rc;
+    rc = nbg_group_accumulate(op, vdtype, ldtype, values, labels, labels_per_row, workspace, rows, n, num_labels, 0, stream);
+    if (rc) return rc;
+    return nbg_group_finalize(op, vdtype, workspace, out, rows, num_labels, ddof, stream);
 }
