@@ -86,7 +86,7 @@ __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 
 // Product of two inputs in the INPUT type, then widened: numba types float32*float32 as
-// float32 (oracle/nbg_oracle.c header).
+// float32 (verified bit-for-bit against the reference in tests/test_gpu_golden.py).
 __device__ __forceinline__ double prod_as_input(float a, float b) { return (double)__fmul_rn(a, b); }
 __device__ __forceinline__ double prod_as_input(double a, double b) { return __dmul_rn(a, b); }
 
@@ -201,16 +201,22 @@ __device__ __forceinline__ void span_fill_edges(T *s, const T *row, int64_t p0, 
     for (int j = pl.hi + tid; j < len; j += THREADS) s[j] = fill;
 }
 
-// Bulk-store s[0, cnt) to g[0, cnt) where s and g share their 16-byte phase: thread 0
-// issues the aligned middle, all threads store the unaligned edges.  Must be followed by
-// bulk_wait_read_all() on thread 0 before the CTA reuses / releases the buffer.
+// Bulk-store s[0, cnt) to g[0, cnt): when s and g share their 16-byte phase thread 0 issues
+// the aligned middle as one bulk store and all threads store the unaligned edges; otherwise
+// (an output tensor whose rows are phased differently from the input's) every thread stores
+// scalars.  Must be followed by bulk_wait_read_all() on thread 0 before the CTA reuses or
+// releases the buffer.
 template <typename T, int THREADS>
 __device__ __forceinline__ void span_store(T *g, const T *s, int cnt) {
     constexpr int PER16 = 16 / (int)sizeof(T);
+    const int tid = threadIdx.x;
+    if ((((uintptr_t)g) & 15) != (smem_u32(s) & 15)) {
+        for (int j = tid; j < cnt; j += THREADS) g[j] = s[j];
+        return;
+    }
     int head = (int)(((16 - ((uintptr_t)g & 15)) & 15) / sizeof(T));
     if (head > cnt) head = cnt;
     int blk = ((cnt - head) / PER16) * PER16;
-    const int tid = threadIdx.x;
     if (tid == 0 && blk > 0) {
         bulk_s2g(g + head, s + head, (uint32_t)blk * (uint32_t)sizeof(T));
         bulk_commit();

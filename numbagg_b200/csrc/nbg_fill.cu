@@ -154,11 +154,11 @@ template <typename T>
 struct FillTile;
 template <>
 struct FillTile<float> {
-    static constexpr int THREADS = 256, E = 17;
+    static constexpr int THREADS = 256, E = 33;
 };
 template <>
 struct FillTile<double> {
-    static constexpr int THREADS = 256, E = 9;
+    static constexpr int THREADS = 256, E = 17;
 };
 
 template <typename T>

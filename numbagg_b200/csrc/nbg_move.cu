@@ -31,7 +31,30 @@
 namespace nbg {
 
 constexpr int kDirectMax = 32;
+constexpr int kRcpMax = 4096;  // windows up to this size use the shared reciprocal table
 
+// sqrt through the float reciprocal-sqrt seed (MUFU.RSQ, ~2^-22 relative error), two Newton
+// steps on y ~ 1/sqrt(v) and one correction of r = v*y: <= 1 ulp.  Values outside
+// (1e-35, 1e35) -- including 0, negatives, inf and NaN -- take the IEEE sqrt path.
+__device__ __forceinline__ double rsqrt_seed(double v) {
+    return (double)rsqrtf((float)v);  // MUFU.RSQ on the float image of v (callers bound v)
+}
+__device__ __forceinline__ double fast_rsqrt(double v) {
+    // callers guarantee 2^-120 < v < 2^120 or handle the specials themselves
+    double y = rsqrt_seed(v);                 // ~2^-22
+    double h = 0.5 * v;
+    y = y * fma(-h * y, y, 1.5);              // ~2^-43
+    y = y * fma(-h * y, y, 1.5);              // ~2^-86 -> rounding-limited
+    return y;
+}
+__device__ __forceinline__ double fast_sqrt(double v) {
+    const bool tiny_or_huge = !(v > 1e-35 && v < 1e35);
+    if (tiny_or_huge) return sqrt(v);  // rare (also NaN / negative / 0 / inf): IEEE path
+    const double y = fast_rsqrt(v);
+    double r = v * y;
+    r = fma(fma(-r, r, v), 0.5 * y, r);
+    return r;
+}
 // ------------------------------------------------------------------------------------ ops
 // Each op lists its channels (running double sums), how one observation contributes, the
 // order of add/remove (moving.py differs between move_sum and the others) and the output.
@@ -44,6 +67,9 @@ struct OpMean {
     __device__ static __forceinline__ T finalize(const double *s, int count) {
         return (T)(s[0] / (double)count);
     }
+    // rc = 1/count, rc1 = 1/(count-1) from the per-CTA reciprocal table (<= 1 ulp from a
+    // true division; see DESIGN.md "finalisation")
+    __device__ static __forceinline__ T finalize_fast(const double *s, double rc, double) { return (T)dmul(s[0], rc); }
 };
 template <typename T>
 struct OpSum {
@@ -52,6 +78,7 @@ struct OpSum {
     static constexpr int MIN_COUNT_FLOOR = 0;  // no clamp: min_count=0 -> 0.0 on empty windows
     __device__ static __forceinline__ void contrib(T a, T, double *c) { c[0] = (double)a; }
     __device__ static __forceinline__ T finalize(const double *s, int) { return (T)s[0]; }
+    __device__ static __forceinline__ T finalize_fast(const double *s, double, double) { return (T)s[0]; }
 };
 template <typename T, bool SQRT>
 struct OpVar {
@@ -67,6 +94,10 @@ struct OpVar {
         double v = dsub(s[1], dmul(s[0], s[0]) / (double)count) / (double)(count - 1);
         return (T)(SQRT ? sqrt(v) : v);
     }
+    __device__ static __forceinline__ T finalize_fast(const double *s, double rc, double rc1) {
+        const double v = dmul(dsub(s[1], dmul(dmul(s[0], s[0]), rc)), rc1);
+        return (T)(SQRT ? fast_sqrt(v) : v);
+    }
 };
 template <typename T>
 struct OpCov {
@@ -81,6 +112,9 @@ struct OpCov {
     __device__ static __forceinline__ T finalize(const double *s, int count) {
         // (prodsum - asum * bsum / count) / (count - 1)   moving.py:218
         return (T)(dsub(s[2], dmul(s[0], s[1]) / (double)count) / (double)(count - 1));
+    }
+    __device__ static __forceinline__ T finalize_fast(const double *s, double rc, double rc1) {
+        return (T)dmul(dsub(s[2], dmul(dmul(s[0], s[1]), rc)), rc1);
     }
 };
 template <typename T>
@@ -105,6 +139,14 @@ struct OpCorr {
         double vv = dmul(var_a, var_b);
         return vv > 0 ? (T)(cov / sqrt(vv)) : quiet_nan<T>();
     }
+    __device__ static __forceinline__ T finalize_fast(const double *s, double rc, double) {
+        const double avg_a = dmul(s[0], rc), avg_b = dmul(s[1], rc);
+        const double var_a = dsub(dmul(s[3], rc), dmul(avg_a, avg_a));
+        const double var_b = dsub(dmul(s[4], rc), dmul(avg_b, avg_b));
+        const double cov = dsub(dmul(s[2], rc), dmul(avg_a, avg_b));
+        const double vv = dmul(var_a, var_b);
+        return vv > 0 ? (T)dmul(cov, (vv > 1e-35 && vv < 1e35) ? fast_rsqrt(vv) : rsqrt(vv)) : quiet_nan<T>();
+    }
 };
 
 template <class Op, typename T>
@@ -113,25 +155,26 @@ __device__ __forceinline__ bool obs_valid(T a, T b) {
     return !is_nan(a);
 }
 
+// Invalid observations contribute +0.0 to every channel and 0 to the count: one select on the
+// INPUT value instead of a select per 64-bit channel (x + 0.0 == x for every running sum that
+// can occur here; the sums start at +0.0).
 template <class Op, typename T>
 __device__ __forceinline__ void acc_add(double *s, int &count, T a, T b) {
-    if (obs_valid<Op>(a, b)) {
-        double c[Op::NCH];
-        Op::contrib(a, b, c);
+    const bool v = obs_valid<Op>(a, b);
+    double c[Op::NCH];
+    Op::contrib(v ? a : (T)0, v ? b : (T)0, c);
 #pragma unroll
-        for (int q = 0; q < Op::NCH; q++) s[q] = dadd(s[q], c[q]);
-        count += 1;
-    }
+    for (int q = 0; q < Op::NCH; q++) s[q] = dadd(s[q], c[q]);
+    count += v ? 1 : 0;
 }
 template <class Op, typename T>
 __device__ __forceinline__ void acc_sub(double *s, int &count, T a, T b) {
-    if (obs_valid<Op>(a, b)) {
-        double c[Op::NCH];
-        Op::contrib(a, b, c);
+    const bool v = obs_valid<Op>(a, b);
+    double c[Op::NCH];
+    Op::contrib(v ? a : (T)0, v ? b : (T)0, c);
 #pragma unroll
-        for (int q = 0; q < Op::NCH; q++) s[q] = dsub(s[q], c[q]);
-        count -= 1;
-    }
+    for (int q = 0; q < Op::NCH; q++) s[q] = dsub(s[q], c[q]);
+    count -= v ? 1 : 0;
 }
 
 // --------------------------------------------------------------------------- row-tile kernel
@@ -141,7 +184,7 @@ struct MoveParams {
     const void *a_halo, *b_halo;
     int64_t halo_len;
     int64_t rows, n;
-    int window;     // <= kMaxHaloWindow on this path
+    int window;     // halo must fit in shared memory on this path
     int min_count;  // already clamped per op, saturated to int
     int tiles_per_row;
 };
@@ -149,29 +192,72 @@ struct MoveParams {
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // shared-memory carve-up (bytes), shared by host sizing and the kernel
-template <typename T, int NIN, int NCH, int THREADS, int E>
+template <typename T, int NIN, int NCH, int THREADS, int E, bool RCP>
 struct MoveSmem {
     static constexpr int TILE = THREADS * E;
+    static constexpr int NCHP = NCH + 1;  // channels + count
+    // mbarrier + per-warp scan totals (2 sets of NCHP doubles per warp: delta scan, halo sum)
+    __host__ __device__ static size_t header_bytes() { return 64 + (size_t)2 * NCHP * (THREADS / 32 + 1) * sizeof(double); }
+    __host__ __device__ static size_t rcp_bytes(int window) { return RCP ? align16((size_t)(window + 2) * sizeof(double)) : 0; }
     __host__ __device__ static size_t in_bytes(int window) { return align16((size_t)(window + TILE) * sizeof(T) + 16); }
-    __host__ __device__ static int chunks(int window) { return (window + TILE + E - 1) / E; }
-    __host__ __device__ static size_t scan_bytes(int window) {
-        return window > kDirectMax ? align16((size_t)(NCH + 1) * (chunks(window) + 1) * sizeof(double)) : 0;
-    }
     __host__ __device__ static size_t out_bytes() { return align16((size_t)TILE * sizeof(T) + 16); }
-    __host__ __device__ static size_t work_bytes(int window) {
-        size_t s = scan_bytes(window), o = out_bytes();
-        return s > o ? s : o;
-    }
+    __host__ __device__ static size_t work_bytes(int) { return out_bytes(); }
     __host__ __device__ static size_t total(int window) {
-        return 64 /*mbarrier + warp scratch header*/ + 34 * sizeof(double) + NIN * in_bytes(window) + work_bytes(window);
+        return header_bytes() + rcp_bytes(window) + NIN * in_bytes(window) + work_bytes(window);
     }
 };
 
-template <typename T, class Op, int THREADS, int E>
+// Window states at every thread's chunk start from per-thread quantities:
+//   delta[c] = (sum over the thread's E entering elements) - (sum over its E leaving ones)
+//   halo[c]  = the thread's share of the `window` elements preceding the tile
+// S(thread t) = sum_all(halo) + sum_{t' < t} delta(t')   -- one shuffle scan + one barrier.
+// Every partial sum is bounded by a window sum, so the rounding error stays at a few ulps
+// of the window sum (better than differencing tile-long prefixes).
+template <int THREADS, int NCHP>
+__device__ __forceinline__ void block_delta_scan(const double *delta, const double *halo, double *state,
+                                                 double *scratch /* 2*NCHP*(THREADS/32+1) */) {
+    constexpr int NW = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double inc[NCHP], hs[NCHP];
+#pragma unroll
+    for (int c = 0; c < NCHP; c++) {
+        inc[c] = delta[c];
+        hs[c] = halo[c];
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+        for (int c = 0; c < NCHP; c++) {
+            const double o = __shfl_up_sync(0xffffffffu, inc[c], d);
+            if (lane >= d) inc[c] += o;
+            hs[c] += __shfl_xor_sync(0xffffffffu, hs[c], d);
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < NCHP; c++) {
+            scratch[c * NW + wid] = inc[c];
+            scratch[(NCHP + c) * NW + wid] = hs[c];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NCHP; c++) {
+        double base = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; w2++) {
+            base += scratch[(NCHP + c) * NW + w2];
+            if (w2 < wid) base += scratch[c * NW + w2];
+        }
+        state[c] = base + (inc[c] - delta[c]);
+    }
+}
+
+template <typename T, class Op, int THREADS, int E, bool RCP>
 __global__ void __launch_bounds__(THREADS) move_rowtile_kernel(MoveParams p) {
-    constexpr int NIN = Op::NIN, NCH = Op::NCH;
+    constexpr int NIN = Op::NIN, NCH = Op::NCH, NCHP = NCH + 1;
     constexpr int TILE = THREADS * E;
-    using SM = MoveSmem<T, NIN, NCH, THREADS, E>;
+    using SM = MoveSmem<T, NIN, NCH, THREADS, E, RCP>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int tid = threadIdx.x;
@@ -183,8 +269,9 @@ __global__ void __launch_bounds__(THREADS) move_rowtile_kernel(MoveParams p) {
     const int64_t p0 = c0 - w;
 
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    double *warp_scratch = reinterpret_cast<double *>(smem_raw + 64);
-    unsigned char *in_base = smem_raw + 64 + 34 * sizeof(double);
+    double *scratch = reinterpret_cast<double *>(smem_raw + 64);
+    double *rcp = reinterpret_cast<double *>(smem_raw + SM::header_bytes());  // rcp[c + 1] = 1 / c
+    unsigned char *in_base = smem_raw + SM::header_bytes() + SM::rcp_bytes(w);
     unsigned char *work_base = in_base + NIN * SM::in_bytes(w);
 
     const T *row_a = reinterpret_cast<const T *>(p.a) + row * p.n;
@@ -213,6 +300,11 @@ __global__ void __launch_bounds__(THREADS) move_rowtile_kernel(MoveParams p) {
     }
     span_fill_edges<T, THREADS>(sa, row_a, p0, len, pla, quiet_nan<T>(), halo_a, p.halo_len);
     if (NIN == 2) span_fill_edges<T, THREADS>(sb, row_b, p0, len, plb, quiet_nan<T>(), halo_b, p.halo_len);
+    if (RCP) {
+        // reciprocal table while the copy is in flight: rcp[c + 1] = 1.0 / c (IEEE division),
+        // rcp[0] = rcp[1] = 0 so that count == 0 and count - 1 == -1 index harmless entries
+        for (int c = tid; c <= w + 1; c += THREADS) rcp[c] = c >= 2 ? 1.0 / (double)(c - 1) : 0.0;
+    }
     if (tx > 0) mbar_wait(bar, 0);
     __syncthreads();
 
@@ -225,33 +317,33 @@ __global__ void __launch_bounds__(THREADS) move_rowtile_kernel(MoveParams p) {
     if (w <= kDirectMax) {
         for (int j = jt; j < jt + w; j++) acc_add<Op, T>(s, count, sa[j], NIN == 2 ? sb[j] : sa[j]);
     } else {
-        // per-chunk totals -> exclusive scan -> prefix difference + remainder
-        double *pref = reinterpret_cast<double *>(work_base);  // [NCH+1][M+1]
-        const int M = SM::chunks(w);
-        const int stride = M + 1;
-        for (int m = tid; m < M; m += THREADS) {
+        // pass 1: this thread's entering-minus-leaving totals + its share of the halo sum
+        double delta[NCHP], halo[NCHP], st[NCHP];
+        {
             double cs[NCH];
 #pragma unroll
             for (int q = 0; q < NCH; q++) cs[q] = 0.0;
             int cc = 0;
-            const int jb = m * E;
 #pragma unroll
             for (int k = 0; k < E; k++) {
-                const int j = jb + k;
-                if (j < len) acc_add<Op, T>(cs, cc, sa[j], NIN == 2 ? sb[j] : sa[j]);
+                acc_add<Op, T>(cs, cc, sa[jt + w + k], NIN == 2 ? sb[jt + w + k] : sa[jt + w + k]);
+                acc_sub<Op, T>(cs, cc, sa[jt + k], NIN == 2 ? sb[jt + k] : sa[jt + k]);
             }
 #pragma unroll
-            for (int q = 0; q < NCH; q++) pref[q * stride + m] = cs[q];
-            pref[NCH * stride + m] = (double)cc;
-        }
-        __syncthreads();
-        for (int q = 0; q <= NCH; q++) block_exclusive_scan<THREADS>(pref + q * stride, M, warp_scratch);
-        const int qfull = w / E;  // whole chunks inside the window
+            for (int q = 0; q < NCH; q++) delta[q] = cs[q];
+            delta[NCH] = (double)cc;
 #pragma unroll
-        for (int q = 0; q < NCH; q++) s[q] = dsub(pref[q * stride + tid + qfull], pref[q * stride + tid]);
-        count = __double2int_rn(pref[NCH * stride + tid + qfull] - pref[NCH * stride + tid]);
-        for (int j = jt + qfull * E; j < jt + w; j++) acc_add<Op, T>(s, count, sa[j], NIN == 2 ? sb[j] : sa[j]);
-        __syncthreads();  // pref is about to be overwritten by the out tile
+            for (int q = 0; q < NCH; q++) cs[q] = 0.0;
+            cc = 0;
+            for (int j = tid; j < w; j += THREADS) acc_add<Op, T>(cs, cc, sa[j], NIN == 2 ? sb[j] : sa[j]);
+#pragma unroll
+            for (int q = 0; q < NCH; q++) halo[q] = cs[q];
+            halo[NCH] = (double)cc;
+        }
+        block_delta_scan<THREADS, NCHP>(delta, halo, st, scratch);
+#pragma unroll
+        for (int q = 0; q < NCH; q++) s[q] = st[q];
+        count = __double2int_rn(st[NCH]);
     }
 
     // ---- running window over this thread's E outputs
@@ -270,7 +362,13 @@ __global__ void __launch_bounds__(THREADS) move_rowtile_kernel(MoveParams p) {
             acc_sub<Op, T>(s, count, ar, br);
             acc_add<Op, T>(s, count, al, bl);
         }
-        sout[jt + k] = (count >= mc) ? Op::finalize(s, count) : quiet_nan<T>();
+        T r;
+        if (RCP) {
+            r = Op::finalize_fast(s, rcp[count + 1], rcp[count]);
+        } else {
+            r = Op::finalize(s, count);
+        }
+        sout[jt + k] = (count >= mc) ? r : quiet_nan<T>();
     }
 
     // ---- drain the out tile
@@ -357,13 +455,26 @@ template <typename T>
 struct TileCfg;
 template <>
 struct TileCfg<float> {
-    static constexpr int THREADS = 256, E = 17;
+    static constexpr int THREADS = 512, E = 17;
 };
 template <>
 struct TileCfg<double> {
-    static constexpr int THREADS = 256, E = 9;
+    static constexpr int THREADS = 512, E = 9;
 };
 
+template <typename T, class Op, bool RCP>
+static int launch_rowtile(MoveParams p, int64_t outer, int64_t n, cudaStream_t stream) {
+    constexpr int THREADS = TileCfg<T>::THREADS, E = TileCfg<T>::E;
+    using SM = MoveSmem<T, Op::NIN, Op::NCH, THREADS, E, RCP>;
+    const int64_t tpr = (n + SM::TILE - 1) / SM::TILE;
+    if (tpr * outer > INT32_MAX) return fail(NBG_ERR_UNSUPPORTED, "nbg_move: more than 2^31 tiles");
+    p.tiles_per_row = (int)tpr;
+    auto kern = move_rowtile_kernel<T, Op, THREADS, E, RCP>;
+    int rc = allow_big_smem(kern, "nbg_move: cudaFuncSetAttribute");
+    if (rc) return rc;
+    kern<<<(unsigned)(tpr * outer), THREADS, SM::total(p.window), stream>>>(p);
+    return check_launch("nbg_move(rowtile)");
+}
 
 template <typename T, class Op>
 static int launch_move(const void *a, const void *b, void *out, int64_t outer, int64_t n, int64_t inner,
@@ -372,21 +483,17 @@ static int launch_move(const void *a, const void *b, void *out, int64_t outer, i
     if (min_count < Op::MIN_COUNT_FLOOR) min_count = Op::MIN_COUNT_FLOOR;
     if (outer * n * inner == 0) return NBG_OK;
     constexpr int THREADS = TileCfg<T>::THREADS, E = TileCfg<T>::E;
-    using SM = MoveSmem<T, Op::NIN, Op::NCH, THREADS, E>;
-    if (inner == 1 && window <= (1 << 20) && SM::total((int)window) <= kMaxSmem) {
+    using SMfast = MoveSmem<T, Op::NIN, Op::NCH, THREADS, E, true>;
+    using SMslow = MoveSmem<T, Op::NIN, Op::NCH, THREADS, E, false>;
+    if (inner == 1 && window <= (1 << 20) && SMslow::total((int)window) <= kMaxSmem) {
         MoveParams p;
         p.a = a, p.b = b, p.out = out, p.a_halo = a_halo, p.b_halo = b_halo, p.halo_len = halo_len;
         p.rows = outer, p.n = n, p.window = (int)window;
         p.min_count = (int)(min_count > INT32_MAX ? INT32_MAX : min_count);
-        const int64_t tpr = (n + SM::TILE - 1) / SM::TILE;
-        if (tpr * outer > INT32_MAX) return fail(NBG_ERR_UNSUPPORTED, "nbg_move: more than 2^31 tiles");
-        p.tiles_per_row = (int)tpr;
-        const size_t smem = SM::total((int)window);
-        auto kern = move_rowtile_kernel<T, Op, THREADS, E>;
-        int rc = allow_big_smem(kern, "nbg_move: cudaFuncSetAttribute");
-        if (rc) return rc;
-        kern<<<(unsigned)(tpr * outer), THREADS, smem, stream>>>(p);
-        return check_launch("nbg_move(rowtile)");
+        p.tiles_per_row = 0;
+        if (window <= kRcpMax && SMfast::total((int)window) <= kMaxSmem)
+            return launch_rowtile<T, Op, true>(p, outer, n, stream);
+        return launch_rowtile<T, Op, false>(p, outer, n, stream);
     }
     // column walk (also the fallback for windows whose halo does not fit in shared memory)
     MoveColParams p;

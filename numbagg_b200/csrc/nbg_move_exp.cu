@@ -315,11 +315,11 @@ template <typename T>
 struct ExpTile;
 template <>
 struct ExpTile<float> {
-    static constexpr int THREADS = 256, E = 17;
+    static constexpr int THREADS = 256, E = 33;
 };
 template <>
 struct ExpTile<double> {
-    static constexpr int THREADS = 256, E = 9;
+    static constexpr int THREADS = 256, E = 17;
 };
 
 struct ExpArgs {

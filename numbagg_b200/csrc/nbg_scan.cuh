@@ -12,7 +12,7 @@
 //      (one warp, 32 descriptors per round) until it meets an inclusive prefix, publishes
 //      its own inclusive prefix,
 //   5. re-runs each chunk from its now-known incoming state and emits outputs (pass B),
-//   6. drains the out tile with one bulk store.
+//   6. drains the tile (outputs overwrite the staged input in place) with one bulk store.
 // Each element is read from HBM once and written once: 2*itemsize algorithmic bytes.
 //
 // An `Agg` type provides:  static Agg identity();  static Agg combine(older, newer);
@@ -222,7 +222,8 @@ struct ScanSmem {
     static constexpr size_t header = 64 + sizeof(Agg) * (THREADS / 32 + 2);
     __host__ __device__ static size_t header_bytes() { return (header + 15) & ~(size_t)15; }
     __host__ __device__ static size_t stream_bytes() { return ((size_t)TILE * sizeof(T) + 16 + 15) & ~(size_t)15; }
-    __host__ __device__ static size_t total() { return header_bytes() + (P::NSTREAM + 1) * stream_bytes(); }
+    // outputs are written in place over stream 0 (each thread only rewrites its own chunk)
+    __host__ __device__ static size_t total() { return header_bytes() + P::NSTREAM * stream_bytes(); }
 };
 
 template <class P, int THREADS, int E>
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(THREADS) scan_rowtile_kernel(ScanParams p) {
     // ---- pass B: re-run every chunk from its incoming state, emit outputs
     const Agg state = Agg::combine(*s_carry, excl);
     T *row_out = reinterpret_cast<T *>(p.out) + row * p.n;
-    T *sout = reinterpret_cast<T *>(streams + NS * SM::stream_bytes() + span_phase(row_out, p0));
+    T *sout = s_[0];  // in place: put(k) overwrites the element get(0, k) already consumed
     auto put = [&](int k, T v) {
         const int j = P::REV ? (TILE - 1 - (k0 + k)) : (k0 + k);
         sout[j] = v;
