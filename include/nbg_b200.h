@@ -162,15 +162,19 @@ size_t nbg_fill_workspace_bytes(int itemsize, int64_t outer, int64_t n, int64_t 
  * of shards, `index_offset` = flat index of the shard's first element) -> [caller combines
  * workspaces across devices] -> finalize.  nbg_group() runs the three steps on one device.
  * The workspace holds, per (row, label), NBG_GROUP_WS_CHANNELS 8-byte slots whose meaning
- * is listed in DESIGN.md ("group workspace"); nbg_group_workspace_bytes() sizes it.
+ * is listed in DESIGN.md ("group workspace"), followed by per-call scratch (the column plan
+ * of the shared-label kernel); nbg_group_workspace_bytes() sizes both for shards of up to
+ * `n` elements per row.  Only the first NBG_GROUP_WS_CHANNELS*rows*num_labels*8 bytes (after
+ * rounding the base up to 256) are state that must be exchanged between devices.
  */
 #define NBG_GROUP_WS_CHANNELS 3
-size_t nbg_group_workspace_bytes(int op, int vdtype, int64_t rows, int64_t num_labels);
+size_t nbg_group_workspace_bytes(int op, int vdtype, int64_t rows, int64_t n, int64_t num_labels);
 int nbg_group_init(int op, int vdtype, void *workspace, int64_t rows, int64_t num_labels,
                    void *stream);
 int nbg_group_accumulate(int op, int vdtype, int ldtype, const void *values,
-                         const void *labels, int labels_per_row, void *workspace, int64_t rows,
-                         int64_t n, int64_t num_labels, int64_t index_offset, void *stream);
+                         const void *labels, int labels_per_row, void *workspace,
+                         size_t workspace_bytes, int64_t rows, int64_t n, int64_t num_labels,
+                         int64_t index_offset, void *stream);
 /* Merge workspace `other` (accumulated over LATER elements) into `accum`; order matters for
  * first/last and for arg* ties.  Used to fold all-gathered per-device partials. */
 int nbg_group_combine(int op, int vdtype, void *accum, const void *other, int64_t rows,

@@ -45,9 +45,9 @@ _SIGNATURES = {
     "nbg_move_exp_workspace_bytes": (_sz, [_int, _int, _i64, _i64, _i64]),
     "nbg_fill": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "nbg_fill_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
-    "nbg_group_workspace_bytes": (_sz, [_int, _int, _i64, _i64]),
+    "nbg_group_workspace_bytes": (_sz, [_int, _int, _i64, _i64, _i64]),
     "nbg_group_init": (_int, [_int, _int, _vp, _i64, _i64, _vp]),
-    "nbg_group_accumulate": (_int, [_int, _int, _int, _vp, _vp, _int, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "nbg_group_accumulate": (_int, [_int, _int, _int, _vp, _vp, _int, _vp, _sz, _i64, _i64, _i64, _i64, _vp]),
     "nbg_group_combine": (_int, [_int, _int, _vp, _vp, _i64, _i64, _vp]),
     "nbg_group_finalize": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _vp]),
     "nbg_group": (_int, [_int, _int, _int, _vp, _vp, _int, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),

@@ -29,6 +29,7 @@
 //                            atomics, and each bin sees its elements in ascending column
 //                            order, i.e. the reference's own summation order.
 #include "nbg_common.cuh"
+#include "nbg_group_rowbins.cuh"
 
 namespace nbg {
 
@@ -390,8 +391,34 @@ static int launch_atomic(const V *values, const L *labels, int labels_per_row, G
 }
 
 template <typename V, typename L>
+static int try_rowbins(int op, const V *values, const L *labels, GroupWs ws, void *scratch, size_t scratch_bytes,
+                       int64_t rows, int64_t n, int64_t K, cudaStream_t stream, bool *handled) {
+    *handled = false;
+    switch (rb_class_of(op)) {
+        case RB_SUM:
+            return rb_launch<V, L, RB_SUM>(values, labels, ws.ch, scratch, scratch_bytes, rows, n, K, stream, handled);
+        case RB_COUNT:
+            return rb_launch<V, L, RB_COUNT>(values, labels, ws.ch, scratch, scratch_bytes, rows, n, K, stream, handled);
+        case RB_MEAN:
+            return rb_launch<V, L, RB_MEAN>(values, labels, ws.ch, scratch, scratch_bytes, rows, n, K, stream, handled);
+        case RB_SUMSQ:
+            return rb_launch<V, L, RB_SUMSQ>(values, labels, ws.ch, scratch, scratch_bytes, rows, n, K, stream, handled);
+        case RB_VAR:
+            return rb_launch<V, L, RB_VAR>(values, labels, ws.ch, scratch, scratch_bytes, rows, n, K, stream, handled);
+        default:
+            return NBG_OK;
+    }
+}
+
+template <typename V, typename L>
 static int dispatch_accumulate(int op, const V *values, const L *labels, int labels_per_row, GroupWs ws, int64_t rows,
-                               int64_t n, int64_t K, int64_t index_offset, cudaStream_t stream) {
+                               int64_t n, int64_t K, int64_t index_offset, void *scratch, size_t scratch_bytes,
+                               cudaStream_t stream) {
+    if (!labels_per_row) {
+        bool handled = false;
+        int rc = try_rowbins<V, L>(op, values, labels, ws, scratch, scratch_bytes, rows, n, K, stream, &handled);
+        if (rc || handled) return rc;
+    }
 #define NBG_GROUP_CASE(OPC) \
     case OPC:               \
         return launch_atomic<V, L, OPC>(values, labels, labels_per_row, ws, rows, n, K, index_offset, stream)
@@ -419,13 +446,14 @@ static int dispatch_accumulate(int op, const V *values, const L *labels, int lab
 
 template <typename V>
 static int dispatch_labels(int op, int ldtype, const void *values, const void *labels, int labels_per_row, GroupWs ws,
-                           int64_t rows, int64_t n, int64_t K, int64_t index_offset, cudaStream_t stream) {
+                           int64_t rows, int64_t n, int64_t K, int64_t index_offset, void *scratch,
+                           size_t scratch_bytes, cudaStream_t stream) {
     if (ldtype == NBG_I32)
         return dispatch_accumulate<V, int32_t>(op, static_cast<const V *>(values), static_cast<const int32_t *>(labels),
-                                               labels_per_row, ws, rows, n, K, index_offset, stream);
+                                               labels_per_row, ws, rows, n, K, index_offset, scratch, scratch_bytes, stream);
     if (ldtype == NBG_I64)
         return dispatch_accumulate<V, int64_t>(op, static_cast<const V *>(values), static_cast<const int64_t *>(labels),
-                                               labels_per_row, ws, rows, n, K, index_offset, stream);
+                                               labels_per_row, ws, rows, n, K, index_offset, scratch, scratch_bytes, stream);
     return fail(NBG_ERR_BAD_DTYPE, "nbg_group: labels dtype must be NBG_I32 or NBG_I64");
 }
 
@@ -435,9 +463,15 @@ static bool float_only(int op) {
 
 }  // namespace nbg
 
-extern "C" size_t nbg_group_workspace_bytes(int, int, int64_t rows, int64_t num_labels) {
-    if (rows <= 0 || num_labels <= 0) return 0;
+static size_t group_state_bytes(int64_t rows, int64_t num_labels) {
     return (size_t)NBG_GROUP_WS_CHANNELS * (size_t)rows * (size_t)num_labels * 8 + 256;
+}
+// scratch for the shared-label plan: 4 bytes per column + one header per (smallest) tile
+static size_t group_scratch_bytes(int64_t n) { return (size_t)n * 4 + (size_t)(n / 128 + 2) * nbg::kRbHdr * 4 + 1024; }
+
+extern "C" size_t nbg_group_workspace_bytes(int, int, int64_t rows, int64_t n, int64_t num_labels) {
+    if (rows <= 0 || num_labels <= 0) return 0;
+    return group_state_bytes(rows, num_labels) + group_scratch_bytes(n > 0 ? n : 0);
 }
 
 static void *align256(void *p) { return reinterpret_cast<void *>(((uintptr_t)p + 255) & ~(uintptr_t)255); }
@@ -455,25 +489,29 @@ extern "C" int nbg_group_init(int op, int vdtype, void *workspace, int64_t rows,
 }
 
 extern "C" int nbg_group_accumulate(int op, int vdtype, int ldtype, const void *values, const void *labels,
-                                    int labels_per_row, void *workspace, int64_t rows, int64_t n, int64_t num_labels,
-                                    int64_t index_offset, void *stream) {
+                                    int labels_per_row, void *workspace, size_t workspace_bytes, int64_t rows,
+                                    int64_t n, int64_t num_labels, int64_t index_offset, void *stream) {
     using namespace nbg;
     if (rows < 0 || n < 0 || num_labels < 0) return fail(NBG_ERR_BAD_ARG, "nbg_group: negative size");
     if (rows * n == 0 || num_labels == 0) return NBG_OK;
     if (!values || !labels || !workspace) return fail(NBG_ERR_BAD_ARG, "nbg_group: null pointer");
     if (float_only(op) && !(vdtype == NBG_F32 || vdtype == NBG_F64))
         return fail(NBG_ERR_BAD_DTYPE, "nbg_group: nanmean/nanvar/nanstd need float values (cast integers to float64)");
+    if (workspace_bytes < group_state_bytes(rows, num_labels)) return fail(NBG_ERR_WORKSPACE, "nbg_group: workspace too small");
     GroupWs ws = GroupWs::carve(align256(workspace), rows, num_labels);
+    // whatever follows the accumulator state is per-call scratch (column plan)
+    unsigned char *scratch = static_cast<unsigned char *>(workspace) + group_state_bytes(rows, num_labels);
+    const size_t scratch_bytes = workspace_bytes - group_state_bytes(rows, num_labels);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (vdtype) {
         case NBG_F32:
-            return dispatch_labels<float>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, st);
+            return dispatch_labels<float>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, scratch, scratch_bytes, st);
         case NBG_F64:
-            return dispatch_labels<double>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, st);
+            return dispatch_labels<double>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, scratch, scratch_bytes, st);
         case NBG_I32:
-            return dispatch_labels<int32_t>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, st);
+            return dispatch_labels<int32_t>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, scratch, scratch_bytes, st);
         case NBG_I64:
-            return dispatch_labels<int64_t>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, st);
+            return dispatch_labels<int64_t>(op, ldtype, values, labels, labels_per_row, ws, rows, n, num_labels, index_offset, scratch, scratch_bytes, st);
         default:
             return fail(NBG_ERR_BAD_DTYPE, "nbg_group: bad values dtype");
     }
@@ -527,11 +565,12 @@ extern "C" int nbg_group(int op, int vdtype, int ldtype, const void *values, con
                          void *out, int64_t rows, int64_t n, int64_t num_labels, int64_t ddof, void *workspace,
                          size_t workspace_bytes, void *stream) {
     using namespace nbg;
-    if (rows * num_labels > 0 && workspace_bytes < nbg_group_workspace_bytes(op, vdtype, rows, num_labels))
+    if (rows * num_labels > 0 && workspace_bytes < group_state_bytes(rows, num_labels))
         return fail(NBG_ERR_WORKSPACE, "nbg_group: workspace too small");
     int rc = nbg_group_init(op, vdtype, workspace, rows, num_labels, stream);
     if (rc) return rc;
-    rc = nbg_group_accumulate(op, vdtype, ldtype, values, labels, labels_per_row, workspace, rows, n, num_labels, 0, stream);
+    rc = nbg_group_accumulate(op, vdtype, ldtype, values, labels, labels_per_row, workspace, workspace_bytes, rows, n,
+                              num_labels, 0, stream);
     if (rc) return rc;
     return nbg_group_finalize(op, vdtype, workspace, out, rows, num_labels, ddof, stream);
 }

@@ -1,0 +1,505 @@
+// nbg_group_rowbins.cuh -- grouped sums when ONE label vector is shared by every row
+// (groupndreduce with axis=int, numbagg/decorators.py:633-645: the xarray/flox case and
+// BASELINE config 2).
+//
+// Idea: because all rows share the labels, the scatter pattern can be resolved ONCE per call
+// and then replayed for every row without atomics.
+//   plan kernel (labels only, O(n)): for every tile of C columns, the valid columns stably
+//     sorted by label, packed as (label << 16 | column), plus 33 boundaries that cut the
+//     sorted list into 32 label-aligned, balanced ranges.
+//   main kernel: a CTA owns 8 rows x a column segment.  It streams row tiles (and the tile's
+//     plan) through a 2-stage TMA ring into shared memory.  Its 256 threads form 32 sub-warps
+//     of 8 lanes: lane = row, sub-warp = one of the 32 label ranges.  A sub-warp walks its
+//     range; every entry is "bins[label][row] (+)= tile[row][column]" on a shared-memory bin
+//     that no other lane can touch during this tile (ranges are label-aligned), so the
+//     update is a plain load/add/store, and every bin receives its elements in ascending
+//     column order -- the reference's own summation order (grouped.py:31-40), which makes the
+//     float32 results bit-identical to numbagg's when a CTA covers whole rows.
+//   Few labels (K * words <= 64): ranges are cut evenly instead and each sub-warp gets
+//     private bins that are summed at the end.
+// Bins are V-typed (accumulation in the OUTPUT dtype, like the reference) and are flushed
+// into the common 8-byte workspace at the end (plain stores for one segment per row,
+// atomics otherwise).
+#pragma once
+
+#include "nbg_common.cuh"
+
+namespace nbg {
+
+constexpr int kRbRows = 8;    // rows per CTA = lanes per sub-warp
+constexpr int kRbSub = 32;    // sub-warps per CTA
+constexpr int kRbThreads = kRbRows * kRbSub;
+constexpr int kRbHdr = 36;    // u32 words per tile header: bounds[33], count, 2 pad (144 B)
+
+enum RbClass { RB_SUM = 0, RB_COUNT = 1, RB_MEAN = 2, RB_SUMSQ = 3, RB_VAR = 4 };
+
+// ----------------------------------------------------------------------------------- plan
+template <typename L>
+__global__ void __launch_bounds__(256) group_plan_kernel(const L *__restrict__ labels, int64_t n, int K, int C,
+                                                         int even_split, uint32_t *__restrict__ plan) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int *offs = reinterpret_cast<int *>(smem_raw);        // [K + 1] histogram -> exclusive offsets
+    int *cursor = offs + (K + 1);                          // [K]
+    uint32_t *slab = reinterpret_cast<uint32_t *>(cursor + K);  // [C] label or 0xffffffff
+    uint32_t *sent = slab + C;                             // [C] sorted entries
+    __shared__ int warp_tot[8];
+    __shared__ int s_count;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * C;
+    uint32_t *out = plan + (size_t)blockIdx.x * (kRbHdr + C);
+
+    for (int k = tid; k <= K; k += 256) offs[k] = 0;
+    __syncthreads();
+    for (int j = tid; j < C; j += 256) {
+        const int64_t col = c0 + j;
+        long long lab = -1;
+        if (col < n) lab = (long long)labels[col];
+        const bool valid = lab >= 0 && lab < K;
+        slab[j] = valid ? (uint32_t)lab : 0xffffffffu;
+        sent[j] = 0;
+        if (valid) atomicAdd(&offs[(int)lab], 1);
+    }
+    __syncthreads();
+    // exclusive scan of offs[0..K) (block of 256 threads, contiguous runs per thread)
+    {
+        const int per = (K + 255) / 256;
+        const int beg = min(tid * per, K), end = min(beg + per, K);
+        int local = 0;
+        for (int k = beg; k < end; k++) local += offs[k];
+        int inc = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        int base = 0;
+        for (int w2 = 0; w2 < wid; w2++) base += warp_tot[w2];
+        int run = base + inc - local;
+        for (int k = beg; k < end; k++) {
+            const int c = offs[k];
+            offs[k] = run;
+            cursor[k] = run;
+            run += c;
+        }
+        if (tid == 255) {
+            int tot = 0;
+            for (int w2 = 0; w2 < 8; w2++) tot += warp_tot[w2];
+            s_count = tot;
+            offs[K] = tot;
+        }
+    }
+    __syncthreads();
+    // stable placement by one warp: columns in ascending order, 32 at a time
+    if (wid == 0) {
+        for (int j0 = 0; j0 < C; j0 += 32) {
+            const int j = j0 + lane;
+            const uint32_t lab = j < C ? slab[j] : 0xffffffffu;
+            const bool valid = lab != 0xffffffffu;
+            const unsigned m = __match_any_sync(0xffffffffu, lab);
+            if (valid) {
+                const int rank = __popc(m & ((1u << lane) - 1u));
+                const int base = cursor[lab];
+                sent[base + rank] = (lab << 16) | (uint32_t)j;
+            }
+            __syncwarp();
+            if (valid && (m & ((1u << lane) - 1u)) == 0) cursor[lab] += __popc(m);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const int count = s_count;
+    if (tid <= kRbSub) {
+        int b;
+        if (tid == kRbSub || count == 0) {
+            b = count;
+        } else {
+            const int e = (int)(((long long)tid * count) / kRbSub);
+            b = even_split ? e : offs[sent[e] >> 16];  // start of the label run containing e
+        }
+        out[tid] = (uint32_t)b;
+    }
+    if (tid == 33) out[33] = (uint32_t)count;
+    if (tid == 34) out[34] = 0;
+    if (tid == 35) out[35] = 0;
+    for (int j = tid; j < C; j += 256) out[kRbHdr + j] = sent[j];
+}
+
+// ----------------------------------------------------------------------------------- bins
+template <typename V>
+struct RbCounter {
+    using type = int32_t;
+};
+template <>
+struct RbCounter<double> {
+    using type = long long;
+};
+template <>
+struct RbCounter<int64_t> {
+    using type = long long;
+};
+
+template <typename V>
+__device__ __forceinline__ V v_add(V a, V b) {
+    return a + b;
+}
+template <>
+__device__ __forceinline__ float v_add<float>(float a, float b) {
+    return __fadd_rn(a, b);
+}
+template <>
+__device__ __forceinline__ double v_add<double>(double a, double b) {
+    return __dadd_rn(a, b);
+}
+template <typename V>
+__device__ __forceinline__ V v_sq(V a) {
+    return (V)((unsigned long long)a * (unsigned long long)a);
+}
+template <>
+__device__ __forceinline__ float v_sq<float>(float a) {
+    return __fmul_rn(a, a);
+}
+template <>
+__device__ __forceinline__ double v_sq<double>(double a) {
+    return __dmul_rn(a, a);
+}
+template <>
+__device__ __forceinline__ int32_t v_sq<int32_t>(int32_t a) {
+    return (int32_t)((uint32_t)a * (uint32_t)a);
+}
+
+template <typename V, int CLS>
+struct RbBin;
+template <typename V>
+struct RbBin<V, RB_SUM> {
+    V s;
+    __device__ __forceinline__ void zero() { s = (V)0; }
+    __device__ __forceinline__ void add(V v) { s = v_add(s, v); }
+    __device__ __forceinline__ void merge(const RbBin &o) { s = v_add(s, o.s); }
+};
+template <typename V>
+struct RbBin<V, RB_SUMSQ> {
+    V s;
+    __device__ __forceinline__ void zero() { s = (V)0; }
+    __device__ __forceinline__ void add(V v) { s = v_add(s, v_sq(v)); }
+    __device__ __forceinline__ void merge(const RbBin &o) { s = v_add(s, o.s); }
+};
+template <typename V>
+struct RbBin<V, RB_COUNT> {
+    typename RbCounter<V>::type c;
+    __device__ __forceinline__ void zero() { c = 0; }
+    __device__ __forceinline__ void add(V) { c += 1; }
+    __device__ __forceinline__ void merge(const RbBin &o) { c += o.c; }
+};
+template <typename V>
+struct alignas(2 * sizeof(V)) RbBin<V, RB_MEAN> {
+    V s;
+    typename RbCounter<V>::type c;
+    __device__ __forceinline__ void zero() {
+        s = (V)0;
+        c = 0;
+    }
+    __device__ __forceinline__ void add(V v) {
+        s = v_add(s, v);
+        c += 1;
+    }
+    __device__ __forceinline__ void merge(const RbBin &o) {
+        s = v_add(s, o.s);
+        c += o.c;
+    }
+};
+template <typename V>
+struct alignas(4 * sizeof(V)) RbBin<V, RB_VAR> {
+    V s, ss;
+    typename RbCounter<V>::type c, pad;
+    __device__ __forceinline__ void zero() {
+        s = (V)0;
+        ss = (V)0;
+        c = 0;
+        pad = 0;
+    }
+    __device__ __forceinline__ void add(V v) {
+        s = v_add(s, v);
+        ss = v_add(ss, v_sq(v));
+        c += 1;
+    }
+    __device__ __forceinline__ void merge(const RbBin &o) {
+        s = v_add(s, o.s);
+        ss = v_add(ss, o.ss);
+        c += o.c;
+    }
+};
+
+template <typename V, int CLS>
+struct RbFlush;  // bin -> the three 8-byte workspace channels (Acc ch0, Acc ch1, i64 ch2)
+
+struct RbParams {
+    const void *values;
+    const uint32_t *plan;
+    void *ws_ch[3];
+    int64_t rows, n;
+    int K, C;
+    int ntiles, tiles_per_seg, nseg;
+    int priv;  // sub-warp-private bins (few labels)
+};
+
+template <typename V>
+__host__ __device__ inline int rb_row_stride(int C) {
+    return C + 16 / (int)sizeof(V);  // +16 bytes: rows start 4 banks apart
+}
+template <typename V, int CLS>
+__host__ __device__ inline size_t rb_stage_bytes(int C) {
+    return ((size_t)(kRbHdr + C) * 4 + (size_t)kRbRows * rb_row_stride<V>(C) * sizeof(V) + 15) & ~(size_t)15;
+}
+template <typename V, int CLS>
+__host__ __device__ inline size_t rb_bins_bytes(int K, int priv) {
+    return ((size_t)K * kRbRows * (priv ? kRbSub : 1) * sizeof(RbBin<V, CLS>) + 15) & ~(size_t)15;
+}
+template <typename V, int CLS>
+__host__ __device__ inline size_t rb_smem_bytes(int K, int C, int priv) {
+    return 64 + rb_bins_bytes<V, CLS>(K, priv) + 2 * rb_stage_bytes<V, CLS>(C);
+}
+
+template <typename V, int CLS>
+__global__ void __launch_bounds__(kRbThreads) group_rowbins_kernel(RbParams p) {
+    using Bin = RbBin<V, CLS>;
+    using Acc = typename std::conditional<std::is_floating_point<V>::value, double, long long>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);  // [2]
+    Bin *bins = reinterpret_cast<Bin *>(smem_raw + 64);
+    unsigned char *stage0 = smem_raw + 64 + rb_bins_bytes<V, CLS>(p.K, p.priv);
+    const size_t stage_bytes = rb_stage_bytes<V, CLS>(p.C);
+    const int C = p.C, K = p.K;
+    const int stride = rb_row_stride<V>(C);
+
+    const int tid = threadIdx.x;
+    const int r = tid & (kRbRows - 1);   // row within the group
+    const int sub = tid >> 3;            // sub-warp = label range
+    const int64_t g = blockIdx.x / p.nseg;
+    const int seg = blockIdx.x % p.nseg;
+    const int64_t r0 = g * kRbRows;
+    const int nrows = (int)min((int64_t)kRbRows, p.rows - r0);
+    const int t_beg = seg * p.tiles_per_seg;
+    const int t_end = min(t_beg + p.tiles_per_seg, p.ntiles);
+    const V *vbase = reinterpret_cast<const V *>(p.values) + r0 * p.n;
+
+    const int nbins = K * kRbRows * (p.priv ? kRbSub : 1);
+    for (int i = tid; i < nbins; i += kRbThreads) bins[i].zero();
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t, int st) {
+        // thread 0 only: plan block + one bulk copy per row of the tile
+        unsigned char *sb = stage0 + (size_t)st * stage_bytes;
+        const int64_t c0 = (int64_t)t * C;
+        const int cols = (int)min((int64_t)C, p.n - c0);
+        const uint32_t plan_bytes = (uint32_t)(kRbHdr + C) * 4u;
+        const uint32_t row_bytes = (uint32_t)cols * (uint32_t)sizeof(V);
+        mbar_arrive_expect_tx(&bar[st], plan_bytes + (uint32_t)nrows * row_bytes);
+        bulk_g2s(sb, p.plan + (size_t)t * (kRbHdr + C), plan_bytes, &bar[st]);
+        V *tile = reinterpret_cast<V *>(sb + (size_t)(kRbHdr + C) * 4);
+        for (int rr = 0; rr < nrows; rr++)
+            bulk_g2s(tile + (size_t)rr * stride, vbase + (int64_t)rr * p.n + c0, row_bytes, &bar[st]);
+    };
+
+    if (tid == 0 && t_beg < t_end) issue(t_beg, 0);
+    Bin *mybins = bins + (p.priv ? (size_t)sub * K * kRbRows : 0);
+    for (int t = t_beg, it = 0; t < t_end; t++, it++) {
+        const int st = it & 1;
+        if (tid == 0 && t + 1 < t_end) issue(t + 1, st ^ 1);  // stage st^1 was drained last iteration
+        mbar_wait(&bar[st], (uint32_t)((it >> 1) & 1));
+        const unsigned char *sb = stage0 + (size_t)st * stage_bytes;
+        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(sb);
+        const uint32_t *ent = hdr + kRbHdr;
+        const V *tile = reinterpret_cast<const V *>(sb + (size_t)(kRbHdr + C) * 4) + (size_t)r * stride;
+        const int b0 = (int)hdr[sub], b1 = (int)hdr[sub + 1];
+        if (r < nrows) {
+            int i = b0;
+            for (; i + 4 <= b1; i += 4) {
+                const uint32_t e0 = ent[i], e1 = ent[i + 1], e2 = ent[i + 2], e3 = ent[i + 3];
+                const V v0 = tile[e0 & 0xffffu], v1 = tile[e1 & 0xffffu], v2 = tile[e2 & 0xffffu], v3 = tile[e3 & 0xffffu];
+                Bin *q0 = mybins + (e0 >> 16) * kRbRows + r;
+                if (!is_nan(v0)) { Bin b = *q0; b.add(v0); *q0 = b; }
+                Bin *q1 = mybins + (e1 >> 16) * kRbRows + r;
+                if (!is_nan(v1)) { Bin b = *q1; b.add(v1); *q1 = b; }
+                Bin *q2 = mybins + (e2 >> 16) * kRbRows + r;
+                if (!is_nan(v2)) { Bin b = *q2; b.add(v2); *q2 = b; }
+                Bin *q3 = mybins + (e3 >> 16) * kRbRows + r;
+                if (!is_nan(v3)) { Bin b = *q3; b.add(v3); *q3 = b; }
+            }
+            for (; i < b1; i++) {
+                const uint32_t e = ent[i];
+                const V v = tile[e & 0xffffu];
+                Bin *q = mybins + (e >> 16) * kRbRows + r;
+                if (!is_nan(v)) { Bin b = *q; b.add(v); *q = b; }
+            }
+        }
+        __syncthreads();  // everyone is done with stage st before it is refilled
+    }
+
+    // ---- flush bins into the 8-byte workspace channels
+    Acc *c0p = reinterpret_cast<Acc *>(p.ws_ch[0]);
+    Acc *c1p = reinterpret_cast<Acc *>(p.ws_ch[1]);
+    long long *c2p = reinterpret_cast<long long *>(p.ws_ch[2]);
+    const bool atomic = p.nseg > 1;
+    for (int idx = tid; idx < K * kRbRows; idx += kRbThreads) {
+        const int rr = idx / K, k = idx - rr * K;  // consecutive threads -> consecutive labels
+        if (rr >= nrows) continue;
+        Bin b = bins[k * kRbRows + rr];
+        if (p.priv) {
+            for (int s2 = 1; s2 < kRbSub; s2++) b.merge(bins[(size_t)s2 * K * kRbRows + k * kRbRows + rr]);
+        }
+        const size_t o = (size_t)(r0 + rr) * K + k;
+        RbFlush<V, CLS>::flush(b, c0p + o, c1p + o, c2p + o, atomic);
+    }
+}
+
+template <typename A>
+__device__ __forceinline__ void rb_put(A *p, A v, bool atomic) {
+    if (atomic) {
+        if (sizeof(A) == 8 && std::is_floating_point<A>::value)
+            atomicAdd(reinterpret_cast<double *>(p), (double)v);
+        else
+            atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+    } else {
+        *p = *p + v;  // the workspace was initialised (and may hold earlier shards)
+    }
+}
+
+template <typename V>
+struct RbFlush<V, RB_SUM> {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, RB_SUM> &b, A *c0, A *, long long *, bool at) {
+        rb_put(c0, (A)b.s, at);
+    }
+};
+template <typename V>
+struct RbFlush<V, RB_SUMSQ> {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, RB_SUMSQ> &b, A *c0, A *, long long *, bool at) {
+        rb_put(c0, (A)b.s, at);
+    }
+};
+template <typename V>
+struct RbFlush<V, RB_COUNT> {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, RB_COUNT> &b, A *, A *, long long *c2, bool at) {
+        rb_put(c2, (long long)b.c, at);
+    }
+};
+template <typename V>
+struct RbFlush<V, RB_MEAN> {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, RB_MEAN> &b, A *c0, A *, long long *c2, bool at) {
+        rb_put(c0, (A)b.s, at);
+        rb_put(c2, (long long)b.c, at);
+    }
+};
+template <typename V>
+struct RbFlush<V, RB_VAR> {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, RB_VAR> &b, A *c0, A *c1, long long *c2, bool at) {
+        rb_put(c0, (A)b.s, at);
+        rb_put(c1, (A)b.ss, at);
+        rb_put(c2, (long long)b.c, at);
+    }
+};
+
+// ------------------------------------------------------------------------------------ host
+inline int rb_class_of(int op) {
+    switch (op) {
+        case NBG_GROUP_NANSUM:
+            return RB_SUM;
+        case NBG_GROUP_NANCOUNT:
+            return RB_COUNT;
+        case NBG_GROUP_NANMEAN:
+            return RB_MEAN;
+        case NBG_GROUP_NANSUM_OF_SQUARES:
+            return RB_SUMSQ;
+        case NBG_GROUP_NANVAR:
+        case NBG_GROUP_NANSTD:
+            return RB_VAR;
+        default:
+            return -1;
+    }
+}
+
+struct RbGeometry {
+    bool ok;
+    int C, priv, ntiles, nseg, tiles_per_seg;
+    size_t smem, plan_bytes;
+};
+
+template <typename V, int CLS>
+static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
+    RbGeometry g = {};
+    constexpr int PER16 = 16 / (int)sizeof(V);
+    if (K <= 0 || K > 65535 || n <= 0 || n >= ((int64_t)1 << 31) || (n % PER16) != 0 || rows < 1) return g;
+    const int words = (int)(sizeof(RbBin<V, CLS>) / sizeof(V));
+    g.priv = (K * words <= 64) ? 1 : 0;
+    const int candidates[3] = {sizeof(V) == 4 ? 1024 : 512, sizeof(V) == 4 ? 512 : 256, sizeof(V) == 4 ? 256 : 128};
+    // prefer two CTAs per SM (<= ~110 KB), else whatever fits
+    for (int pass = 0; pass < 2 && !g.ok; pass++) {
+        for (int c = 0; c < 3; c++) {
+            const size_t s = rb_smem_bytes<V, CLS>((int)K, candidates[c], g.priv);
+            if (s <= (pass == 0 ? (size_t)110 * 1024 : kMaxSmem)) {
+                g.C = candidates[c];
+                g.smem = s;
+                g.ok = true;
+                break;
+            }
+        }
+    }
+    if (!g.ok) return g;
+    g.ntiles = (int)((n + g.C - 1) / g.C);
+    const int64_t groups = (rows + kRbRows - 1) / kRbRows;
+    // enough CTAs for ~8 waves of 2 CTAs/SM; whole rows per CTA (bit-exact order) when possible
+    const int64_t want = (int64_t)kNumSMs * 2 * 8;
+    int64_t nseg = groups >= want ? 1 : (want + groups - 1) / groups;
+    if (nseg > g.ntiles) nseg = g.ntiles;
+    if (nseg < 1) nseg = 1;
+    g.tiles_per_seg = (int)((g.ntiles + nseg - 1) / nseg);
+    g.nseg = (g.ntiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
+    g.plan_bytes = (size_t)g.ntiles * (kRbHdr + g.C) * 4 + 256;
+    return g;
+}
+
+template <typename V, typename L, int CLS>
+static int rb_launch(const V *values, const L *labels, void *ws_ch[3], void *scratch, size_t scratch_bytes,
+                     int64_t rows, int64_t n, int64_t K, cudaStream_t stream, bool *handled) {
+    *handled = false;
+    const RbGeometry g = rb_geometry<V, CLS>(rows, n, K);
+    if (!g.ok || scratch == nullptr || scratch_bytes < g.plan_bytes) return NBG_OK;
+    if (((uintptr_t)values & 15) != 0) return NBG_OK;
+    uint32_t *plan = reinterpret_cast<uint32_t *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    const size_t plan_smem = (size_t)(2 * K + 1) * 4 + (size_t)2 * g.C * 4 + 16;
+    auto pk = group_plan_kernel<L>;
+    int rc = allow_big_smem(pk, "nbg_group(plan): cudaFuncSetAttribute");
+    if (rc) return rc;
+    pk<<<(unsigned)g.ntiles, 256, plan_smem, stream>>>(labels, n, (int)K, g.C, g.priv, plan);
+    rc = check_launch("nbg_group(plan)");
+    if (rc) return rc;
+    RbParams p;
+    p.values = values;
+    p.plan = plan;
+    p.ws_ch[0] = ws_ch[0], p.ws_ch[1] = ws_ch[1], p.ws_ch[2] = ws_ch[2];
+    p.rows = rows, p.n = n, p.K = (int)K, p.C = g.C;
+    p.ntiles = g.ntiles, p.tiles_per_seg = g.tiles_per_seg, p.nseg = g.nseg, p.priv = g.priv;
+    const int64_t groups = (rows + kRbRows - 1) / kRbRows;
+    if (groups * g.nseg > INT32_MAX) return NBG_OK;
+    auto kern = group_rowbins_kernel<V, CLS>;
+    rc = allow_big_smem(kern, "nbg_group(rowbins): cudaFuncSetAttribute");
+    if (rc) return rc;
+    kern<<<(unsigned)(groups * g.nseg), kRbThreads, g.smem, stream>>>(p);
+    rc = check_launch("nbg_group(rowbins)");
+    if (rc) return rc;
+    *handled = true;
+    return NBG_OK;
+}
+
+}  // namespace nbg

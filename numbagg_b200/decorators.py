@@ -311,7 +311,7 @@ def run_group(name: str, values: torch.Tensor, labels: torch.Tensor, num_labels:
     lcode = _NBG_DTYPE[dev.np_dtype_of(labels)]
     rows, n = values.shape
     out = torch.empty((rows, num_labels), dtype=values.dtype, device=values.device)
-    ws_bytes = L.nbg_group_workspace_bytes(code, vcode, rows, num_labels)
+    ws_bytes = L.nbg_group_workspace_bytes(code, vcode, rows, n, num_labels)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=values.device)
     rc = L.nbg_group(
         code, vcode, lcode, dev.ptr(values), dev.ptr(labels), int(labels_per_row), dev.ptr(out),
