@@ -21,7 +21,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libnbg_b200.so")
 SOURCES = ["nbg_abi.cu", "nbg_move.cu", "nbg_move_exp.cu", "nbg_fill.cu", "nbg_group.cu"]
-HEADERS = ["nbg_common.cuh", os.path.join("..", "..", "include", "nbg_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "nbg_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -5,17 +5,17 @@
 // Idea: because all rows share the labels, the scatter pattern can be resolved ONCE per call
 // and then replayed for every row without atomics.
 //   plan kernel (labels only, O(n)): for every tile of C columns, the valid columns stably
-//     sorted by label, packed as (label << 16 | column), plus 33 boundaries that cut the
-//     sorted list into 32 label-aligned, balanced ranges.
+//     sorted by label, packed as (label << 16 | column), plus 65 boundaries that cut the
+//     sorted list into 64 label-aligned, balanced ranges.
 //   main kernel: a CTA owns 8 rows x a column segment.  It streams row tiles (and the tile's
-//     plan) through a 2-stage TMA ring into shared memory.  Its 256 threads form 32 sub-warps
-//     of 8 lanes: lane = row, sub-warp = one of the 32 label ranges.  A sub-warp walks its
+//     plan) through a 2-stage TMA ring into shared memory.  Its 512 threads form 64 sub-warps
+//     of 8 lanes: lane = row, sub-warp = one of the 64 label ranges.  A sub-warp walks its
 //     range; every entry is "bins[label][row] (+)= tile[row][column]" on a shared-memory bin
 //     that no other lane can touch during this tile (ranges are label-aligned), so the
 //     update is a plain load/add/store, and every bin receives its elements in ascending
 //     column order -- the reference's own summation order (grouped.py:31-40), which makes the
 //     float32 results bit-identical to numbagg's when a CTA covers whole rows.
-//   Few labels (K * words <= 64): ranges are cut evenly instead and each sub-warp gets
+//   Few labels (K * words <= 32): ranges are cut evenly instead and each sub-warp gets
 //     private bins that are summed at the end.
 // Bins are V-typed (accumulation in the OUTPUT dtype, like the reference) and are flushed
 // into the common 8-byte workspace at the end (plain stores for one segment per row,
@@ -27,9 +27,9 @@
 namespace nbg {
 
 constexpr int kRbRows = 8;    // rows per CTA = lanes per sub-warp
-constexpr int kRbSub = 32;    // sub-warps per CTA
-constexpr int kRbThreads = kRbRows * kRbSub;
-constexpr int kRbHdr = 36;    // u32 words per tile header: bounds[33], count, 2 pad (144 B)
+constexpr int kRbSub = 64;    // sub-warps per CTA
+constexpr int kRbThreads = kRbRows * kRbSub;  // 512
+constexpr int kRbHdr = 68;    // u32 words per tile header: bounds[65], count, 2 pad (272 B)
 
 enum RbClass { RB_SUM = 0, RB_COUNT = 1, RB_MEAN = 2, RB_SUMSQ = 3, RB_VAR = 4 };
 
@@ -120,9 +120,9 @@ __global__ void __launch_bounds__(256) group_plan_kernel(const L *__restrict__ l
         }
         out[tid] = (uint32_t)b;
     }
-    if (tid == 33) out[33] = (uint32_t)count;
-    if (tid == 34) out[34] = 0;
-    if (tid == 35) out[35] = 0;
+    if (tid == kRbSub + 1) out[kRbSub + 1] = (uint32_t)count;
+    if (tid == kRbSub + 2) out[kRbSub + 2] = 0;
+    if (tid == kRbSub + 3) out[kRbSub + 3] = 0;
     for (int j = tid; j < C; j += 256) out[kRbHdr + j] = sent[j];
 }
 
@@ -175,21 +175,22 @@ template <typename V>
 struct RbBin<V, RB_SUM> {
     V s;
     __device__ __forceinline__ void zero() { s = (V)0; }
-    __device__ __forceinline__ void add(V v) { s = v_add(s, v); }
+    // `ok` false (NaN observation): adds +0, which leaves every reachable sum unchanged
+    __device__ __forceinline__ void add(V v, bool ok) { s = v_add(s, ok ? v : (V)0); }
     __device__ __forceinline__ void merge(const RbBin &o) { s = v_add(s, o.s); }
 };
 template <typename V>
 struct RbBin<V, RB_SUMSQ> {
     V s;
     __device__ __forceinline__ void zero() { s = (V)0; }
-    __device__ __forceinline__ void add(V v) { s = v_add(s, v_sq(v)); }
+    __device__ __forceinline__ void add(V v, bool ok) { s = v_add(s, v_sq(ok ? v : (V)0)); }
     __device__ __forceinline__ void merge(const RbBin &o) { s = v_add(s, o.s); }
 };
 template <typename V>
 struct RbBin<V, RB_COUNT> {
     typename RbCounter<V>::type c;
     __device__ __forceinline__ void zero() { c = 0; }
-    __device__ __forceinline__ void add(V) { c += 1; }
+    __device__ __forceinline__ void add(V, bool ok) { c += ok ? 1 : 0; }
     __device__ __forceinline__ void merge(const RbBin &o) { c += o.c; }
 };
 template <typename V>
@@ -200,9 +201,9 @@ struct alignas(2 * sizeof(V)) RbBin<V, RB_MEAN> {
         s = (V)0;
         c = 0;
     }
-    __device__ __forceinline__ void add(V v) {
-        s = v_add(s, v);
-        c += 1;
+    __device__ __forceinline__ void add(V v, bool ok) {
+        s = v_add(s, ok ? v : (V)0);
+        c += ok ? 1 : 0;
     }
     __device__ __forceinline__ void merge(const RbBin &o) {
         s = v_add(s, o.s);
@@ -219,10 +220,11 @@ struct alignas(4 * sizeof(V)) RbBin<V, RB_VAR> {
         c = 0;
         pad = 0;
     }
-    __device__ __forceinline__ void add(V v) {
-        s = v_add(s, v);
-        ss = v_add(ss, v_sq(v));
-        c += 1;
+    __device__ __forceinline__ void add(V v, bool ok) {
+        const V m = ok ? v : (V)0;
+        s = v_add(s, m);
+        ss = v_add(ss, v_sq(m));
+        c += ok ? 1 : 0;
     }
     __device__ __forceinline__ void merge(const RbBin &o) {
         s = v_add(s, o.s);
@@ -308,35 +310,50 @@ __global__ void __launch_bounds__(kRbThreads) group_rowbins_kernel(RbParams p) {
     };
 
     if (tid == 0 && t_beg < t_end) issue(t_beg, 0);
-    Bin *mybins = bins + (p.priv ? (size_t)sub * K * kRbRows : 0);
+    // 32-bit shared-window addresses: the RMW stream below must compile to LDS/STS on
+    // register+immediate addresses, not to generic loads
+    const uint32_t bins_s = smem_u32(bins) + (uint32_t)((p.priv ? (size_t)sub * K * kRbRows : 0) + r) * (uint32_t)sizeof(Bin);
+    constexpr uint32_t kLabelStep = kRbRows * (uint32_t)sizeof(Bin);  // bytes between labels
+    auto bin_at = [&](uint32_t e) -> Bin * {
+        return reinterpret_cast<Bin *>(__cvta_shared_to_generic(bins_s + (e >> 16) * kLabelStep));
+    };
     for (int t = t_beg, it = 0; t < t_end; t++, it++) {
         const int st = it & 1;
         if (tid == 0 && t + 1 < t_end) issue(t + 1, st ^ 1);  // stage st^1 was drained last iteration
         mbar_wait(&bar[st], (uint32_t)((it >> 1) & 1));
-        const unsigned char *sb = stage0 + (size_t)st * stage_bytes;
-        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(sb);
-        const uint32_t *ent = hdr + kRbHdr;
-        const V *tile = reinterpret_cast<const V *>(sb + (size_t)(kRbHdr + C) * 4) + (size_t)r * stride;
+        const uint32_t sb = smem_u32(stage0 + (size_t)st * stage_bytes);
+        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(__cvta_shared_to_generic(sb));
+        const uint32_t ent_s = sb + kRbHdr * 4;
+        const uint32_t tile_s = sb + (uint32_t)(kRbHdr + C) * 4 + (uint32_t)r * (uint32_t)stride * (uint32_t)sizeof(V);
         const int b0 = (int)hdr[sub], b1 = (int)hdr[sub + 1];
+        auto ent_at = [&](int i) -> uint32_t {
+            return *reinterpret_cast<const uint32_t *>(__cvta_shared_to_generic(ent_s + (uint32_t)i * 4u));
+        };
+        auto val_at = [&](uint32_t e) -> V {
+            return *reinterpret_cast<const V *>(__cvta_shared_to_generic(tile_s + (e & 0xffffu) * (uint32_t)sizeof(V)));
+        };
         if (r < nrows) {
             int i = b0;
             for (; i + 4 <= b1; i += 4) {
-                const uint32_t e0 = ent[i], e1 = ent[i + 1], e2 = ent[i + 2], e3 = ent[i + 3];
-                const V v0 = tile[e0 & 0xffffu], v1 = tile[e1 & 0xffffu], v2 = tile[e2 & 0xffffu], v3 = tile[e3 & 0xffffu];
-                Bin *q0 = mybins + (e0 >> 16) * kRbRows + r;
-                if (!is_nan(v0)) { Bin b = *q0; b.add(v0); *q0 = b; }
-                Bin *q1 = mybins + (e1 >> 16) * kRbRows + r;
-                if (!is_nan(v1)) { Bin b = *q1; b.add(v1); *q1 = b; }
-                Bin *q2 = mybins + (e2 >> 16) * kRbRows + r;
-                if (!is_nan(v2)) { Bin b = *q2; b.add(v2); *q2 = b; }
-                Bin *q3 = mybins + (e3 >> 16) * kRbRows + r;
-                if (!is_nan(v3)) { Bin b = *q3; b.add(v3); *q3 = b; }
+                const uint32_t e0 = ent_at(i), e1 = ent_at(i + 1), e2 = ent_at(i + 2), e3 = ent_at(i + 3);
+                const V v0 = val_at(e0), v1 = val_at(e1), v2 = val_at(e2), v3 = val_at(e3);
+                // read-modify-write in entry order: consecutive entries may share a label
+                Bin *q0 = bin_at(e0);
+                { Bin b = *q0; b.add(v0, !is_nan(v0)); *q0 = b; }
+                Bin *q1 = bin_at(e1);
+                { Bin b = *q1; b.add(v1, !is_nan(v1)); *q1 = b; }
+                Bin *q2 = bin_at(e2);
+                { Bin b = *q2; b.add(v2, !is_nan(v2)); *q2 = b; }
+                Bin *q3 = bin_at(e3);
+                { Bin b = *q3; b.add(v3, !is_nan(v3)); *q3 = b; }
             }
             for (; i < b1; i++) {
-                const uint32_t e = ent[i];
-                const V v = tile[e & 0xffffu];
-                Bin *q = mybins + (e >> 16) * kRbRows + r;
-                if (!is_nan(v)) { Bin b = *q; b.add(v); *q = b; }
+                const uint32_t e = ent_at(i);
+                const V v = val_at(e);
+                Bin *q = bin_at(e);
+                Bin b = *q;
+                b.add(v, !is_nan(v));
+                *q = b;
             }
         }
         __syncthreads();  // everyone is done with stage st before it is refilled
@@ -441,7 +458,7 @@ static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
     constexpr int PER16 = 16 / (int)sizeof(V);
     if (K <= 0 || K > 65535 || n <= 0 || n >= ((int64_t)1 << 31) || (n % PER16) != 0 || rows < 1) return g;
     const int words = (int)(sizeof(RbBin<V, CLS>) / sizeof(V));
-    g.priv = (K * words <= 64) ? 1 : 0;
+    g.priv = (K * words <= 32) ? 1 : 0;
     const int candidates[3] = {sizeof(V) == 4 ? 1024 : 512, sizeof(V) == 4 ? 512 : 256, sizeof(V) == 4 ? 256 : 128};
     // prefer two CTAs per SM (<= ~110 KB), else whatever fits
     for (int pass = 0; pass < 2 && !g.ok; pass++) {
@@ -458,9 +475,11 @@ static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
     if (!g.ok) return g;
     g.ntiles = (int)((n + g.C - 1) / g.C);
     const int64_t groups = (rows + kRbRows - 1) / kRbRows;
-    // enough CTAs for ~8 waves of 2 CTAs/SM; whole rows per CTA (bit-exact order) when possible
-    const int64_t want = (int64_t)kNumSMs * 2 * 8;
-    int64_t nseg = groups >= want ? 1 : (want + groups - 1) / groups;
+    // Whole rows per CTA (=> the reference's exact summation order) once there are >= 4 waves
+    // of row groups; otherwise cut rows into column segments for ~8 waves and merge the
+    // partial bins with atomics.
+    const int64_t slots = (int64_t)kNumSMs * 2;
+    int64_t nseg = groups >= 4 * slots ? 1 : (8 * slots + groups - 1) / groups;
     if (nseg > g.ntiles) nseg = g.ntiles;
     if (nseg < 1) nseg = 1;
     g.tiles_per_seg = (int)((g.ntiles + nseg - 1) / nseg);
