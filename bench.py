@@ -290,38 +290,38 @@ def run_ours(args, wl):
     ms_step = ms_total / args.steps
     value = world * elements / (ms_step * 1e-3)
 
-    # ---- e2e through the public numpy API on a bounded host batch (pinned in, pinned out)
-    erows = rows if rows * n * a.element_size() <= (4 << 30) else max(1, int((4 << 30) // (n * a.element_size())))
-    en = n if rows > 1 or family == "group1d" and False else n
-    if rows == 1:
-        en = min(n, (4 << 30) // a.element_size() // (2 if family == "group1d" else 1))
+    # ---- e2e through the public numpy API on a bounded host batch: every step copies the
+    # pinned host inputs to the device, runs the kernels and copies the result back to the host
+    budget = 4 << 30  # bytes of host input per step
+    item = a.element_size()
+    if rows > 1:
+        erows = max(1, min(rows, budget // (n * item * len(tensors))))
+        en = n
+    else:
         erows = 1
+        en = min(n, budget // (item * len(tensors) + (8 if family == "group1d" else 0)))
+        en -= en % 4
     e_args, e_kwargs = host_batch(family, func, dt, erows, en, params, seed=rank)
     pinned = []
     for x in e_args:
         px = nb.empty_pinned(x.shape, x.dtype)
         px[...] = x
         pinned.append(px)
+    del e_args
     f_public = getattr(nb, func)
     res = f_public(*pinned, **e_kwargs)
-    out_pinned = nb.empty_pinned(res.shape, res.dtype)
     h2d = sum(x.nbytes for x in pinned)
-    d2h = out_pinned.nbytes
-
-    def step_e2e():
-        r = f_public(*pinned, **e_kwargs)  # H2D + kernels + D2H inside
-        out_pinned[...] = r if False else r  # result already on host
-        return r
+    d2h = res.nbytes
 
     for _ in range(2):
-        step_e2e()
+        f_public(*pinned, **e_kwargs)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e_steps = max(2, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(e_steps):
-        step_e2e()
+        res = f_public(*pinned, **e_kwargs)  # H2D + kernels + D2H (returns a host array)
     torch.cuda.synchronize()
     e_s = (time.perf_counter() - t0) / e_steps
     if world > 1:

@@ -81,11 +81,19 @@ def to_device(x, dtype: np.dtype | None = None, device: torch.device | None = No
 
 
 def to_host(t: torch.Tensor, out: np.ndarray | None = None) -> np.ndarray:
+    """Device -> host.  Without `out` the result lands in page-locked memory from torch's
+    caching host allocator (full-speed D2H; the numpy array keeps the buffer alive)."""
     if out is not None:
         dst = torch.from_numpy(out)
         dst.copy_(t, non_blocking=False)
         return out
-    return t.cpu().numpy()
+    if t.numel() == 0:
+        return t.cpu().numpy()
+    src = t if t.is_contiguous() else t.contiguous()
+    host = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+    host.copy_(src, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
 
 
 def empty_pinned(shape, dtype) -> np.ndarray:

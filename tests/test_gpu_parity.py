@@ -1,0 +1,367 @@
+"""CUDA path vs the oracle (oracle/nbg_oracle.c, pinned bit-for-bit to the reference by
+tests/test_oracle_golden.py) on seeded inputs at sizes the oracle finishes in seconds, plus
+size-independent properties at larger sizes.  Everything goes through the public drop-in API
+(numpy in / numpy out) or the C ABI behind it.  Tolerances: tests/_parity.py (north_star)."""
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests._parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import numbagg_b200
+
+    return numbagg_b200
+
+
+def fixture_array(shape, nan_frac=0.1, seed=0, dtype=np.float64):
+    a = np.random.RandomState(seed).rand(*shape)
+    return np.where(a > nan_frac, a, np.nan).astype(dtype)
+
+
+ONE = ["move_mean", "move_sum", "move_std", "move_var"]
+TWO = ["move_cov", "move_corr"]
+
+
+def _scale(func, arrs, window=1):
+    m = max(float(np.nanmax(np.abs(a))) for a in arrs)
+    if "corr" in func:
+        return 1.0
+    s = m * m if any(t in func for t in ("var", "std", "cov")) else m
+    return s * (window if func == "move_sum" else 1)
+
+
+# ------------------------------------------------------------------------------- moving
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("window,min_count", [(1, None), (2, 1), (20, 1), (32, 5), (33, None), (100, 50), (1000, 500), (4096, 1), (5000, 10), (20000, 1)])
+def test_move_vs_oracle_tiles(nb, dtype, window, min_count):
+    # 20000 columns: several row tiles per row for both dtypes; windows on both sides of the
+    # direct / delta-scan switch (32), of the reciprocal-table limit (4096) and window == n
+    a = fixture_array((6, 20000), dtype=dtype, seed=1)
+    b = (a.astype(np.float64) ** 2 + 1).astype(dtype)
+    for f in ONE:
+        got = getattr(nb, f)(a, window=window, min_count=min_count)
+        exp = getattr(oracle, f)(a, window=window, min_count=min_count)
+        assert_parity(f, got, exp, scale=_scale(f, [a], window))
+    for f in TWO:
+        got = getattr(nb, f)(a, b, window=window, min_count=min_count)
+        exp = getattr(oracle, f)(a, b, window=window, min_count=min_count)
+        assert_parity(f, got, exp, scale=_scale(f, [a, b], window))
+
+
+@pytest.mark.parametrize("n", [1, 2, 16, 17, 4607, 4608, 4609, 8703, 8704, 8705, 10001])
+def test_move_ragged_lengths(nb, n):
+    # tile sizes are 4608 (float64) and 8704 (float32): hit the boundaries and odd row pitches
+    for dtype in (np.float64, np.float32):
+        a = fixture_array((3, n), dtype=dtype, seed=n)
+        w = min(n, 20)
+        for f in ("move_mean", "move_sum", "move_std"):
+            got = getattr(nb, f)(a, window=w, min_count=1)
+            exp = getattr(oracle, f)(a, window=w, min_count=1)
+            assert_parity(f, got, exp, scale=_scale(f, [a], w))
+
+
+def test_move_axes_and_layouts(nb):
+    a = fixture_array((7, 33, 50), seed=3)
+    for axis in (0, 1, 2, -2):
+        for f in ("move_mean", "move_var"):
+            got = getattr(nb, f)(a, window=5, min_count=2, axis=axis)
+            exp = getattr(oracle, f)(a, window=5, min_count=2, axis=axis)
+            assert_parity(f, got, exp, scale=_scale(f, [a]))
+    # F-ordered, transposed and strided views: no layout may change values
+    af = np.asfortranarray(a[0])
+    for arr in (af, a[0].T, a[:, ::2, 1:40:3], a[::-1]):
+        got = nb.move_sum(arr, window=3, min_count=1, axis=-1)
+        exp = oracle.move_sum(arr, window=3, min_count=1, axis=-1)
+        assert_parity("move_sum", got, exp, scale=3.0)
+        got = nb.move_sum(arr, window=3, min_count=1, axis=0)
+        exp = oracle.move_sum(arr, window=3, min_count=1, axis=0)
+        assert_parity("move_sum", got, exp, scale=3.0)
+
+
+def test_move_long_columns_other_axis(nb):
+    # core axis = 0 of a C-contiguous matrix: column-walk kernel, segmented along the core axis
+    a = fixture_array((30000, 37), seed=4)
+    b = a**2 + 1
+    for f in ("move_mean", "move_std"):
+        got = getattr(nb, f)(a, window=100, min_count=10, axis=0)
+        exp = getattr(oracle, f)(a, window=100, min_count=10, axis=0)
+        assert_parity(f, got, exp, scale=_scale(f, [a]))
+    got = nb.move_corr(a, b, window=100, min_count=10, axis=0)
+    assert_parity("move_corr", got, oracle.move_corr(a, b, window=100, min_count=10, axis=0), scale=1.0)
+
+
+def test_move_dtype_rules_and_tensors(nb):
+    import torch
+
+    ints = np.arange(40).reshape(4, 10)
+    got = nb.move_mean(ints, window=3)
+    assert got.dtype == np.float64
+    assert_parity("move_mean", got, oracle.move_mean(ints, window=3))
+    h = np.arange(10, dtype=np.float16)
+    assert nb.move_mean(h, window=3).dtype == np.float32
+    # float32 stability tests of the reference (test_moving.py:180-192)
+    arr = np.array([0.1, 0.2, 0.3] * 100, dtype=np.float32)
+    np.testing.assert_array_equal(nb.move_mean(arr, window=1), arr)
+    tiled = np.tile(np.arange(10, dtype=np.float32) * 1.7, 30)
+    assert nb.move_sum(tiled, window=10)[-1] == np.sum(tiled[:10], dtype=np.float64).astype(np.float32)
+    # CUDA tensors in -> CUDA tensor out, same stream, no host round trip
+    t = torch.from_numpy(fixture_array((5, 300))).cuda()
+    r = nb.move_mean(t, window=7, min_count=1)
+    assert isinstance(r, torch.Tensor) and r.is_cuda and r.dtype == torch.float64
+    assert_parity("move_mean", r.cpu().numpy(), oracle.move_mean(t.cpu().numpy(), window=7, min_count=1))
+
+
+def test_move_all_nan_and_inf(nb):
+    a = np.full((2, 5000), np.nan)
+    for f in ONE:
+        np.testing.assert_array_equal(getattr(nb, f)(a, window=10, min_count=0), getattr(oracle, f)(a, window=10, min_count=0))
+    x = np.array([1.0, np.inf, 2.0, -np.inf, 3.0, 4.0, 5.0])
+    np.testing.assert_array_equal(nb.move_sum(x, window=2, min_count=1), oracle.move_sum(x, window=2, min_count=1))
+
+
+# --------------------------------------------------------------------------- exp moving
+EXP_ONE = ["move_exp_nancount", "move_exp_nanmean", "move_exp_nansum", "move_exp_nanvar", "move_exp_nanstd"]
+EXP_TWO = ["move_exp_nancov", "move_exp_nancorr"]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("alpha", [0.5, 0.1, 0.001])
+def test_move_exp_vs_oracle_long_rows(nb, dtype, alpha):
+    # 200k columns: ~45 (float64) / ~24 (float32) chained tiles per row, 30 % NaN (config 3)
+    a = fixture_array((3, 200_000), nan_frac=0.3, dtype=dtype, seed=5)
+    b = (a.astype(np.float64) ** 2 + 1).astype(dtype)
+    al = np.float32(alpha) if dtype == np.float32 else alpha
+    for f in EXP_ONE:
+        for mw in (0, 0.5):
+            got = getattr(nb, f)(a, alpha=al, min_weight=mw)
+            exp = getattr(oracle, f)(a, alpha=al, min_weight=mw)
+            assert_parity(f, got, exp, scale=(1.0 / alpha if f == "move_exp_nansum" else 1.0))
+    for f in EXP_TWO:
+        got = getattr(nb, f)(a, b, alpha=al)
+        exp = getattr(oracle, f)(a, b, alpha=al)
+        assert_parity(f, got, exp, scale=4.0)
+
+
+def test_move_exp_alpha_forms_and_axes(nb):
+    a = fixture_array((5, 9000), seed=6)
+    al1 = np.random.RandomState(7).rand(9000) * 0.9 + 0.05
+    aln = np.random.RandomState(8).rand(5, 9000) * 0.9 + 0.05
+    for f in EXP_ONE:
+        for al in (al1, aln):
+            assert_parity(f, getattr(nb, f)(a, alpha=al), getattr(oracle, f)(a, alpha=al), scale=20.0)
+        got = getattr(nb, f)(a.T.copy(), alpha=aln.T.copy(), axis=0)
+        assert_parity(f, got, getattr(oracle, f)(a.T.copy(), alpha=aln.T.copy(), axis=0), scale=20.0)
+        got = getattr(nb, f)(a.T.copy(), alpha=0.3, axis=0)
+        assert_parity(f, got, getattr(oracle, f)(a.T.copy(), alpha=0.3, axis=0), scale=4.0)
+    # alpha with zeros: no decay, the look-back can never stop early
+    al0 = al1.copy()
+    al0[::3] = 0.0
+    assert_parity("move_exp_nansum", nb.move_exp_nansum(a, alpha=al0), oracle.move_exp_nansum(a, alpha=al0), scale=100.0)
+    # float32 data + python float alpha runs the float64 loop
+    a32 = a.astype(np.float32)
+    got = nb.move_exp_nanmean(a32, alpha=0.25)
+    assert got.dtype == np.float64
+    assert_parity("move_exp_nanmean", got, oracle.move_exp_nanmean(a32, alpha=0.25))
+
+
+def test_move_exp_leading_nans_across_tiles(nb):
+    a = fixture_array((2, 30000), nan_frac=0.3, seed=9)
+    a[:, :12000] = np.nan  # more than two whole tiles of NaN before the first observation
+    for f in EXP_ONE:
+        assert_parity(f, getattr(nb, f)(a, alpha=0.1), getattr(oracle, f)(a, alpha=0.1), scale=10.0)
+
+
+# -------------------------------------------------------------------------------- fills
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("limit", [None, 0, 1, 7, 5000, 40000])
+def test_fill_vs_oracle_bit_exact(nb, dtype, limit):
+    a = fixture_array((3, 100_000), nan_frac=0.3, dtype=dtype, seed=10)
+    a[1, 20_000:65_000] = np.nan  # a NaN run spanning many tiles
+    a[2, :] = np.nan
+    a[2, 77] = 3.5
+    for f in ("ffill", "bfill"):
+        got = getattr(nb, f)(a, limit=limit)
+        exp = getattr(oracle, f)(a, limit=limit)
+        assert got.dtype == exp.dtype
+        np.testing.assert_array_equal(got, exp)
+        got0 = getattr(nb, f)(a.T.copy(), limit=limit, axis=0)
+        np.testing.assert_array_equal(got0, exp.T)
+
+
+def test_fill_misc_dtypes(nb):
+    h = np.array([np.nan, 1, np.nan, 2], dtype=np.float16)
+    r = nb.ffill(h)
+    assert r.dtype == np.float16
+    np.testing.assert_array_equal(r, np.array([np.nan, 1, 1, 2], dtype=np.float16))
+    x = np.array([np.inf, np.nan, -np.inf, np.nan])
+    np.testing.assert_array_equal(nb.ffill(x), [np.inf, np.inf, -np.inf, -np.inf])
+    np.testing.assert_array_equal(nb.bfill(x), [np.inf, -np.inf, -np.inf, np.nan])
+
+
+# ------------------------------------------------------------------------------ grouped
+GROUP = oracle.GROUPED_FUNCS
+GROUP_FLOAT_ONLY = {"group_nanvar", "group_nanstd"}
+
+
+def _group_check(nb, f, values, labels, f32_sum_note=False, **kw):
+    got = getattr(nb, f)(values, labels, **kw)
+    exp = getattr(oracle, f)(values, labels, **kw)
+    mask = None
+    if exp.dtype.kind in "iu" and f in ("group_nanfirst", "group_nanlast", "group_nanargmax", "group_nanargmin", "group_nanmin", "group_nanmax"):
+        mask = oracle.group_nancount(values, labels, **kw) == 0
+    scale = None
+    if f in GROUP_FLOAT_ONLY:
+        scale = float(np.nanmax(np.abs(values))) ** 2
+    assert_parity(f, got, exp, scale=scale, int_empty_mask=mask)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("K", [3, 12, 300, 5000, 70000])
+def test_group_shared_labels_vs_oracle(nb, dtype, K):
+    # labels shared by all rows (axis=-1): few-label private bins, row-bins, and -- beyond the
+    # shared-memory bin table -- the atomic path; ~100 observations per group at most so the
+    # float32 reference itself is accurate to well below rtol
+    rows, n = 19, 4000
+    rs = np.random.RandomState(K)
+    v = np.round((fixture_array((rows, n), dtype=dtype, seed=K) - 0.4) * 8, 2).astype(dtype)
+    labels = rs.randint(-1, K + 2, size=n)  # includes skipped (-1) and out-of-range labels
+    for f in GROUP:
+        _group_check(nb, f, v, labels, num_labels=K, axis=-1)
+
+
+def test_group_rowbins_is_bit_exact_with_whole_rows(nb):
+    # >= 4 waves of 8-row groups => one CTA per row group walks whole rows in column order:
+    # float32 sums must then be IDENTICAL to the sequential reference, not just close
+    rows, n, K = 9600, 256, 37
+    v = fixture_array((rows, n), dtype=np.float32, seed=21)
+    labels = np.random.RandomState(21).randint(0, K, size=n)
+    for f in ("group_nansum", "group_nanmean", "group_nansum_of_squares", "group_nancount", "group_nanvar", "group_nanstd"):
+        got = getattr(nb, f)(v, labels, num_labels=K, axis=-1)
+        exp = getattr(oracle, f)(v, labels, num_labels=K, axis=-1)
+        np.testing.assert_array_equal(got, exp, err_msg=f)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32, np.int64])
+def test_group_axis_modes_and_dtypes(nb, dtype):
+    rs = np.random.RandomState(11)
+    if np.dtype(dtype).kind == "f":
+        v = fixture_array((6, 5, 40), dtype=dtype, seed=12)
+    else:
+        v = rs.randint(-9, 10, size=(6, 5, 40)).astype(dtype)
+    for f in GROUP:
+        if f in GROUP_FLOAT_ONLY and np.dtype(dtype).kind != "f":
+            continue
+        _group_check(nb, f, v, rs.randint(0, 4, size=40), axis=-1)
+        _group_check(nb, f, v, rs.randint(0, 3, size=6), axis=0)
+        _group_check(nb, f, v, rs.randint(-1, 5, size=(5, 40)), axis=(1, 2))
+        _group_check(nb, f, v, rs.randint(0, 7, size=(6, 5, 40)), axis=None)
+        _group_check(nb, f, v.reshape(-1), rs.randint(0, 7, size=v.size))
+
+
+def test_group_bool_narrow_ints_and_label_dtypes(nb):
+    rs = np.random.RandomState(13)
+    bv = rs.rand(500) > 0.5
+    bl = rs.randint(0, 4, size=500)
+    for f in ("group_nansum", "group_nanany", "group_nanall", "group_nancount", "group_nanmean"):
+        _group_check(nb, f, bv, bl)
+    v = fixture_array((300,), seed=14)
+    for ldt in (np.int8, np.int16, np.int32, np.int64):
+        _group_check(nb, "group_nansum", v, rs.randint(0, 5, size=300).astype(ldt))
+    i8 = rs.randint(-100, 100, size=400).astype(np.int8)
+    got = nb.group_nansum(i8, rs.randint(0, 3, size=400))
+    assert got.dtype == np.int8  # wrap-around accumulation in the values dtype
+    # num_labels inferred from labels.max()
+    got = nb.group_nanmax(v, np.array([0, 5] * 150))
+    assert got.shape == (6,)
+    # group axis goes LAST (SURVEY discrepancy table)
+    assert nb.group_nansum(np.arange(12.0).reshape(4, 3), np.array([0, 1, 0, 1]), axis=0).shape == (3, 2)
+
+
+def test_group_high_cardinality_1d(nb):
+    # config-5 style: per-element labels, many groups, global atomics
+    n, K = 3_000_000, 400_000
+    rs = np.random.RandomState(15)
+    v = fixture_array((n,), seed=16)
+    labels = rs.randint(0, K, size=n)
+    for f in ("group_nanargmax", "group_nanargmin", "group_nanfirst", "group_nanlast", "group_nanvar", "group_nansum", "group_nanmin", "group_nancount"):
+        _group_check(nb, f, v, labels, num_labels=K)
+
+
+# ---------------------------------------------------------------------------- properties
+def test_properties_large_fill(nb):
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand((1, 100_000_000), generator=g, device="cuda", dtype=torch.float64)
+    x[x <= 0.3] = float("nan")
+    x[0, :5] = float("nan")
+    f = nb.ffill(x)
+    # idempotence, no NaN after the first valid value, untouched valid values
+    assert torch.equal(torch.nan_to_num(nb.ffill(f), nan=-1.0), torch.nan_to_num(f, nan=-1.0))
+    first_valid = int(torch.nonzero(~torch.isnan(x[0]))[0])
+    assert not torch.isnan(f[0, first_valid:]).any() and torch.isnan(f[0, :first_valid]).all()
+    valid = ~torch.isnan(x)
+    assert torch.equal(f[valid], x[valid])
+    # bfill is ffill of the mirrored row
+    b = nb.bfill(x)
+    bm = nb.ffill(torch.flip(x, dims=[1]))
+    assert torch.equal(torch.nan_to_num(torch.flip(bm, dims=[1]), nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+    # limit: every filled run is at most `limit` long
+    fl = nb.ffill(x, limit=2)
+    filled = (~torch.isnan(fl)) & torch.isnan(x)
+    run3 = filled[0, 2:] & filled[0, 1:-1] & filled[0, :-2]
+    assert not run3.any()
+
+
+def test_properties_large_move_and_exp(nb):
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand((64, 1_000_000), generator=g, device="cuda", dtype=torch.float32)
+    x[x <= 0.1] = float("nan")
+    # window=1 mean is the identity (exact, reference test_moving.py:180-192)
+    m1 = nb.move_mean(x, window=1, min_count=1)
+    assert torch.equal(torch.nan_to_num(m1, nan=-1.0), torch.nan_to_num(x, nan=-1.0))
+    # causality / tiling independence: results on a prefix equal the prefix of the results,
+    # and shifting the row start (different tile alignment) changes nothing beyond rounding
+    full = nb.move_std(x, window=1000, min_count=500)
+    part = nb.move_std(x[:, :333_333].contiguous(), window=1000, min_count=500)
+    torch.testing.assert_close(part, full[:, :333_333], rtol=1e-5, atol=1e-6, equal_nan=True)
+    e_full = nb.move_exp_nanmean(x, alpha=np.float32(0.1))
+    e_part = nb.move_exp_nanmean(x[:, :333_333].contiguous(), alpha=np.float32(0.1))
+    torch.testing.assert_close(e_part, e_full[:, :333_333], rtol=1e-5, atol=1e-6, equal_nan=True)
+    # mean * count == sum  (count from min_count-free move_sum of the validity mask)
+    s = nb.move_sum(x, window=50, min_count=1)
+    mean = nb.move_mean(x, window=50, min_count=1)
+    cnt = nb.move_sum((~torch.isnan(x)).to(torch.float32), window=50, min_count=1)
+    torch.testing.assert_close(mean * cnt, s, rtol=1e-5, atol=1e-5, equal_nan=True)
+
+
+def test_properties_large_group(nb):
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(2)
+    rows, n, K = 2048, 200_000, 1000
+    v = torch.rand((rows, n), generator=g, device="cuda", dtype=torch.float32)
+    v[v <= 0.1] = float("nan")
+    labels = torch.randint(-1, K, (n,), generator=g, device="cuda")
+    s = nb.group_nansum(v, labels, num_labels=K, axis=-1)
+    c = nb.group_nancount(v, labels, num_labels=K, axis=-1)
+    keep = (labels >= 0)[None, :] & ~torch.isnan(v)
+    # checksum of checksums: group sums add up to the masked row sums; counts are exact
+    row_sum = torch.where(keep, v, torch.zeros_like(v)).to(torch.float64).sum(dim=1)
+    torch.testing.assert_close(s.to(torch.float64).sum(dim=1), row_sum, rtol=1e-5, atol=0)
+    assert torch.equal(c.sum(dim=1).to(torch.int64), keep.sum(dim=1))
+    mean = nb.group_nanmean(v, labels, num_labels=K, axis=-1)
+    torch.testing.assert_close(mean * c, s, rtol=1e-5, atol=1e-6, equal_nan=True)
+    mx = nb.group_nanmax(v, labels, num_labels=K, axis=-1)
+    am = nb.group_nanargmax(v, labels, num_labels=K, axis=-1)
+    ok = ~torch.isnan(am)
+    picked = torch.gather(v, 1, torch.nan_to_num(am, nan=0.0).to(torch.int64))
+    assert torch.equal(picked[ok], mx[ok])
