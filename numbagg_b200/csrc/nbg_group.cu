@@ -86,20 +86,25 @@ __device__ __forceinline__ void atomic_add_acc(double *p, double v) { atomicAdd(
 __device__ __forceinline__ void atomic_add_acc(long long *p, long long v) {
     atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
 }
-__device__ __forceinline__ void atomic_mul_acc(double *p, double v) {
+// Products accumulate with a CAS loop.  float32 products round (and overflow / underflow) in
+// float32 after every factor, like the reference's in-dtype accumulation (grouped.py:124-132);
+// the slot still holds a double.  Integers multiply modulo 2^64 (truncated at the end).
+template <typename V>
+__device__ __forceinline__ void atomic_mul_acc(void *p, V v) {
     unsigned long long *a = reinterpret_cast<unsigned long long *>(p);
     unsigned long long old = *a, assumed;
     do {
         assumed = old;
-        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(__dmul_rn(__longlong_as_double((long long)assumed), v)));
-    } while (old != assumed);
-}
-__device__ __forceinline__ void atomic_mul_acc(long long *p, long long v) {
-    unsigned long long *a = reinterpret_cast<unsigned long long *>(p);
-    unsigned long long old = *a, assumed;
-    do {
-        assumed = old;
-        old = atomicCAS(a, assumed, assumed * (unsigned long long)v);
+        unsigned long long next;
+        if constexpr (std::is_same<V, float>::value) {
+            const float prod = __fmul_rn((float)__longlong_as_double((long long)assumed), v);
+            next = (unsigned long long)__double_as_longlong((double)prod);
+        } else if constexpr (std::is_same<V, double>::value) {
+            next = (unsigned long long)__double_as_longlong(__dmul_rn(__longlong_as_double((long long)assumed), v));
+        } else {
+            next = assumed * (unsigned long long)(long long)v;
+        }
+        old = atomicCAS(a, assumed, next);
     } while (old != assumed);
 }
 
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(256) group_atomic_kernel(const V *__restrict__
             atomic_add_acc(c1 + label, (Acc)sq_as_input(v));
             atomic_add_acc(cnt + label, 1ll);
         } else if (OP == NBG_GROUP_NANPROD) {
-            atomic_mul_acc(c0 + label, (Acc)v);
+            atomic_mul_acc<V>(c0 + label, v);
         } else if (OP == NBG_GROUP_NANMAX) {
             atomicMax(key0 + label, order_key((double)v));
         } else if (OP == NBG_GROUP_NANMIN) {
@@ -467,7 +472,10 @@ static size_t group_state_bytes(int64_t rows, int64_t num_labels) {
     return (size_t)NBG_GROUP_WS_CHANNELS * (size_t)rows * (size_t)num_labels * 8 + 256;
 }
 // scratch for the shared-label plan: 4 bytes per column + one header per (smallest) tile
-static size_t group_scratch_bytes(int64_t n) { return (size_t)n * 4 + (size_t)(n / 128 + 2) * nbg::kRbHdr * 4 + 1024; }
+static size_t group_scratch_bytes(int64_t n) {
+    // widest tile is 1024 columns (a short row still needs one whole tile), narrowest 128
+    return (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * nbg::kRbHdr * 4 + 1024;
+}
 
 extern "C" size_t nbg_group_workspace_bytes(int, int, int64_t rows, int64_t n, int64_t num_labels) {
     if (rows <= 0 || num_labels <= 0) return 0;

@@ -411,3 +411,47 @@ class groupndreduce(NumbaBase):
         if work_dt != result_dt:
             res = res.to(dev._NP_TO_TORCH[result_dt])
         return _finish(res, as_tensor)
+
+
+# ------------------------------------------------------- grouped: three-step (sharded) form
+def group_state_numel(rows: int, num_labels: int) -> int:
+    return _lib.NBG_GROUP_WS_CHANNELS * rows * num_labels
+
+
+def run_group_partial(name: str, values: torch.Tensor, labels: torch.Tensor, num_labels: int,
+                      index_offset: int = 0, labels_per_row: bool = False) -> torch.Tensor:
+    """init + accumulate for one element shard.  Returns the accumulator state as an int64
+    tensor (NBG_GROUP_WS_CHANNELS, rows, num_labels) -- raw 8-byte slots (include/nbg_b200.h)."""
+    L = _lib.lib()
+    code = _lib.GROUP_OPS[name]
+    vcode = _NBG_DTYPE[dev.np_dtype_of(values)]
+    lcode = _NBG_DTYPE[dev.np_dtype_of(labels)]
+    rows, n = values.shape
+    ws_bytes = L.nbg_group_workspace_bytes(code, vcode, rows, n, num_labels)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=values.device)
+    assert ws.data_ptr() % 256 == 0
+    _lib.check(L.nbg_group_init(code, vcode, ws.data_ptr(), rows, num_labels, dev.stream_ptr()), "nbg_group_init")
+    _lib.check(
+        L.nbg_group_accumulate(code, vcode, lcode, dev.ptr(values), dev.ptr(labels), int(labels_per_row),
+                               ws.data_ptr(), ws_bytes, rows, n, num_labels, int(index_offset), dev.stream_ptr()),
+        f"nbg_group_accumulate({name})",
+    )
+    nstate = group_state_numel(rows, num_labels)
+    return ws[: nstate * 8].view(torch.int64).view(_lib.NBG_GROUP_WS_CHANNELS, rows, num_labels)
+
+
+def run_group_combine(name: str, vdtype: np.dtype, acc: torch.Tensor, other: torch.Tensor) -> None:
+    """acc <- merge(acc, other) where `other` covers LATER elements (nbg_group_combine)."""
+    _, rows, K = acc.shape
+    rc = _lib.lib().nbg_group_combine(_lib.GROUP_OPS[name], _NBG_DTYPE[np.dtype(vdtype)], acc.data_ptr(),
+                                      other.data_ptr(), rows, K, dev.stream_ptr())
+    _lib.check(rc, f"nbg_group_combine({name})")
+
+
+def run_group_finalize(name: str, vdtype: np.dtype, state: torch.Tensor, ddof: int) -> torch.Tensor:
+    _, rows, K = state.shape
+    out = torch.empty((rows, K), dtype=dev._NP_TO_TORCH[np.dtype(vdtype)], device=state.device)
+    rc = _lib.lib().nbg_group_finalize(_lib.GROUP_OPS[name], _NBG_DTYPE[np.dtype(vdtype)], state.data_ptr(),
+                                       out.data_ptr(), rows, K, int(ddof), dev.stream_ptr())
+    _lib.check(rc, f"nbg_group_finalize({name})")
+    return out
