@@ -388,3 +388,68 @@ def test_properties_large_group(nb):
     ok = ~torch.isnan(am)
     picked = torch.gather(v, 1, torch.nan_to_num(am, nan=0.0).to(torch.int64))
     assert torch.equal(picked[ok], mx[ok])
+
+
+# ------------------------------------------ core-axis sharding protocol on a single device
+def test_shard_protocol_halo_carry_partials_single_gpu(nb):
+    """The C-ABI hooks that multi-GPU sharding uses (a_halo, carry_in/agg_out, group partial
+    states + combine) driven from one device: two shards processed one after the other must
+    reproduce the unsharded result."""
+    import torch
+
+    from numbagg_b200 import decorators as D
+    from numbagg_b200 import distributed as nd
+
+    a = fixture_array((4, 50_000), nan_frac=0.3, seed=31)
+    b = a**2 + 1
+    cut = 20_011  # odd cut: shard rows are not 16-byte aligned
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    s0a, s1a = ta[:, :cut].contiguous(), ta[:, cut:].contiguous()
+    s0b, s1b = tb[:, :cut].contiguous(), tb[:, cut:].contiguous()
+    for w in (20, 1000):
+        for f in ("move_mean", "move_std", "move_corr"):
+            arrs0, arrs1 = ([s0a, s0b], [s1a, s1b]) if f == "move_corr" else ([s0a], [s1a])
+            halos = [x[:, -w:].contiguous() for x in arrs0]
+            got = torch.cat([D.run_move(f, arrs0, w, 5, -1), D.run_move(f, arrs1, w, 5, -1, halos)], dim=1)
+            args = (a, b) if f == "move_corr" else (a,)
+            # corr divides by variances built from the reference's never-resynced running sums:
+            # its own drift over 50k steps is ~1e-11 relative here (see test_move_vs_oracle_tiles)
+            assert_parity(f, got.cpu().numpy(), getattr(oracle, f)(*args, window=w, min_count=5),
+                          scale=_scale(f, list(args)), atol=1e-9 if f == "move_corr" else None)
+    for f in EXP_ONE + EXP_TWO:
+        arrs0, arrs1 = ([s0a, s0b], [s1a, s1b]) if f in EXP_TWO else ([s0a], [s1a])
+        o0, agg0 = D.run_move_exp(f, arrs0, 0.05, 0.1, -1, None, True, True)
+        o1, agg1 = D.run_move_exp(f, arrs1, 0.05, 0.1, -1, agg0, True, True)
+        args = (a, b) if f in EXP_TWO else (a,)
+        assert_parity(f, torch.cat([o0, o1], dim=1).cpu().numpy(), getattr(oracle, f)(*args, alpha=0.05, min_weight=0.1), scale=20.0)
+        # aggregate-only pass + host-side composition == state after scanning both shards
+        _, only1 = D.run_move_exp(f, arrs1, 0.05, 0.1, -1, None, True, False)
+        torch.testing.assert_close(nd.exp_compose(f, agg0, only1), agg1, rtol=1e-12, atol=1e-300)
+    x = a.copy()
+    x[1, 15_000:30_000] = np.nan
+    tx = torch.from_numpy(x).cuda()
+    for limit in (3, 20_000, 50_000):
+        f0, g0 = D.run_fill("ffill", tx[:, :cut].contiguous(), limit, -1, None, True, True)
+        f1, _ = D.run_fill("ffill", tx[:, cut:].contiguous(), limit, -1, g0, False, True)
+        np.testing.assert_array_equal(torch.cat([f0, f1], dim=1).cpu().numpy(), oracle.ffill(x, limit=limit))
+        b1, h1 = D.run_fill("bfill", tx[:, cut:].contiguous(), limit, -1, None, True, True)
+        b0, _ = D.run_fill("bfill", tx[:, :cut].contiguous(), limit, -1, h1, False, True)
+        np.testing.assert_array_equal(torch.cat([b0, b1], dim=1).cpu().numpy(), oracle.bfill(x, limit=limit))
+    labels = np.random.RandomState(32).randint(-1, 40, size=a.shape[1])
+    tl = torch.from_numpy(labels).cuda()
+    for f in oracle.GROUPED_FUNCS:
+        p0 = D.run_group_partial(f, s0a, tl[:cut].contiguous(), 40, 0)
+        p1 = D.run_group_partial(f, s1a, tl[cut:].contiguous(), 40, cut)
+        if f in nd._ADDITIVE_GROUP_OPS:
+            p0[:2].view(torch.float64).add_(p1[:2].view(torch.float64))
+            p0[2].add_(p1[2])
+        else:
+            D.run_group_combine(f, np.float64, p0, p1)
+        got = D.run_group_finalize(f, np.float64, p0, 1).cpu().numpy()
+        _group_check_arrays(f, got, getattr(oracle, f)(a, labels, num_labels=40, axis=-1), a)
+
+
+def _group_check_arrays(f, got, exp, values):
+    m = float(np.nanmax(np.abs(values)))
+    scale = m * m * 1500 if (f in GROUP_FLOAT_ONLY or f == "group_nansum_of_squares") else (m * 1500 if f in ("group_nansum", "group_nanmean") else None)
+    assert_parity(f, got, exp, scale=scale)
