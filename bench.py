@@ -66,6 +66,7 @@ WORKLOADS = {
     "cfg4_move_cov": ("move", "move_cov", "f32", 1000, 1_000_000, dict(window=1000, min_count=500)),
     "cfg4_move_corr": ("move", "move_corr", "f32", 1000, 1_000_000, dict(window=1000, min_count=500)),
     # configs[4]: high-cardinality 1-D grouped reductions (per-element labels)
+    "cfg5_group_nansum1d": ("group1d", "group_nansum", "f64", 1, 2_000_000_000, dict(num_labels=10_000_000)),
     "cfg5_group_nanargmax": ("group1d", "group_nanargmax", "f64", 1, 2_000_000_000, dict(num_labels=10_000_000)),
     "cfg5_group_nanfirst": ("group1d", "group_nanfirst", "f64", 1, 2_000_000_000, dict(num_labels=10_000_000)),
     "cfg5_group_nanvar": ("group1d", "group_nanvar", "f64", 1, 2_000_000_000, dict(num_labels=10_000_000)),

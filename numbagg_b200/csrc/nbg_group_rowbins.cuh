@@ -22,6 +22,8 @@
 // atomics otherwise).
 #pragma once
 
+#include <stdlib.h>
+
 #include "nbg_common.cuh"
 
 namespace nbg {
@@ -459,7 +461,8 @@ static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
     if (K <= 0 || K > 65535 || n <= 0 || n >= ((int64_t)1 << 31) || (n % PER16) != 0 || rows < 1) return g;
     const int words = (int)(sizeof(RbBin<V, CLS>) / sizeof(V));
     g.priv = (K * words <= 32) ? 1 : 0;
-    const int candidates[3] = {sizeof(V) == 4 ? 1024 : 512, sizeof(V) == 4 ? 512 : 256, sizeof(V) == 4 ? 256 : 128};
+    int candidates[3] = {sizeof(V) == 4 ? 1024 : 512, sizeof(V) == 4 ? 512 : 256, sizeof(V) == 4 ? 256 : 128};
+    if (const char *e = getenv("NBG_RB_C")) candidates[0] = candidates[1] = candidates[2] = atoi(e);  // tuning hook
     // prefer two CTAs per SM (<= ~110 KB), else whatever fits
     for (int pass = 0; pass < 2 && !g.ok; pass++) {
         for (int c = 0; c < 3; c++) {
@@ -480,6 +483,7 @@ static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
     // partial bins with atomics.
     const int64_t slots = (int64_t)kNumSMs * 2;
     int64_t nseg = groups >= 4 * slots ? 1 : (8 * slots + groups - 1) / groups;
+    if (const char *e = getenv("NBG_RB_NSEG")) nseg = atoi(e);  // tuning hook
     if (nseg > g.ntiles) nseg = g.ntiles;
     if (nseg < 1) nseg = 1;
     g.tiles_per_seg = (int)((g.ntiles + nseg - 1) / nseg);
