@@ -60,6 +60,56 @@ def _finish(result: torch.Tensor, as_tensor: bool, out=None):
     return dev.to_host(result)
 
 
+# ------------------------------------------------------- host <-> device pipelining (numpy)
+_PIPELINE_MIN_BYTES = 64 << 20
+_PIPELINE_CHUNK_BYTES = 96 << 20
+_PIPELINE_STREAMS: dict[int, list] = {}
+
+
+def _pipeline_streams(device: torch.device, k: int = 3):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _PIPELINE_STREAMS:
+        _PIPELINE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(k)]
+    return _PIPELINE_STREAMS[key]
+
+
+def _rows_pipelined(host_arrs: list[np.ndarray], work_dtype: np.dtype, axis: int, device_fn) -> np.ndarray | None:
+    """numpy inputs whose leading dimension is NOT the core axis are independent along it:
+    stream them through the GPU in row blocks on a few CUDA streams so that the H2D copy of
+    block i+1, the kernels of block i and the D2H copy of block i-1 overlap (PCIe is full
+    duplex).  `device_fn(list_of_device_tensors) -> device tensor` of the block's shape.
+    Returns None when the input does not qualify (small, 1-D, core axis leading)."""
+    a0 = host_arrs[0]
+    nd = a0.ndim
+    if nd < 2 or axis % nd == 0 or a0.shape[0] < 2:
+        return None
+    if any(x.shape != a0.shape or not x.flags.c_contiguous or x.dtype != work_dtype for x in host_arrs):
+        return None
+    if a0.nbytes < _PIPELINE_MIN_BYTES:
+        return None
+    device = dev.require_cuda()
+    tdt = dev._NP_TO_TORCH[np.dtype(work_dtype)]
+    nblocks = int(min(a0.shape[0], max(2, a0.nbytes // _PIPELINE_CHUNK_BYTES)))
+    bounds = [a0.shape[0] * i // nblocks for i in range(nblocks + 1)]
+    host_in = [torch.from_numpy(x) for x in host_arrs]
+    host_out = torch.empty(a0.shape, dtype=tdt, pin_memory=True)
+    streams = _pipeline_streams(device)
+    main = torch.cuda.current_stream(device)
+    for st in streams:
+        st.wait_stream(main)
+    for i in range(nblocks):
+        st = streams[i % len(streams)]
+        lo, hi = bounds[i], bounds[i + 1]
+        with torch.cuda.stream(st):
+            d_in = [h[lo:hi].to(device, non_blocking=True) for h in host_in]
+            d_out = device_fn(d_in)
+            host_out[lo:hi].copy_(d_out, non_blocking=True)
+    for st in streams:
+        main.wait_stream(st)
+    main.synchronize()
+    return host_out.numpy()
+
+
 class NumbaBase:
     """Counterpart of numbagg.decorators.NumbaBase (:103-162): carries the function's
     name/doc, ``repr`` and public signature.  ``target`` is always "cuda"."""
@@ -141,6 +191,11 @@ class ndmove(NumbaBase):
             # NumPy refuses to cast a float window/min_count to the int64 loop operand
             raise TypeError(f"window and min_count must be integers: {window!r}, {min_count!r}")
         dt = _float_loop_dtype(*[dev.np_dtype_of(a) for a in arr])
+        if not as_tensor and out is None:
+            piped = _rows_pipelined(list(arr), dt, axis,
+                                    lambda ts: run_move(self.__name__, ts, window, min_count, axis))
+            if piped is not None:
+                return piped
         ts = [dev.to_device(a, dt) for a in arr]
         if len(ts) > 1 and any(t.shape != ts[0].shape for t in ts):
             ts = [t.contiguous() for t in torch.broadcast_tensors(*ts)]
@@ -221,6 +276,13 @@ class ndmoveexp(NumbaBase):
             # loop selection (python float -> float64, np.float32 -> float32)
             alpha_dtype = np.asarray(alpha).dtype
         dt = _float_loop_dtype(*[dev.np_dtype_of(a) for a in arr], alpha_dtype)
+        if not as_tensor and out is None and not alpha_is_array:
+            a_s = float(np.float32(alpha)) if dt == _F32 else float(alpha)
+            m_s = float(np.float32(min_weight)) if dt == _F32 else float(min_weight)
+            piped = _rows_pipelined(list(arr), dt, axis,
+                                    lambda ts: run_move_exp(self.__name__, ts, a_s, m_s, axis)[0])
+            if piped is not None:
+                return piped
         ts = [dev.to_device(a, dt) for a in arr]
         if len(ts) > 1 and any(t.shape != ts[0].shape for t in ts):
             ts = [t.contiguous() for t in torch.broadcast_tensors(*ts)]
@@ -291,6 +353,10 @@ class ndfill(NumbaBase):
         if dt.kind == "c":
             raise TypeError(f"Unsupported dtype for fill operation: {dt}")
         work = _F32 if dt == np.dtype(np.float16) else dt  # float16 <-> float32 is exact
+        if not as_tensor and out is None and work == dt:
+            piped = _rows_pipelined([arr], dt, axis, lambda ts: run_fill(self.__name__, ts[0], limit, axis)[0])
+            if piped is not None:
+                return piped
         t = dev.to_device(arr, work)
         if t.dim() == 0:
             raise ValueError("ffill/bfill need at least one dimension")

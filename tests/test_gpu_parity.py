@@ -453,3 +453,20 @@ def _group_check_arrays(f, got, exp, values):
     m = float(np.nanmax(np.abs(values)))
     scale = m * m * 1500 if (f in GROUP_FLOAT_ONLY or f == "group_nansum_of_squares") else (m * 1500 if f in ("group_nansum", "group_nanmean") else None)
     assert_parity(f, got, exp, scale=scale)
+
+
+def test_numpy_inputs_pipelined_in_row_blocks(nb):
+    """Large numpy inputs are streamed through the GPU in row blocks (H2D / kernels / D2H
+    overlapped on several streams): same values as the one-shot path and the oracle."""
+    a = fixture_array((96, 200_000), nan_frac=0.2, seed=41)  # 154 MB > the pipelining threshold
+    b = a**2 + 1
+    pa, pb = nb.empty_pinned(a.shape, a.dtype), nb.empty_pinned(a.shape, a.dtype)
+    pa[...], pb[...] = a, b
+    for arr_a, arr_b in ((a, b), (pa, pb)):
+        assert_parity("move_mean", nb.move_mean(arr_a, window=20, min_count=1), oracle.move_mean(a, window=20, min_count=1), scale=1.0)
+        assert_parity("move_corr", nb.move_corr(arr_a, arr_b, window=50, min_count=5), oracle.move_corr(a, b, window=50, min_count=5), scale=1.0, atol=1e-9)
+        assert_parity("move_exp_nanmean", nb.move_exp_nanmean(arr_a, alpha=0.1), oracle.move_exp_nanmean(a, alpha=0.1), scale=1.0)
+        np.testing.assert_array_equal(nb.ffill(arr_a, limit=3), oracle.ffill(a, limit=3))
+        np.testing.assert_array_equal(nb.bfill(arr_a), oracle.bfill(a))
+    a3 = a.reshape(96, 400, 500)
+    assert_parity("move_sum", nb.move_sum(a3, window=7, min_count=1, axis=1), oracle.move_sum(a3, window=7, min_count=1, axis=1), scale=7.0)
