@@ -161,13 +161,15 @@ size_t nbg_fill_workspace_bytes(int itemsize, int64_t outer, int64_t n, int64_t 
  * Three-step form for element-sharded inputs (multi-GPU): init -> accumulate (any number
  * of shards, `index_offset` = flat index of the shard's first element) -> [caller combines
  * workspaces across devices] -> finalize.  nbg_group() runs the three steps on one device.
- * The workspace holds, per (row, label), NBG_GROUP_WS_CHANNELS 8-byte slots whose meaning
- * is listed in DESIGN.md ("group workspace"), followed by per-call scratch (the column plan
+ * The workspace holds one record of nbg_group_record_words(op) 8-byte slots per (row, label),
+ * ws[row][label][slot] (slot meanings per op: DESIGN.md "group workspace"), followed by
+ * per-call scratch (the column plan
  * of the shared-label kernel); nbg_group_workspace_bytes() sizes both for shards of up to
- * `n` elements per row.  Only the first NBG_GROUP_WS_CHANNELS*rows*num_labels*8 bytes (after
- * rounding the base up to 256) are state that must be exchanged between devices.
+ * `n` elements per row.  Only the first record_words*rows*num_labels*8 bytes (after rounding
+ * the base up to 256) are state that must be exchanged between devices.
  */
-#define NBG_GROUP_WS_CHANNELS 3
+#define NBG_GROUP_WS_CHANNELS 4 /* upper bound of nbg_group_record_words() */
+int nbg_group_record_words(int op); /* 8-byte slots per (row, label) record: 1, 2 or 4 */
 size_t nbg_group_workspace_bytes(int op, int vdtype, int64_t rows, int64_t n, int64_t num_labels);
 int nbg_group_init(int op, int vdtype, void *workspace, int64_t rows, int64_t num_labels,
                    void *stream);

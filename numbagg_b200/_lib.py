@@ -25,7 +25,7 @@ GROUP_OPS = dict(
 )
 NBG_EXP_STATE = 11
 NBG_FILL_STATE = 3
-NBG_GROUP_WS_CHANNELS = 3
+NBG_GROUP_WS_CHANNELS = 4
 
 _i64 = ctypes.c_int64
 _vp = ctypes.c_void_p
@@ -45,6 +45,7 @@ _SIGNATURES = {
     "nbg_move_exp_workspace_bytes": (_sz, [_int, _int, _i64, _i64, _i64]),
     "nbg_fill": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "nbg_fill_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
+    "nbg_group_record_words": (_int, [_int]),
     "nbg_group_workspace_bytes": (_sz, [_int, _int, _i64, _i64, _i64]),
     "nbg_group_init": (_int, [_int, _int, _vp, _i64, _i64, _vp]),
     "nbg_group_accumulate": (_int, [_int, _int, _int, _vp, _vp, _int, _vp, _sz, _i64, _i64, _i64, _i64, _vp]),

@@ -242,6 +242,7 @@ struct RbParams {
     const void *values;
     const uint32_t *plan;
     void *ws_ch[3];
+    int64_t ws_stride;
     int64_t rows, n;
     int K, C;
     int ntiles, tiles_per_seg, nseg;
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(kRbThreads) group_rowbins_kernel(RbParams p) {
         if (p.priv) {
             for (int s2 = 1; s2 < kRbSub; s2++) b.merge(bins[(size_t)s2 * K * kRbRows + k * kRbRows + rr]);
         }
-        const size_t o = (size_t)(r0 + rr) * K + k;
+        const size_t o = ((size_t)(r0 + rr) * K + k) * (size_t)p.ws_stride;  // record offset (words)
         RbFlush<V, CLS>::flush(b, c0p + o, c1p + o, c2p + o, atomic);
     }
 }
@@ -493,7 +494,7 @@ static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
 }
 
 template <typename V, typename L, int CLS>
-static int rb_launch(const V *values, const L *labels, void *ws_ch[3], void *scratch, size_t scratch_bytes,
+static int rb_launch(const V *values, const L *labels, void *ws_ch[3], int64_t ws_stride, void *scratch, size_t scratch_bytes,
                      int64_t rows, int64_t n, int64_t K, cudaStream_t stream, bool *handled) {
     *handled = false;
     const RbGeometry g = rb_geometry<V, CLS>(rows, n, K);
@@ -511,6 +512,7 @@ static int rb_launch(const V *values, const L *labels, void *ws_ch[3], void *scr
     p.values = values;
     p.plan = plan;
     p.ws_ch[0] = ws_ch[0], p.ws_ch[1] = ws_ch[1], p.ws_ch[2] = ws_ch[2];
+    p.ws_stride = ws_stride;
     p.rows = rows, p.n = n, p.K = (int)K, p.C = g.C;
     p.ntiles = g.ntiles, p.tiles_per_seg = g.tiles_per_seg, p.nseg = g.nseg, p.priv = g.priv;
     const int64_t groups = (rows + kRbRows - 1) / kRbRows;

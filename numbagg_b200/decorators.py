@@ -480,14 +480,15 @@ class groupndreduce(NumbaBase):
 
 
 # ------------------------------------------------------- grouped: three-step (sharded) form
-def group_state_numel(rows: int, num_labels: int) -> int:
-    return _lib.NBG_GROUP_WS_CHANNELS * rows * num_labels
+def group_record_words(name: str) -> int:
+    """8-byte slots per (row, label) record of this op's accumulator state (1, 2 or 4)."""
+    return int(_lib.lib().nbg_group_record_words(_lib.GROUP_OPS[name]))
 
 
 def run_group_partial(name: str, values: torch.Tensor, labels: torch.Tensor, num_labels: int,
                       index_offset: int = 0, labels_per_row: bool = False) -> torch.Tensor:
     """init + accumulate for one element shard.  Returns the accumulator state as an int64
-    tensor (NBG_GROUP_WS_CHANNELS, rows, num_labels) -- raw 8-byte slots (include/nbg_b200.h)."""
+    tensor (rows, num_labels, record_words) -- raw 8-byte slots (include/nbg_b200.h)."""
     L = _lib.lib()
     code = _lib.GROUP_OPS[name]
     vcode = _NBG_DTYPE[dev.np_dtype_of(values)]
@@ -502,20 +503,20 @@ def run_group_partial(name: str, values: torch.Tensor, labels: torch.Tensor, num
                                ws.data_ptr(), ws_bytes, rows, n, num_labels, int(index_offset), dev.stream_ptr()),
         f"nbg_group_accumulate({name})",
     )
-    nstate = group_state_numel(rows, num_labels)
-    return ws[: nstate * 8].view(torch.int64).view(_lib.NBG_GROUP_WS_CHANNELS, rows, num_labels)
+    words = group_record_words(name)
+    return ws[: words * rows * num_labels * 8].view(torch.int64).view(rows, num_labels, words)
 
 
 def run_group_combine(name: str, vdtype: np.dtype, acc: torch.Tensor, other: torch.Tensor) -> None:
     """acc <- merge(acc, other) where `other` covers LATER elements (nbg_group_combine)."""
-    _, rows, K = acc.shape
+    rows, K, _ = acc.shape
     rc = _lib.lib().nbg_group_combine(_lib.GROUP_OPS[name], _NBG_DTYPE[np.dtype(vdtype)], acc.data_ptr(),
                                       other.data_ptr(), rows, K, dev.stream_ptr())
     _lib.check(rc, f"nbg_group_combine({name})")
 
 
 def run_group_finalize(name: str, vdtype: np.dtype, state: torch.Tensor, ddof: int) -> torch.Tensor:
-    _, rows, K = state.shape
+    rows, K, _ = state.shape
     out = torch.empty((rows, K), dtype=dev._NP_TO_TORCH[np.dtype(vdtype)], device=state.device)
     rc = _lib.lib().nbg_group_finalize(_lib.GROUP_OPS[name], _NBG_DTYPE[np.dtype(vdtype)], state.data_ptr(),
                                        out.data_ptr(), rows, K, int(ddof), dev.stream_ptr())

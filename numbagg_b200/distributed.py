@@ -30,9 +30,10 @@ _EXP_SQ_CHANNEL = {
     "move_exp_nancount": None, "move_exp_nanmean": None, "move_exp_nansum": None,
     "move_exp_nanvar": 3, "move_exp_nanstd": 3, "move_exp_nancov": 4, "move_exp_nancorr": 4,
 }
+# additive ops: (float-sum slots, count slots) inside a record (ws_layout() in nbg_group.cu)
 _ADDITIVE_GROUP_OPS = {
-    "group_nansum", "group_nanmean", "group_nancount", "group_nansum_of_squares", "group_nanvar",
-    "group_nanstd",
+    "group_nansum": ([0], []), "group_nansum_of_squares": ([0], []), "group_nancount": ([], [0]),
+    "group_nanmean": ([0], [1]), "group_nanvar": ([0, 1], [2]), "group_nanstd": ([0, 1], [2]),
 }
 
 
@@ -180,10 +181,17 @@ def group_sharded(name: str, values: torch.Tensor, labels: torch.Tensor, *, num_
     vdtype = D.dev.np_dtype_of(values)
     state = backend.group_partial(name, values, labels, num_labels, index_offset, labels_per_row)
     if name in _ADDITIVE_GROUP_OPS:
+        # sums of float data are float64 bit patterns: reduce them through a float64 view
+        sum_slots, count_slots = _ADDITIVE_GROUP_OPS[name]
         if vdtype.kind == "f":
-            sums = state[:2].view(torch.float64)
-            dist.all_reduce(sums, group=group)
-            dist.all_reduce(state[2], group=group)
+            for sl in sum_slots:
+                t = state[..., sl].contiguous().view(torch.float64)
+                dist.all_reduce(t, group=group)
+                state[..., sl] = t.view(torch.int64)
+            for sl in count_slots:
+                t = state[..., sl].contiguous()
+                dist.all_reduce(t, group=group)
+                state[..., sl] = t
         else:
             dist.all_reduce(state, group=group)
         total = state

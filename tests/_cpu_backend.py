@@ -57,6 +57,24 @@ def _slices_last(t, axis):
     return np.ascontiguousarray(a).reshape(-1, a.shape[-1]), a.shape
 
 
+# record layout per op (ws_layout() in numbagg_b200/csrc/nbg_group.cu): (words, slot of ch0/ch1/ch2)
+def _layout(name):
+    if name == "group_nancount":
+        return 1, (0, 0, 0)
+    if name == "group_nanmean":
+        return 2, (0, 0, 1)
+    if name in ("group_nanvar", "group_nanstd"):
+        return 4, (0, 1, 2)
+    if name in ("group_nanfirst", "group_nanlast", "group_nanargmax", "group_nanargmin"):
+        return 2, (0, 1, 0)
+    return 1, (0, 0, 0)
+
+
+def _channels(rec, name):
+    words, slots = _layout(name)
+    return [rec[..., slots[0]], rec[..., slots[1]], rec[..., slots[2]]]
+
+
 class OracleBackend:
     @staticmethod
     def move(name, arrs, window, min_count, axis, halos):
@@ -138,18 +156,19 @@ class OracleBackend:
         v = values.numpy().astype(np.float64)
         rows, n = v.shape
         lab = labels.numpy().reshape(-1, n) if labels_per_row else np.broadcast_to(labels.numpy(), (rows, n))
-        st = np.zeros((3, rows, K), dtype=np.int64)
+        rec = np.zeros((rows, K, _layout(name)[0]), dtype=np.int64)
+        st = _channels(rec, name)
         f0 = st[0].view(np.float64)
         f1 = st[1].view(np.float64)
         k0 = st[0].view(np.uint64)
         if name == "group_nanprod":
             f0[:] = 1.0
         if name == "group_nanall":
-            st[0] = 1
+            st[0][:] = 1
         if name in ("group_nanfirst", "group_nanargmax", "group_nanargmin"):
-            st[1] = np.iinfo(np.int64).max
+            st[1][:] = np.iinfo(np.int64).max
         if name == "group_nanlast":
-            st[1] = -1
+            st[1][:] = -1
         for r in range(rows):
             for i in range(n):
                 l, x = int(lab[r, i]), v[r, i]
@@ -163,18 +182,18 @@ class OracleBackend:
                 if name == "group_nansum_of_squares":
                     f0[r, l] += x * x
                 if name in ("group_nanmean", "group_nancount", "group_nanvar", "group_nanstd"):
-                    st[2, r, l] += 1
+                    st[2][r, l] += 1
                 if name == "group_nanprod":
                     f0[r, l] *= x
                 if name == "group_nanany" and x != 0:
-                    st[0, r, l] = 1
+                    st[0][r, l] = 1
                 if name == "group_nanall" and x == 0:
-                    st[0, r, l] = 0
-                if name == "group_nanfirst" and gi < st[1, r, l]:
-                    st[1, r, l] = gi
+                    st[0][r, l] = 0
+                if name == "group_nanfirst" and gi < st[1][r, l]:
+                    st[1][r, l] = gi
                     f0[r, l] = x
-                if name == "group_nanlast" and gi > st[1, r, l]:
-                    st[1, r, l] = gi
+                if name == "group_nanlast" and gi > st[1][r, l]:
+                    st[1][r, l] = gi
                     f0[r, l] = x
                 if name in ("group_nanmax", "group_nanmin", "group_nanargmax", "group_nanargmin"):
                     k = OracleBackend._key(np.array([x]))[0]
@@ -182,21 +201,23 @@ class OracleBackend:
                         k = ~k
                     if k > k0[r, l]:
                         k0[r, l] = k
-                        st[1, r, l] = gi if "arg" in name else st[1, r, l]
-        return torch.from_numpy(st)
+                        st[1][r, l] = gi if "arg" in name else st[1][r, l]
+        return torch.from_numpy(rec)
 
     @staticmethod
     def group_combine(name, vdtype, acc, other):
-        a, o = acc.numpy(), other.numpy()
+        ra, ro = acc.numpy(), other.numpy()
+        a = _channels(ra, name)
+        o = _channels(ro, name)
         ak, ok = a[0].view(np.uint64), o[0].view(np.uint64)
         if name == "group_nanprod":
             a[0].view(np.float64)[:] *= o[0].view(np.float64)
         elif name in ("group_nanmin", "group_nanmax"):
             np.maximum(ak, ok, out=ak)
         elif name == "group_nanany":
-            a[0] |= o[0]
+            a[0][:] |= o[0]
         elif name == "group_nanall":
-            a[0] &= o[0]
+            a[0][:] &= o[0]
         elif name == "group_nanfirst":
             m = o[1] < a[1]
             a[1][m], a[0][m] = o[1][m], o[0][m]
@@ -213,7 +234,8 @@ class OracleBackend:
 
     @staticmethod
     def group_finalize(name, vdtype, state, ddof):
-        st = state.numpy()
+        rec = state.numpy()
+        st = _channels(rec, name)
         f0, f1, cnt = st[0].view(np.float64), st[1].view(np.float64), st[2]
         k0 = st[0].view(np.uint64)
         with np.errstate(all="ignore"):

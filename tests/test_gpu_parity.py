@@ -441,8 +441,11 @@ def test_shard_protocol_halo_carry_partials_single_gpu(nb):
         p0 = D.run_group_partial(f, s0a, tl[:cut].contiguous(), 40, 0)
         p1 = D.run_group_partial(f, s1a, tl[cut:].contiguous(), 40, cut)
         if f in nd._ADDITIVE_GROUP_OPS:
-            p0[:2].view(torch.float64).add_(p1[:2].view(torch.float64))
-            p0[2].add_(p1[2])
+            sum_slots, count_slots = nd._ADDITIVE_GROUP_OPS[f]
+            for sl in sum_slots:
+                p0[..., sl] = (p0[..., sl].contiguous().view(torch.float64) + p1[..., sl].contiguous().view(torch.float64)).view(torch.int64)
+            for sl in count_slots:
+                p0[..., sl] += p1[..., sl]
         else:
             D.run_group_combine(f, np.float64, p0, p1)
         got = D.run_group_finalize(f, np.float64, p0, 1).cpu().numpy()
