@@ -54,6 +54,7 @@ struct FillPolicy {
     using T = T_;
     using Agg = FillAgg;
     static constexpr int NSTREAM = 1;
+    static constexpr int MIN_CTAS = 6;  // <= 42 registers: six 35 KB tiles per SM
     static constexpr bool REV = REV_;
     __device__ static __forceinline__ const T *stream_row(const ScanParams &p, int, int64_t row) {
         return reinterpret_cast<const T *>(p.in[0]) + row * p.n;

@@ -227,7 +227,7 @@ struct ScanSmem {
 };
 
 template <class P, int THREADS, int E>
-__global__ void __launch_bounds__(THREADS) scan_rowtile_kernel(ScanParams p) {
+__global__ void __launch_bounds__(THREADS, P::MIN_CTAS) scan_rowtile_kernel(ScanParams p) {
     using T = typename P::T;
     using Agg = typename P::Agg;
     using SM = ScanSmem<P, THREADS, E>;
