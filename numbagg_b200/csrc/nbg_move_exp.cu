@@ -198,7 +198,7 @@ struct ExpPolicy {
     using Op = Op_;
     using Agg = ExpAgg<Op>;
     static constexpr int NSTREAM = Op::NIN + (ALPHA_STREAM ? 1 : 0);
-    static constexpr int MIN_CTAS = (Op::NCH <= 3 && !ALPHA_STREAM) ? 5 : 1;  // light ops: <= 51 registers
+    static constexpr int MIN_CTAS = (Op::NCH <= 3 && !ALPHA_STREAM) ? 5 : 2;  // light ops: <= 51 registers; heavy: <= 128
     static constexpr bool REV = false;
     __device__ static __forceinline__ const T *stream_row(const ScanParams &p, int s, int64_t row) {
         if (ALPHA_STREAM && s == Op::NIN)

@@ -180,6 +180,9 @@ __device__ __forceinline__ Agg lookback_exclusive(const ScanWorkspace<Agg> &ws, 
         const Agg window = agg_shfl(p, 0);
         excl = Agg::combine(window, excl);
         if (stop_mask) break;
+        // no single tile stopped the walk, but the COMPOSITION walked so far may already be
+        // absorbing (e.g. the decay product underflowed to 0 across several exp tiles)
+        if (Agg::absorbing(excl)) break;
         newest -= 32;
         if (newest < row_first) break;  // cannot happen: the row's first tile is inclusive
     }
