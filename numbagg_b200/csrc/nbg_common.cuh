@@ -90,6 +90,18 @@ __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ double prod_as_input(float a, float b) { return (double)__fmul_rn(a, b); }
 __device__ __forceinline__ double prod_as_input(double a, double b) { return __dmul_rn(a, b); }
 
+// ----------------------------------------------------------------------------- key encoding
+// Order-preserving map double -> u64; never 0 for a non-NaN input, so 0 can mean "empty".
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    if (v == 0.0) v = 0.0;  // -0.0 and +0.0 compare equal in the reference
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_to_double(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }

@@ -40,18 +40,6 @@ namespace nbg {
 
 constexpr int64_t kIdxNone = INT64_MAX;
 
-// ----------------------------------------------------------------------------- key encoding
-// Order-preserving map double -> u64; never 0 for a non-NaN input, so 0 can mean "empty".
-__device__ __forceinline__ unsigned long long order_key(double v) {
-    if (v == 0.0) v = 0.0;  // -0.0 and +0.0 compare equal in the reference
-    unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double key_to_double(unsigned long long k) {
-    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
-    return __longlong_as_double((long long)b);
-}
-
 template <typename V>
 struct VTraits;
 template <>
@@ -449,22 +437,30 @@ static int launch_atomic(const V *values, const L *labels, int labels_per_row, G
 
 template <typename V, typename L>
 static int try_rowbins(int op, const V *values, const L *labels, GroupWs ws, void *scratch, size_t scratch_bytes,
-                       int64_t rows, int64_t n, int64_t K, cudaStream_t stream, bool *handled) {
+                       int64_t rows, int64_t n, int64_t K, int64_t index_offset, cudaStream_t stream, bool *handled) {
     *handled = false;
+#define NBG_RB_CASE(CLS) \
+    case CLS:            \
+        return rb_launch<V, L, CLS>(values, labels, ws.ch, ws.stride, scratch, scratch_bytes, rows, n, K, index_offset, stream, handled)
     switch (rb_class_of(op)) {
-        case RB_SUM:
-            return rb_launch<V, L, RB_SUM>(values, labels, ws.ch, ws.stride, scratch, scratch_bytes, rows, n, K, stream, handled);
-        case RB_COUNT:
-            return rb_launch<V, L, RB_COUNT>(values, labels, ws.ch, ws.stride, scratch, scratch_bytes, rows, n, K, stream, handled);
-        case RB_MEAN:
-            return rb_launch<V, L, RB_MEAN>(values, labels, ws.ch, ws.stride, scratch, scratch_bytes, rows, n, K, stream, handled);
-        case RB_SUMSQ:
-            return rb_launch<V, L, RB_SUMSQ>(values, labels, ws.ch, ws.stride, scratch, scratch_bytes, rows, n, K, stream, handled);
-        case RB_VAR:
-            return rb_launch<V, L, RB_VAR>(values, labels, ws.ch, ws.stride, scratch, scratch_bytes, rows, n, K, stream, handled);
+        NBG_RB_CASE(RB_SUM);
+        NBG_RB_CASE(RB_COUNT);
+        NBG_RB_CASE(RB_MEAN);
+        NBG_RB_CASE(RB_SUMSQ);
+        NBG_RB_CASE(RB_VAR);
+        NBG_RB_CASE(RB_PROD);
+        NBG_RB_CASE(RB_MAX);
+        NBG_RB_CASE(RB_MIN);
+        NBG_RB_CASE(RB_ARGMAX);
+        NBG_RB_CASE(RB_ARGMIN);
+        NBG_RB_CASE(RB_FIRST);
+        NBG_RB_CASE(RB_LAST);
+        NBG_RB_CASE(RB_ANY);
+        NBG_RB_CASE(RB_ALL);
         default:
             return NBG_OK;
     }
+#undef NBG_RB_CASE
 }
 
 template <typename V, typename L>
@@ -473,7 +469,7 @@ static int dispatch_accumulate(int op, const V *values, const L *labels, int lab
                                cudaStream_t stream) {
     if (!labels_per_row) {
         bool handled = false;
-        int rc = try_rowbins<V, L>(op, values, labels, ws, scratch, scratch_bytes, rows, n, K, stream, &handled);
+        int rc = try_rowbins<V, L>(op, values, labels, ws, scratch, scratch_bytes, rows, n, K, index_offset, stream, &handled);
         if (rc || handled) return rc;
     }
 #define NBG_GROUP_CASE(OPC) \

@@ -23,6 +23,7 @@
 #pragma once
 
 #include <stdlib.h>
+#include <string.h>
 
 #include "nbg_common.cuh"
 
@@ -33,7 +34,10 @@ constexpr int kRbSub = 64;    // sub-warps per CTA
 constexpr int kRbThreads = kRbRows * kRbSub;  // 512
 constexpr int kRbHdr = 68;    // u32 words per tile header: bounds[65], count, 2 pad (272 B)
 
-enum RbClass { RB_SUM = 0, RB_COUNT = 1, RB_MEAN = 2, RB_SUMSQ = 3, RB_VAR = 4 };
+enum RbClass {
+    RB_SUM = 0, RB_COUNT = 1, RB_MEAN = 2, RB_SUMSQ = 3, RB_VAR = 4,  // additive (mergeable with atomics)
+    RB_PROD = 5, RB_MAX = 6, RB_MIN = 7, RB_ARGMAX = 8, RB_ARGMIN = 9, RB_FIRST = 10, RB_LAST = 11, RB_ANY = 12, RB_ALL = 13
+};
 
 // ----------------------------------------------------------------------------------- plan
 template <typename L>
@@ -178,21 +182,24 @@ struct RbBin<V, RB_SUM> {
     V s;
     __device__ __forceinline__ void zero() { s = (V)0; }
     // `ok` false (NaN observation): adds +0, which leaves every reachable sum unchanged
-    __device__ __forceinline__ void add(V v, bool ok) { s = v_add(s, ok ? v : (V)0); }
+    template <typename I>
+    __device__ __forceinline__ void add(V v, bool ok, I) { s = v_add(s, ok ? v : (V)0); }
     __device__ __forceinline__ void merge(const RbBin &o) { s = v_add(s, o.s); }
 };
 template <typename V>
 struct RbBin<V, RB_SUMSQ> {
     V s;
     __device__ __forceinline__ void zero() { s = (V)0; }
-    __device__ __forceinline__ void add(V v, bool ok) { s = v_add(s, v_sq(ok ? v : (V)0)); }
+    template <typename I>
+    __device__ __forceinline__ void add(V v, bool ok, I) { s = v_add(s, v_sq(ok ? v : (V)0)); }
     __device__ __forceinline__ void merge(const RbBin &o) { s = v_add(s, o.s); }
 };
 template <typename V>
 struct RbBin<V, RB_COUNT> {
     typename RbCounter<V>::type c;
     __device__ __forceinline__ void zero() { c = 0; }
-    __device__ __forceinline__ void add(V, bool ok) { c += ok ? 1 : 0; }
+    template <typename I>
+    __device__ __forceinline__ void add(V, bool ok, I) { c += ok ? 1 : 0; }
     __device__ __forceinline__ void merge(const RbBin &o) { c += o.c; }
 };
 template <typename V>
@@ -203,7 +210,8 @@ struct alignas(2 * sizeof(V)) RbBin<V, RB_MEAN> {
         s = (V)0;
         c = 0;
     }
-    __device__ __forceinline__ void add(V v, bool ok) {
+    template <typename I>
+    __device__ __forceinline__ void add(V v, bool ok, I) {
         s = v_add(s, ok ? v : (V)0);
         c += ok ? 1 : 0;
     }
@@ -222,7 +230,8 @@ struct alignas(4 * sizeof(V)) RbBin<V, RB_VAR> {
         c = 0;
         pad = 0;
     }
-    __device__ __forceinline__ void add(V v, bool ok) {
+    template <typename I>
+    __device__ __forceinline__ void add(V v, bool ok, I) {
         const V m = ok ? v : (V)0;
         s = v_add(s, m);
         ss = v_add(ss, v_sq(m));
@@ -233,6 +242,112 @@ struct alignas(4 * sizeof(V)) RbBin<V, RB_VAR> {
         ss = v_add(ss, o.ss);
         c += o.c;
     }
+};
+
+// ---- non-additive classes: the reference's loop bodies on a privately owned bin ----------
+template <typename V>
+__device__ __forceinline__ V v_mul(V a, V b) {
+    return (V)((unsigned long long)a * (unsigned long long)b);
+}
+template <>
+__device__ __forceinline__ float v_mul<float>(float a, float b) {
+    return __fmul_rn(a, b);
+}
+template <>
+__device__ __forceinline__ double v_mul<double>(double a, double b) {
+    return __dmul_rn(a, b);
+}
+template <>
+__device__ __forceinline__ int32_t v_mul<int32_t>(int32_t a, int32_t b) {
+    return (int32_t)((uint32_t)a * (uint32_t)b);
+}
+
+template <typename V>
+struct RbBin<V, RB_PROD> {  // grouped.py:124-132
+    V pr;
+    __device__ __forceinline__ void zero() { pr = (V)1; }
+    template <typename I>
+    __device__ __forceinline__ void add(V v, bool ok, I) { pr = v_mul(pr, ok ? v : (V)1); }
+    __device__ __forceinline__ void merge(const RbBin &o) { pr = v_mul(pr, o.pr); }
+};
+template <typename V, bool IS_MAX>
+struct alignas(2 * sizeof(V)) RbExtreme {  // grouped.py:211-244: compare as double, first extreme wins
+    V best;
+    typename RbCounter<V>::type has;
+    __device__ __forceinline__ void zero() {
+        best = (V)0;
+        has = 0;
+    }
+    template <typename I>
+    __device__ __forceinline__ void add(V v, bool ok, I) {
+        const bool better = IS_MAX ? ((double)v > (double)best) : ((double)v < (double)best);
+        const bool take = ok && (!has || better);
+        best = take ? v : best;
+        has |= ok ? 1 : 0;
+    }
+};
+template <typename V>
+struct RbBin<V, RB_MAX> : RbExtreme<V, true> {};
+template <typename V>
+struct RbBin<V, RB_MIN> : RbExtreme<V, false> {};
+template <typename V, bool IS_MAX>
+struct alignas(4 * sizeof(V)) RbArgExtreme {  // grouped.py:54-92
+    V best;
+    typename RbCounter<V>::type idx, has, pad;
+    __device__ __forceinline__ void zero() {
+        best = (V)0;
+        idx = 0;
+        has = 0;
+        pad = 0;
+    }
+    template <typename I>
+    __device__ __forceinline__ void add(V v, bool ok, I gi) {
+        const bool better = IS_MAX ? ((double)v > (double)best) : ((double)v < (double)best);
+        const bool take = ok && (!has || better);
+        best = take ? v : best;
+        idx = take ? (typename RbCounter<V>::type)gi : idx;
+        has |= ok ? 1 : 0;
+    }
+};
+template <typename V>
+struct RbBin<V, RB_ARGMAX> : RbArgExtreme<V, true> {};
+template <typename V>
+struct RbBin<V, RB_ARGMIN> : RbArgExtreme<V, false> {};
+template <typename V, bool FIRST>
+struct alignas(4 * sizeof(V)) RbEdge {  // grouped.py:95-121: first / last valid value (+ its index)
+    V val;
+    typename RbCounter<V>::type idx, has, pad;
+    __device__ __forceinline__ void zero() {
+        val = (V)0;
+        idx = 0;
+        has = 0;
+        pad = 0;
+    }
+    template <typename I>
+    __device__ __forceinline__ void add(V v, bool ok, I gi) {
+        const bool take = FIRST ? (ok && !has) : ok;
+        val = take ? v : val;
+        idx = take ? (typename RbCounter<V>::type)gi : idx;
+        has |= ok ? 1 : 0;
+    }
+};
+template <typename V>
+struct RbBin<V, RB_FIRST> : RbEdge<V, true> {};
+template <typename V>
+struct RbBin<V, RB_LAST> : RbEdge<V, false> {};
+template <typename V>
+struct RbBin<V, RB_ANY> {  // grouped.py:247-257
+    typename RbCounter<V>::type flag;
+    __device__ __forceinline__ void zero() { flag = 0; }
+    template <typename I>
+    __device__ __forceinline__ void add(V v, bool ok, I) { flag |= (ok && v != (V)0) ? 1 : 0; }
+};
+template <typename V>
+struct RbBin<V, RB_ALL> {  // grouped.py:260-270
+    typename RbCounter<V>::type flag;
+    __device__ __forceinline__ void zero() { flag = 1; }
+    template <typename I>
+    __device__ __forceinline__ void add(V v, bool ok, I) { flag &= (ok && v == (V)0) ? 0 : 1; }
 };
 
 template <typename V, int CLS>
@@ -247,6 +362,7 @@ struct RbParams {
     int K, C;
     int ntiles, tiles_per_seg, nseg;
     int priv;  // sub-warp-private bins (few labels)
+    int64_t index_offset;  // flat index of column 0 of this shard (arg* / first / last)
 };
 
 template <typename V>
@@ -329,6 +445,7 @@ __global__ void __launch_bounds__(kRbThreads) group_rowbins_kernel(RbParams p) {
         const uint32_t ent_s = sb + kRbHdr * 4;
         const uint32_t tile_s = sb + (uint32_t)(kRbHdr + C) * 4 + (uint32_t)r * (uint32_t)stride * (uint32_t)sizeof(V);
         const int b0 = (int)hdr[sub], b1 = (int)hdr[sub + 1];
+        const int cbase = t * C;  // column of tile entry 0 within the row (n < 2^31 on this path)
         auto ent_at = [&](int i) -> uint32_t {
             return *reinterpret_cast<const uint32_t *>(__cvta_shared_to_generic(ent_s + (uint32_t)i * 4u));
         };
@@ -342,20 +459,20 @@ __global__ void __launch_bounds__(kRbThreads) group_rowbins_kernel(RbParams p) {
                 const V v0 = val_at(e0), v1 = val_at(e1), v2 = val_at(e2), v3 = val_at(e3);
                 // read-modify-write in entry order: consecutive entries may share a label
                 Bin *q0 = bin_at(e0);
-                { Bin b = *q0; b.add(v0, !is_nan(v0)); *q0 = b; }
+                { Bin b = *q0; b.add(v0, !is_nan(v0), cbase + (int)(e0 & 0xffffu)); *q0 = b; }
                 Bin *q1 = bin_at(e1);
-                { Bin b = *q1; b.add(v1, !is_nan(v1)); *q1 = b; }
+                { Bin b = *q1; b.add(v1, !is_nan(v1), cbase + (int)(e1 & 0xffffu)); *q1 = b; }
                 Bin *q2 = bin_at(e2);
-                { Bin b = *q2; b.add(v2, !is_nan(v2)); *q2 = b; }
+                { Bin b = *q2; b.add(v2, !is_nan(v2), cbase + (int)(e2 & 0xffffu)); *q2 = b; }
                 Bin *q3 = bin_at(e3);
-                { Bin b = *q3; b.add(v3, !is_nan(v3)); *q3 = b; }
+                { Bin b = *q3; b.add(v3, !is_nan(v3), cbase + (int)(e3 & 0xffffu)); *q3 = b; }
             }
             for (; i < b1; i++) {
                 const uint32_t e = ent_at(i);
                 const V v = val_at(e);
                 Bin *q = bin_at(e);
                 Bin b = *q;
-                b.add(v, !is_nan(v));
+                b.add(v, !is_nan(v), cbase + (int)(e & 0xffffu));
                 *q = b;
             }
         }
@@ -371,11 +488,17 @@ __global__ void __launch_bounds__(kRbThreads) group_rowbins_kernel(RbParams p) {
         const int rr = idx / K, k = idx - rr * K;  // consecutive threads -> consecutive labels
         if (rr >= nrows) continue;
         Bin b = bins[k * kRbRows + rr];
-        if (p.priv) {
-            for (int s2 = 1; s2 < kRbSub; s2++) b.merge(bins[(size_t)s2 * K * kRbRows + k * kRbRows + rr]);
+        if constexpr (CLS <= RB_VAR) {
+            if (p.priv) {
+                for (int s2 = 1; s2 < kRbSub; s2++) b.merge(bins[(size_t)s2 * K * kRbRows + k * kRbRows + rr]);
+            }
         }
         const size_t o = ((size_t)(r0 + rr) * K + k) * (size_t)p.ws_stride;  // record offset (words)
-        RbFlush<V, CLS>::flush(b, c0p + o, c1p + o, c2p + o, atomic);
+        if constexpr (CLS <= RB_VAR) {
+            RbFlush<V, CLS>::flush(b, c0p + o, c1p + o, c2p + o, atomic);
+        } else {
+            RbFlush<V, CLS>::flush(b, c0p + o, c1p + o, p.index_offset, atomic);
+        }
     }
 }
 
@@ -430,6 +553,109 @@ struct RbFlush<V, RB_VAR> {
     }
 };
 
+
+// Non-additive classes: merge the bin into the workspace record (this CTA is the only writer of
+// its rows' records; the record may already hold earlier shards of the same device).
+template <typename V>
+struct RbFlush<V, RB_PROD> {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, RB_PROD> &b, A *c0, A *, int64_t, bool atomic) {
+        // V-typed product (keeps the float32 rounding of the reference), CAS loop when several
+        // column segments share the record
+        unsigned long long *w = reinterpret_cast<unsigned long long *>(c0);
+        unsigned long long old = *w, assumed;
+        do {
+            assumed = old;
+            A cur;
+            memcpy(&cur, &assumed, 8);
+            A next;
+            if (std::is_floating_point<A>::value) next = (A)v_mul((V)cur, b.pr);
+            else next = (A)((unsigned long long)cur * (unsigned long long)(long long)b.pr);
+            unsigned long long nb;
+            memcpy(&nb, &next, 8);
+            if (!atomic) {
+                *w = nb;
+                break;
+            }
+            old = atomicCAS(w, assumed, nb);
+        } while (old != assumed);
+    }
+};
+template <typename V, int CLS>
+struct RbFlushExtreme {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, CLS> &b, A *c0, A *, int64_t, bool atomic) {
+        if (!b.has) return;
+        unsigned long long k = order_key((double)b.best);
+        if (CLS == RB_MIN) k = ~k;
+        unsigned long long *w = reinterpret_cast<unsigned long long *>(c0);
+        if (atomic) atomicMax(w, k);
+        else if (k > *w) *w = k;
+    }
+};
+template <typename V>
+struct RbFlush<V, RB_MAX> : RbFlushExtreme<V, RB_MAX> {};
+template <typename V>
+struct RbFlush<V, RB_MIN> : RbFlushExtreme<V, RB_MIN> {};
+template <typename V, int CLS>
+struct RbFlushArg {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, CLS> &b, A *c0, A *c1, int64_t off, bool) {
+        if (!b.has) return;
+        unsigned long long k = order_key((double)b.best);
+        if (CLS == RB_ARGMIN) k = ~k;
+        unsigned long long *w = reinterpret_cast<unsigned long long *>(c0);
+        long long *wi = reinterpret_cast<long long *>(c1);
+        const long long gi = (long long)b.idx + off;
+        if (k > *w) {
+            *w = k;
+            *wi = gi;
+        } else if (k == *w && gi < *wi) {
+            *wi = gi;
+        }
+    }
+};
+template <typename V>
+struct RbFlush<V, RB_ARGMAX> : RbFlushArg<V, RB_ARGMAX> {};
+template <typename V>
+struct RbFlush<V, RB_ARGMIN> : RbFlushArg<V, RB_ARGMIN> {};
+template <typename V, int CLS>
+struct RbFlushEdge {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, CLS> &b, A *c0, A *c1, int64_t off, bool) {
+        if (!b.has) return;
+        unsigned long long *w = reinterpret_cast<unsigned long long *>(c0);
+        long long *wi = reinterpret_cast<long long *>(c1);
+        const long long gi = (long long)b.idx + off;
+        const bool take = CLS == RB_FIRST ? (gi < *wi) : (gi > *wi);
+        if (take) {
+            unsigned long long bits;
+            if (sizeof(V) == 8) bits = *reinterpret_cast<const unsigned long long *>(&b.val);
+            else bits = (unsigned long long)*reinterpret_cast<const unsigned int *>(&b.val);
+            *w = bits;
+            *wi = gi;
+        }
+    }
+};
+template <typename V>
+struct RbFlush<V, RB_FIRST> : RbFlushEdge<V, RB_FIRST> {};
+template <typename V>
+struct RbFlush<V, RB_LAST> : RbFlushEdge<V, RB_LAST> {};
+template <typename V>
+struct RbFlush<V, RB_ANY> {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, RB_ANY> &b, A *c0, A *, int64_t, bool) {
+        if (b.flag) *reinterpret_cast<long long *>(c0) = 1;
+    }
+};
+template <typename V>
+struct RbFlush<V, RB_ALL> {
+    template <typename A>
+    __device__ static __forceinline__ void flush(const RbBin<V, RB_ALL> &b, A *c0, A *, int64_t, bool) {
+        if (!b.flag) *reinterpret_cast<long long *>(c0) = 0;
+    }
+};
+
 // ------------------------------------------------------------------------------------ host
 inline int rb_class_of(int op) {
     switch (op) {
@@ -444,6 +670,24 @@ inline int rb_class_of(int op) {
         case NBG_GROUP_NANVAR:
         case NBG_GROUP_NANSTD:
             return RB_VAR;
+        case NBG_GROUP_NANPROD:
+            return RB_PROD;
+        case NBG_GROUP_NANMAX:
+            return RB_MAX;
+        case NBG_GROUP_NANMIN:
+            return RB_MIN;
+        case NBG_GROUP_NANARGMAX:
+            return RB_ARGMAX;
+        case NBG_GROUP_NANARGMIN:
+            return RB_ARGMIN;
+        case NBG_GROUP_NANFIRST:
+            return RB_FIRST;
+        case NBG_GROUP_NANLAST:
+            return RB_LAST;
+        case NBG_GROUP_NANANY:
+            return RB_ANY;
+        case NBG_GROUP_NANALL:
+            return RB_ALL;
         default:
             return -1;
     }
@@ -461,7 +705,7 @@ static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
     constexpr int PER16 = 16 / (int)sizeof(V);
     if (K <= 0 || K > 65535 || n <= 0 || n >= ((int64_t)1 << 31) || (n % PER16) != 0 || rows < 1) return g;
     const int words = (int)(sizeof(RbBin<V, CLS>) / sizeof(V));
-    g.priv = (K * words <= 32) ? 1 : 0;
+    g.priv = (CLS <= RB_VAR && K * words <= 32) ? 1 : 0;
     int candidates[3] = {sizeof(V) == 4 ? 1024 : 512, sizeof(V) == 4 ? 512 : 256, sizeof(V) == 4 ? 256 : 128};
     if (const char *e = getenv("NBG_RB_C")) candidates[0] = candidates[1] = candidates[2] = atoi(e);  // tuning hook
     // prefer two CTAs per SM (<= ~110 KB), else whatever fits
@@ -484,6 +728,8 @@ static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
     // partial bins with atomics.
     const int64_t slots = (int64_t)kNumSMs * 2;
     int64_t nseg = groups >= 4 * slots ? 1 : (8 * slots + groups - 1) / groups;
+    // (value, index) states are merged by the owner only: no column segments for those
+    if (CLS == RB_ARGMAX || CLS == RB_ARGMIN || CLS == RB_FIRST || CLS == RB_LAST) nseg = 1;
     if (const char *e = getenv("NBG_RB_NSEG")) nseg = atoi(e);  // tuning hook
     if (nseg > g.ntiles) nseg = g.ntiles;
     if (nseg < 1) nseg = 1;
@@ -495,7 +741,7 @@ static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
 
 template <typename V, typename L, int CLS>
 static int rb_launch(const V *values, const L *labels, void *ws_ch[3], int64_t ws_stride, void *scratch, size_t scratch_bytes,
-                     int64_t rows, int64_t n, int64_t K, cudaStream_t stream, bool *handled) {
+                     int64_t rows, int64_t n, int64_t K, int64_t index_offset, cudaStream_t stream, bool *handled) {
     *handled = false;
     const RbGeometry g = rb_geometry<V, CLS>(rows, n, K);
     if (!g.ok || scratch == nullptr || scratch_bytes < g.plan_bytes) return NBG_OK;
@@ -513,6 +759,7 @@ static int rb_launch(const V *values, const L *labels, void *ws_ch[3], int64_t w
     p.plan = plan;
     p.ws_ch[0] = ws_ch[0], p.ws_ch[1] = ws_ch[1], p.ws_ch[2] = ws_ch[2];
     p.ws_stride = ws_stride;
+    p.index_offset = index_offset;
     p.rows = rows, p.n = n, p.K = (int)K, p.C = g.C;
     p.ntiles = g.ntiles, p.tiles_per_seg = g.tiles_per_seg, p.nseg = g.nseg, p.priv = g.priv;
     const int64_t groups = (rows + kRbRows - 1) / kRbRows;
