@@ -100,12 +100,7 @@ def empty_pinned(shape, dtype) -> np.ndarray:
     """A numpy array backed by page-locked host memory: H2D/D2H copies of such arrays run
     at full PCIe speed and asynchronously (used by bench.py's e2e leg)."""
     t = torch.empty(shape, dtype=_NP_TO_TORCH[np.dtype(dtype)], pin_memory=True)
-    arr = t.numpy()
-    _PINNED_KEEPALIVE[id(arr)] = t
-    return arr
-
-
-_PINNED_KEEPALIVE: dict[int, torch.Tensor] = {}
+    return t.numpy()  # the array's base keeps the pinned storage alive
 
 
 def stream_ptr() -> int:
@@ -124,7 +119,15 @@ class CoreView:
     C-contiguous input: pure reshape.  F-contiguous input: the reversed-axes view is
     C-contiguous, so it is used instead (again no copy) and results are permuted back.
     Anything else is made contiguous first (one extra pass; not on any BASELINE config).
+
+    A strided core axis (inner > 1) is handled by the column-walk kernels, one thread per
+    column.  When there are too few columns to fill the GPU and the core axis is long (the
+    (time, few series) layout with axis=0), the core axis is moved last with one transposing
+    copy instead, so the row-tile kernels can parallelise ALONG the core axis.
     """
+
+    MIN_COLUMNS = 32768   # fewer columns than this cannot occupy 148 SMs with one thread each
+    MIN_CORE_LEN = 2048
 
     def __init__(self, t: torch.Tensor, axis: int):
         nd = t.dim()
@@ -142,21 +145,35 @@ class CoreView:
                 self.transposed = True
             else:
                 t = t.contiguous()
+        shape = tuple(t.shape)
+        outer = math.prod(shape[:axis])
+        inner = math.prod(shape[axis + 1 :])
+        self.moved_from = None
+        if inner > 1 and outer * inner < self.MIN_COLUMNS and shape[axis] >= self.MIN_CORE_LEN:
+            self.moved_from = axis
+            t = t.movedim(axis, -1).contiguous()
+            axis = nd - 1
+            shape = tuple(t.shape)
+            outer, inner = outer * inner, 1
         self.t = t
         self.axis = axis
-        shape = tuple(t.shape)
         self.shape = shape
-        self.outer = math.prod(shape[:axis])
+        self.outer = outer
         self.n = shape[axis]
-        self.inner = math.prod(shape[axis + 1 :])
+        self.inner = inner
 
     def like(self, other: torch.Tensor) -> torch.Tensor:
-        """Bring a same-shaped operand into this view's memory order."""
+        """Bring an operand shaped like the data (along all but possibly the core axis) into
+        this view's memory order."""
         if self.transposed:
             other = other.permute(*reversed(range(other.dim())))
+        if self.moved_from is not None:
+            other = other.movedim(self.moved_from, -1)
         return other if other.is_contiguous() else other.contiguous()
 
     def restore(self, out: torch.Tensor) -> torch.Tensor:
+        if self.moved_from is not None:
+            out = out.movedim(-1, self.moved_from)
         if self.transposed:
             return out.permute(*reversed(range(out.dim())))
         return out

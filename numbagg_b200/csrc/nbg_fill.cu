@@ -56,6 +56,7 @@ struct FillPolicy {
     static constexpr int NSTREAM = 1;
     static constexpr int MIN_CTAS = 6;  // <= 42 registers: six 35 KB tiles per SM
     static constexpr bool REV = REV_;
+    static constexpr bool OVERLAP_INDEPENDENT = true;  // most chunks follow a valid value in the tile
     __device__ static __forceinline__ const T *stream_row(const ScanParams &p, int, int64_t row) {
         return reinterpret_cast<const T *>(p.in[0]) + row * p.n;
     }

@@ -200,6 +200,7 @@ struct ExpPolicy {
     static constexpr int NSTREAM = Op::NIN + (ALPHA_STREAM ? 1 : 0);
     static constexpr int MIN_CTAS = (Op::NCH <= 3 && !ALPHA_STREAM) ? 5 : 2;  // light ops: <= 51 registers; heavy: <= 128
     static constexpr bool REV = false;
+    static constexpr bool OVERLAP_INDEPENDENT = false;  // a chunk is carry-free only after ~7k elements of decay
     __device__ static __forceinline__ const T *stream_row(const ScanParams &p, int s, int64_t row) {
         if (ALPHA_STREAM && s == Op::NIN)
             return reinterpret_cast<const T *>(p.in[2]) + (p.alpha_nd ? row * p.n : 0);

@@ -193,6 +193,8 @@ __device__ __forceinline__ Agg lookback_exclusive(const ScanWorkspace<Agg> &ws, 
 // Generic row-tile chained-scan kernel.  Policy P supplies:
 //   using T;  using Agg;  static constexpr int NSTREAM;   (input streams staged per tile)
 //   static constexpr bool REV;                            (scan from the row end: bfill)
+//   static constexpr bool OVERLAP_INDEPENDENT;            (chunks with an absorbing in-tile prefix
+//                                                          skip the wait for the tile carry)
 //   __device__ static const T* stream_row(const ScanParams&, int s, int64_t row);
 //   __device__ static Agg load_carry(const ScanParams&, int64_t row);
 //   __device__ static void store_agg(const ScanParams&, int64_t row, const Agg&);
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(THREADS, P::MIN_CTAS) scan_rowtile_kernel(Scan
     constexpr int NS = P::NSTREAM;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    volatile int *s_flag = reinterpret_cast<volatile int *>(smem_raw + 16);  // carry published
     Agg *scratch = reinterpret_cast<Agg *>(smem_raw + 64);  // [THREADS/32] + carry + spare
     Agg *s_carry = scratch + THREADS / 32;
     unsigned char *streams = smem_raw + SM::header_bytes();
@@ -249,6 +252,7 @@ __global__ void __launch_bounds__(THREADS, P::MIN_CTAS) scan_rowtile_kernel(Scan
     // same forward-progress assumption CUB's single-pass scan makes).
     const int64_t tile_lin = blockIdx.x;
     if (tid == 0) {
+        *s_flag = 0;
         mbar_init(bar, 1);
         mbar_fence_init();
     }
@@ -294,7 +298,11 @@ __global__ void __launch_bounds__(THREADS, P::MIN_CTAS) scan_rowtile_kernel(Scan
     Agg tile_total;
     const Agg excl = block_scan_agg<Agg, THREADS>(mine, scratch, &tile_total);
 
-    // ---- tile carry: first tile of a row takes carry_in, the others look back
+    // ---- tile carry: first tile of a row takes carry_in, the others look back.  Only
+    // threads whose chunk state DEPENDS on the carry wait for it: a chunk whose in-tile
+    // prefix is absorbing (a valid value earlier in the tile for fills, an underflowed decay
+    // product for exp) starts pass B immediately, overlapping the look-back latency.
+    const bool independent = P::OVERLAP_INDEPENDENT && Agg::absorbing(excl);
     if (tid < 32) {
         const int64_t row_first = row * p.tiles_per_row;
         Agg carry;
@@ -309,14 +317,26 @@ __global__ void __launch_bounds__(THREADS, P::MIN_CTAS) scan_rowtile_kernel(Scan
             const Agg incl = Agg::combine(carry, tile_total);
             desc_publish(ws.desc + tile_lin, incl, kTileInclusive);
             *s_carry = carry;
+            __threadfence_block();
+            *s_flag = 1;
             if (p.agg_out && tile == p.tiles_per_row - 1) P::store_agg(p, row, incl);
         }
     }
-    __syncthreads();
     if (p.out == nullptr) return;
 
     // ---- pass B: re-run every chunk from its incoming state, emit outputs
-    const Agg state = Agg::combine(*s_carry, excl);
+    Agg state = excl;
+    if (P::OVERLAP_INDEPENDENT) {
+        if (!independent) {
+            while (*s_flag == 0) {
+            }
+            __threadfence_block();
+            state = Agg::combine(*s_carry, excl);
+        }
+    } else {
+        __syncthreads();  // hardware barrier: cheaper than spinning when every chunk needs the carry
+        state = Agg::combine(*s_carry, excl);
+    }
     T *row_out = reinterpret_cast<T *>(p.out) + row * p.n;
     T *sout = s_[0];  // in place: put(k) overwrites the element get(0, k) already consumed
     auto put = [&](int k, T v) {

@@ -473,3 +473,22 @@ def test_numpy_inputs_pipelined_in_row_blocks(nb):
         np.testing.assert_array_equal(nb.bfill(arr_a), oracle.bfill(a))
     a3 = a.reshape(96, 400, 500)
     assert_parity("move_sum", nb.move_sum(a3, window=7, min_count=1, axis=1), oracle.move_sum(a3, window=7, min_count=1, axis=1), scale=7.0)
+
+
+def test_time_major_layout_few_columns(nb):
+    """(time, few series) C-ordered arrays with axis=0: the core axis is strided and there
+    are too few columns for one-thread-per-column kernels, so it is transposed once and the
+    row-tile kernels run along it.  Values must not depend on the route taken."""
+    a = fixture_array((40_000, 6), nan_frac=0.3, seed=51)
+    b = a**2 + 1
+    assert_parity("move_mean", nb.move_mean(a, window=50, min_count=5, axis=0), oracle.move_mean(a, window=50, min_count=5, axis=0), scale=1.0)
+    assert_parity("move_cov", nb.move_cov(a, b, window=50, min_count=5, axis=0), oracle.move_cov(a, b, window=50, min_count=5, axis=0), scale=4.0)
+    assert_parity("move_exp_nanvar", nb.move_exp_nanvar(a, alpha=0.05, axis=0), oracle.move_exp_nanvar(a, alpha=0.05, axis=0), scale=1.0)
+    al = np.random.RandomState(52).rand(40_000, 6) * 0.5 + 0.01
+    assert_parity("move_exp_nanmean", nb.move_exp_nanmean(a, alpha=al, axis=0), oracle.move_exp_nanmean(a, alpha=al, axis=0), scale=1.0)
+    assert_parity("move_exp_nansum", nb.move_exp_nansum(a, alpha=al[:, 0].copy(), axis=0), oracle.move_exp_nansum(a, alpha=al[:, 0].copy(), axis=0), scale=100.0)
+    for limit in (None, 4):
+        np.testing.assert_array_equal(nb.ffill(a, limit=limit, axis=0), oracle.ffill(a, limit=limit, axis=0))
+        np.testing.assert_array_equal(nb.bfill(a, limit=limit, axis=0), oracle.bfill(a, limit=limit, axis=0))
+    a3 = fixture_array((3, 5000, 4), seed=53)
+    assert_parity("move_sum", nb.move_sum(a3, window=9, min_count=1, axis=1), oracle.move_sum(a3, window=9, min_count=1, axis=1), scale=9.0)
