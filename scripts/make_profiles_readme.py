@@ -1,0 +1,31 @@
+"""profiles/README.md from a bench_all.jsonl (scripts/run_all_benches.sh).  usage: make_profiles_readme.py <jsonl> <tag>"""
+import json, sys
+path, tag = sys.argv[1], sys.argv[2]
+rows = []
+for line in open(path):
+    try:
+        d = json.loads(line)
+    except Exception:
+        continue
+    if "config" in d:
+        rows.append(d)
+out = [f"# profiles — round {tag}", "",
+       "All numbers from one B200 (`gpurun`), device-resident inputs, CUDA events, >= 3 warm-up steps,",
+       "inputs larger than L2 (except cfg1).  `roofline` = algorithmic bytes / step time / measured copy",
+       "bandwidth (6447.8 GB/s, MEASURED_PEAKS.json).  `e2e` = public numpy API with pinned host buffers",
+       "(H2D + kernels + D2H inside the timed region; row blocks are pipelined on three streams).",
+       "`cpu` = oracle port (C, OpenMP over rows) on the box's 16 host cores; 1-D inputs use one core,",
+       "like the reference's gufunc.", "",
+       "| workload | shape | Gel/s | ms/step | roofline (of measured) | e2e Gel/s | cpu Gel/s (cores) | kernels/step |",
+       "|---|---|---:|---:|---:|---:|---:|---:|"]
+for d in rows:
+    c = d["config"]
+    out.append(f"| {c['workload']} ({c['func']}, {d['dtype']}) | {c['shape'][0]}x{c['shape'][1]} | {d['value']/1e9:.1f} | {d['ms_per_step']:.3f} | "
+               f"{d['roofline']['frac']:.3f} | {d['e2e']['value']/1e9:.2f} | {d['cpu_baseline']['value']/1e9:.2f} ({d['cpu_baseline']['cores']}) | {d['gpu_launches']/d['steps']:.0f} |")
+out += ["", "Files:", "",
+        "* `*_bench_all*.jsonl` — the raw bench.py JSON lines behind the table.",
+        "* `*_launches_default_bench*.csv` — ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`) of the default bench command; the row-bins kernel is ~99 % of each step.",
+        "* `*_ncu_*.txt` — per-kernel summaries of `ncu --set full` captures (scripts/ncu_summary.py): duration, DRAM bytes (= algorithmic bytes: no re-reads), pipe utilisation, stall reasons, top stalled SASS instructions.",
+        ""]
+open("profiles/README.md", "w").write("\n".join(out))
+print("\n".join(out[:40]))
