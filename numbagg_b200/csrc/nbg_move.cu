@@ -96,6 +96,13 @@ struct OpVar {
     }
     __device__ static __forceinline__ T finalize_fast(const double *s, double rc, double rc1) {
         const double v = dmul(dsub(s[1], dmul(dmul(s[0], s[0]), rc)), rc1);
+        if constexpr (SQRT && std::is_same<T, float>::value) {
+            // float32 output: the square root of the float32-rounded variance is within 1 ulp
+            // (6e-8) of rounding the double root; values outside the float range take the
+            // double path (also negatives -> NaN, 0 -> 0)
+            if (v > 1e-30 && v < 1e30) return __fsqrt_rn((float)v);
+            return (T)sqrt(v);
+        }
         return (T)(SQRT ? fast_sqrt(v) : v);
     }
 };
@@ -145,6 +152,9 @@ struct OpCorr {
         const double var_b = dsub(dmul(s[4], rc), dmul(avg_b, avg_b));
         const double cov = dsub(dmul(s[2], rc), dmul(avg_a, avg_b));
         const double vv = dmul(var_a, var_b);
+        if constexpr (std::is_same<T, float>::value) {
+            if (vv > 1e-30 && vv < 1e30) return __fmul_rn((float)cov, rsqrtf((float)vv));  // ~2e-7 relative
+        }
         return vv > 0 ? (T)dmul(cov, (vv > 1e-35 && vv < 1e35) ? fast_rsqrt(vv) : rsqrt(vv)) : quiet_nan<T>();
     }
 };

@@ -43,6 +43,12 @@ struct ExpMean {  // moving_exp.py:41-72    channels: numer, denom, weight
         c[2] = alpha;
     }
     __device__ static __forceinline__ T output(const double *s, bool, double mw) {
+        if constexpr (std::is_same<T, float>::value) {
+            // float32 output: divide in float32 when both operands are comfortably inside its
+            // range (<= 1.5 ulp = 2e-7 from rounding the double quotient), else in double
+            if (fabs(s[0]) < 1e30 && s[1] > 1e-30 && s[1] < 1e30)
+                return s[2] >= mw ? __fdiv_rn((float)s[0], (float)s[1]) : quiet_nan<T>();
+        }
         return s[2] >= mw ? (T)(s[0] / s[1]) : quiet_nan<T>();
     }
 };
