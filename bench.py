@@ -33,6 +33,16 @@ sys.path.insert(0, ROOT)
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+def measured_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
+    committed `ncu --set full` capture of this exact workload (profiles/r01_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return float(json.load(f)[workload]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -347,7 +357,7 @@ def run_ours(args, wl):
                      ms_per_step=e_s * 1e3, note="public numpy API; pinned host input; H2D + kernels + D2H timed"),
             gpu_launches=int(launches),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                          traffic=None, peak_source=peak_src,
+                          traffic=measured_traffic(args.workload), peak_source=peak_src,
                           note="algorithmic bytes per step / CUDA-event step time (all kernels of the step)"),
             cpu_baseline=base,
         )
