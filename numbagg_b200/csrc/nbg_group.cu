@@ -200,10 +200,12 @@ __global__ void __launch_bounds__(256) group_atomic_kernel(const V *__restrict__
     for (int q = 0; q < PER; q++) {
         const int64_t i = base + (int64_t)q * 256 + threadIdx.x;
         if (i >= n) break;
-        int64_t label = (int64_t)lrow[i];
+        // streaming loads (evict-first): the inputs are read once and must not push the
+        // accumulator table out of L2, where the atomics are resolved
+        int64_t label = (int64_t)__ldcs(lrow + i);
         if (label < 0 || label >= K) continue;
         label *= ws.stride;  // record offset in 8-byte words
-        const V v = vrow[i];
+        const V v = __ldcs(vrow + i);
         if (is_nan(v)) continue;
         const int64_t gi = index_offset + i;
         if (OP == NBG_GROUP_NANSUM) {
