@@ -110,6 +110,65 @@ def _rows_pipelined(host_arrs: list[np.ndarray], work_dtype: np.dtype, axis: int
     return host_out.numpy()
 
 
+def _core_pipelined(host_arrs: list[np.ndarray], work_dtype: np.dtype, reverse: bool, chunk_fn) -> np.ndarray | None:
+    """1-D numpy inputs (one long core axis): stream the axis through the GPU in chunks, in
+    scan order, handing the running state from chunk to chunk ON THE DEVICE -- the same
+    halo / carry protocol the multi-GPU shards use (include/nbg_b200.h) -- while the H2D copy
+    of the next chunk and the D2H copy of the previous one overlap with the kernels.
+    `chunk_fn(device_chunks, state) -> (device_out, new_state)`; `state` is None for the
+    first chunk.  Returns None when the input does not qualify."""
+    a0 = host_arrs[0]
+    full_shape = a0.shape
+    if a0.ndim == 0 or a0.size != a0.shape[-1] or a0.nbytes < _PIPELINE_MIN_BYTES:
+        return None  # not a single long slice along the last axis
+    if any(x.shape != a0.shape or not x.flags.c_contiguous or x.dtype != work_dtype for x in host_arrs):
+        return None
+    host_arrs = [x.reshape(-1) for x in host_arrs]
+    a0 = host_arrs[0]
+    device = dev.require_cuda()
+    tdt = dev._NP_TO_TORCH[np.dtype(work_dtype)]
+    n = a0.shape[0]
+    nchunks = int(max(2, a0.nbytes // _PIPELINE_CHUNK_BYTES))
+    bounds = [n * i // nchunks for i in range(nchunks + 1)]
+    order = range(nchunks - 1, -1, -1) if reverse else range(nchunks)
+    host_in = [torch.from_numpy(x) for x in host_arrs]
+    host_out = torch.empty(a0.shape, dtype=tdt, pin_memory=True)
+    main = torch.cuda.current_stream(device)
+    copy_in, copy_out = _pipeline_streams(device)[:2]
+    copy_in.wait_stream(main)
+    copy_out.wait_stream(main)
+    state = None
+    staged = {}
+
+    def stage(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        with torch.cuda.stream(copy_in):
+            t = [h[lo:hi].to(device, non_blocking=True) for h in host_in]
+            ev = torch.cuda.Event()
+            ev.record(copy_in)
+        staged[i] = (t, ev)
+
+    seq = list(order)
+    stage(seq[0])
+    for pos, i in enumerate(seq):
+        if pos + 1 < len(seq):
+            stage(seq[pos + 1])  # prefetch while chunk i computes
+        d_in, ev = staged.pop(i)
+        main.wait_event(ev)
+        d_out, state = chunk_fn(d_in, state)
+        for t in d_in:
+            t.record_stream(main)
+        done = torch.cuda.Event()
+        done.record(main)
+        copy_out.wait_event(done)
+        with torch.cuda.stream(copy_out):
+            host_out[bounds[i]:bounds[i + 1]].copy_(d_out, non_blocking=True)
+        d_out.record_stream(copy_out)
+    main.wait_stream(copy_out)
+    main.synchronize()
+    return host_out.numpy().reshape(full_shape)
+
+
 class NumbaBase:
     """Counterpart of numbagg.decorators.NumbaBase (:103-162): carries the function's
     name/doc, ``repr`` and public signature.  ``target`` is always "cuda"."""
@@ -194,6 +253,15 @@ class ndmove(NumbaBase):
         if not as_tensor and out is None:
             piped = _rows_pipelined(list(arr), dt, axis,
                                     lambda ts: run_move(self.__name__, ts, window, min_count, axis))
+            if piped is None:
+                def chunk(ts, halos):
+                    o = run_move(self.__name__, ts, window, min_count, 0, halos)
+                    # next chunk's halo: the last `window` elements seen so far
+                    new = [t[-window:] if t.shape[0] >= window else
+                           (torch.cat([h, t])[-window:] if halos else t) for t, h in zip(ts, halos or ts)]
+                    return o, [x.contiguous() for x in new]
+                if axis % arr[0].ndim == arr[0].ndim - 1:
+                    piped = _core_pipelined(list(arr), dt, False, chunk)
             if piped is not None:
                 return piped
         ts = [dev.to_device(a, dt) for a in arr]
@@ -281,6 +349,9 @@ class ndmoveexp(NumbaBase):
             m_s = float(np.float32(min_weight)) if dt == _F32 else float(min_weight)
             piped = _rows_pipelined(list(arr), dt, axis,
                                     lambda ts: run_move_exp(self.__name__, ts, a_s, m_s, axis)[0])
+            if piped is None and axis % arr[0].ndim == arr[0].ndim - 1:
+                piped = _core_pipelined(list(arr), dt, False,
+                                        lambda ts, st: run_move_exp(self.__name__, ts, a_s, m_s, 0, st, True, True))
             if piped is not None:
                 return piped
         ts = [dev.to_device(a, dt) for a in arr]
@@ -355,6 +426,9 @@ class ndfill(NumbaBase):
         work = _F32 if dt == np.dtype(np.float16) else dt  # float16 <-> float32 is exact
         if not as_tensor and out is None and work == dt:
             piped = _rows_pipelined([arr], dt, axis, lambda ts: run_fill(self.__name__, ts[0], limit, axis)[0])
+            if piped is None and axis % arr.ndim == arr.ndim - 1:
+                piped = _core_pipelined([arr], dt, self.__name__ == "bfill",
+                                        lambda ts, st: run_fill(self.__name__, ts[0], limit, 0, st, True, True))
             if piped is not None:
                 return piped
         t = dev.to_device(arr, work)

@@ -492,3 +492,25 @@ def test_time_major_layout_few_columns(nb):
         np.testing.assert_array_equal(nb.bfill(a, limit=limit, axis=0), oracle.bfill(a, limit=limit, axis=0))
     a3 = fixture_array((3, 5000, 4), seed=53)
     assert_parity("move_sum", nb.move_sum(a3, window=9, min_count=1, axis=1), oracle.move_sum(a3, window=9, min_count=1, axis=1), scale=9.0)
+
+
+def test_numpy_1d_inputs_pipelined_along_core_axis(nb):
+    """Long 1-D numpy inputs are streamed in core-axis chunks with the state (halo / carry)
+    handed from chunk to chunk on the device."""
+    n = 30_000_000  # 240 MB float64 -> 2 chunks
+    a = fixture_array((n,), nan_frac=0.3, seed=61)
+    a[14_998_000:15_002_000] = np.nan  # a NaN run across the chunk boundary (shorter than the
+    # ~7070 steps after which 0.9**k underflows: beyond that the reference returns ratios of
+    # stuck subnormals -- DESIGN.md "known parity limits")
+    assert_parity("move_exp_nanmean", nb.move_exp_nanmean(a, alpha=0.1), oracle.move_exp_nanmean(a, alpha=0.1), scale=1.0)
+    # (slow decays are kept to ~1e4-term memories: with alpha=1e-7 two valid evaluation orders of
+    # the 1e7-term recurrence already differ by 2e-11 relative)
+    assert_parity("move_exp_nansum", nb.move_exp_nansum(a, alpha=1e-4, min_weight=1e-4), oracle.move_exp_nansum(a, alpha=1e-4, min_weight=1e-4), scale=1e4)
+    assert_parity("move_exp_nanmean", nb.move_exp_nanmean(a.reshape(1, 1, n), alpha=0.1), oracle.move_exp_nanmean(a.reshape(1, 1, n), alpha=0.1), scale=1.0)
+    a[9_000_000:16_000_000] = np.nan  # fills: a NaN run of 7M elements across the chunk boundary
+    for limit in (None, 5, 6_500_000):
+        np.testing.assert_array_equal(nb.ffill(a, limit=limit), oracle.ffill(a, limit=limit))
+        np.testing.assert_array_equal(nb.bfill(a, limit=limit), oracle.bfill(a, limit=limit))
+    b = a**2 + 1
+    assert_parity("move_mean", nb.move_mean(a, window=1000, min_count=10), oracle.move_mean(a, window=1000, min_count=10), scale=1.0)
+    assert_parity("move_cov", nb.move_cov(a, b, window=50, min_count=5), oracle.move_cov(a, b, window=50, min_count=5), scale=4.0)
