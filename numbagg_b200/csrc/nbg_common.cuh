@@ -82,8 +82,6 @@ __device__ __forceinline__ double quiet_nan<double>() {
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 
 // Product of two inputs in the INPUT type, then widened: numba types float32*float32 as
 // float32 (verified bit-for-bit against the reference in tests/test_gpu_golden.py).
@@ -235,47 +233,6 @@ __device__ __forceinline__ void span_store(T *g, const T *s, int cnt) {
     }
     for (int j = tid; j < head; j += THREADS) g[j] = s[j];
     for (int j = head + blk + tid; j < cnt; j += THREADS) g[j] = s[j];
-}
-
-// ---- block-wide exclusive scan of doubles (in place, in shared memory) ------------------
-// arr[0..m) -> exclusive prefix sums; arr[m] receives the total.  THREADS threads, all call.
-template <int THREADS>
-__device__ __forceinline__ void block_exclusive_scan(double *arr, int m, double *warp_scratch /* >= 32 */) {
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, wid = tid >> 5;
-    const int per = (m + THREADS - 1) / THREADS;
-    const int beg = min(tid * per, m), end = min(beg + per, m);
-    double local = 0.0;
-    for (int j = beg; j < end; j++) local += arr[j];
-    // inclusive warp scan
-    double inc = local;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        double o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += o;
-    }
-    if (lane == 31) warp_scratch[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        double w = (lane < THREADS / 32) ? warp_scratch[lane] : 0.0;
-        double winc = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            double o = __shfl_up_sync(0xffffffffu, winc, d);
-            if (lane >= d) winc += o;
-        }
-        warp_scratch[lane] = winc - w;  // exclusive warp offsets
-        if (lane == 31) warp_scratch[32] = winc;  // grand total (lane 31 holds sum of all 32 slots)
-    }
-    __syncthreads();
-    double run = warp_scratch[wid] + (inc - local);
-    for (int j = beg; j < end; j++) {
-        double v = arr[j];
-        arr[j] = run;
-        run += v;
-    }
-    if (tid == 0) arr[m] = warp_scratch[32];
-    __syncthreads();
 }
 
 }  // namespace nbg
