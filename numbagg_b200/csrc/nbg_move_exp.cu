@@ -204,7 +204,7 @@ struct ExpPolicy {
     using Op = Op_;
     using Agg = ExpAgg<Op>;
     static constexpr int NSTREAM = Op::NIN + (ALPHA_STREAM ? 1 : 0);
-    static constexpr int MIN_CTAS = (Op::NCH <= 3 && !ALPHA_STREAM) ? 5 : 2;  // light ops: <= 51 registers; heavy: <= 128
+    static constexpr int MIN_CTAS = (Op::NCH <= 3 && !ALPHA_STREAM) ? 5 : (Op::NCH <= 5 ? 4 : 3);  // register caps: 51 / 64 / 85
     static constexpr bool REV = false;
     static constexpr bool OVERLAP_INDEPENDENT = false;  // a chunk is carry-free only after ~7k elements of decay
     __device__ static __forceinline__ const T *stream_row(const ScanParams &p, int s, int64_t row) {
