@@ -34,6 +34,25 @@ constexpr int kRbSub = 64;    // sub-warps per CTA
 constexpr int kRbThreads = kRbRows * kRbSub;  // 512
 constexpr int kRbHdr = 68;    // u32 words per tile header: bounds[65], count, 2 pad (272 B)
 
+// Bin slot of a label.  The 64 label ranges a tile is cut into are, for labels that are
+// roughly uniform, close to the NOMINAL ranges [s*W, (s+1)*W), W = ceil(K/64).  Slots are laid
+// out so that the four sub-warps of a warp (nominal ranges 4g..4g+3) own slots = 0,1,2,3 mod 4:
+// bins[slot][row] is 8 consecutive words per slot, so those four sub-warps then touch four
+// different bank octets and their bin accesses stop conflicting.  (A pure performance
+// permutation: any label distribution stays correct.)  W == 0: identity.
+__host__ __device__ inline int rb_slot_of(int label, int W) {
+    if (W == 0) return label;
+    const int s_nom = label / W, j = label - s_nom * W;
+    return ((s_nom >> 2) * W + j) * 4 + (s_nom & 3);
+}
+__host__ __device__ inline int rb_label_of(int slot, int W) {
+    if (W == 0) return slot;
+    const int q = slot & 3, t = slot >> 2;
+    const int g = t / W, j = t - g * W;
+    return (g * 4 + q) * W + j;
+}
+__host__ __device__ inline int rb_num_slots(int K, int W) { return W == 0 ? K : 64 * W; }
+
 enum RbClass {
     RB_SUM = 0, RB_COUNT = 1, RB_MEAN = 2, RB_SUMSQ = 3, RB_VAR = 4,  // additive (mergeable with atomics)
     RB_PROD = 5, RB_MAX = 6, RB_MIN = 7, RB_ARGMAX = 8, RB_ARGMIN = 9, RB_FIRST = 10, RB_LAST = 11, RB_ANY = 12, RB_ALL = 13
@@ -42,7 +61,7 @@ enum RbClass {
 // ----------------------------------------------------------------------------------- plan
 template <typename L>
 __global__ void __launch_bounds__(256) group_plan_kernel(const L *__restrict__ labels, int64_t n, int K, int C,
-                                                         int even_split, uint32_t *__restrict__ plan) {
+                                                         int even_split, int W, uint32_t *__restrict__ plan) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int *offs = reinterpret_cast<int *>(smem_raw);        // [K + 1] histogram -> exclusive offsets
     int *cursor = offs + (K + 1);                          // [K]
@@ -107,7 +126,7 @@ __global__ void __launch_bounds__(256) group_plan_kernel(const L *__restrict__ l
             if (valid) {
                 const int rank = __popc(m & ((1u << lane) - 1u));
                 const int base = cursor[lab];
-                sent[base + rank] = (lab << 16) | (uint32_t)j;
+                sent[base + rank] = ((uint32_t)rb_slot_of((int)lab, W) << 16) | (uint32_t)j;
             }
             __syncwarp();
             if (valid && (m & ((1u << lane) - 1u)) == 0) cursor[lab] += __popc(m);
@@ -122,7 +141,7 @@ __global__ void __launch_bounds__(256) group_plan_kernel(const L *__restrict__ l
             b = count;
         } else {
             const int e = (int)(((long long)tid * count) / kRbSub);
-            b = even_split ? e : offs[sent[e] >> 16];  // start of the label run containing e
+            b = even_split ? e : offs[rb_label_of((int)(sent[e] >> 16), W)];  // start of the label run containing e
         }
         out[tid] = (uint32_t)b;
     }
@@ -362,6 +381,7 @@ struct RbParams {
     int K, C;
     int ntiles, tiles_per_seg, nseg;
     int priv;  // sub-warp-private bins (few labels)
+    int W;     // nominal label-range width of the slot permutation (0: identity)
     int64_t index_offset;  // flat index of column 0 of this shard (arg* / first / last)
 };
 
@@ -373,9 +393,15 @@ template <typename V, int CLS>
 __host__ __device__ inline size_t rb_stage_bytes(int C) {
     return ((size_t)(kRbHdr + C) * 4 + (size_t)kRbRows * rb_row_stride<V>(C) * sizeof(V) + 15) & ~(size_t)15;
 }
+// the slot permutation only pays while one slot (8 rows x bin) spans fewer than 32 banks
+template <typename V, int CLS>
+__host__ __device__ inline int rb_nominal_width(int K, int priv) {
+    return (priv || sizeof(RbBin<V, CLS>) > 8) ? 0 : (K + 63) / 64;
+}
 template <typename V, int CLS>
 __host__ __device__ inline size_t rb_bins_bytes(int K, int priv) {
-    return ((size_t)K * kRbRows * (priv ? kRbSub : 1) * sizeof(RbBin<V, CLS>) + 15) & ~(size_t)15;
+    const int slots = rb_num_slots(K, rb_nominal_width<V, CLS>(K, priv));
+    return ((size_t)slots * kRbRows * (priv ? kRbSub : 1) * sizeof(RbBin<V, CLS>) + 15) & ~(size_t)15;
 }
 template <typename V, int CLS>
 __host__ __device__ inline size_t rb_smem_bytes(int K, int C, int priv) {
@@ -405,7 +431,8 @@ __global__ void __launch_bounds__(kRbThreads) group_rowbins_kernel(RbParams p) {
     const int t_end = min(t_beg + p.tiles_per_seg, p.ntiles);
     const V *vbase = reinterpret_cast<const V *>(p.values) + r0 * p.n;
 
-    const int nbins = K * kRbRows * (p.priv ? kRbSub : 1);
+    const int nslots = rb_num_slots(K, p.W);
+    const int nbins = nslots * kRbRows * (p.priv ? kRbSub : 1);
     for (int i = tid; i < nbins; i += kRbThreads) bins[i].zero();
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -487,7 +514,7 @@ __global__ void __launch_bounds__(kRbThreads) group_rowbins_kernel(RbParams p) {
     for (int idx = tid; idx < K * kRbRows; idx += kRbThreads) {
         const int rr = idx / K, k = idx - rr * K;  // consecutive threads -> consecutive labels
         if (rr >= nrows) continue;
-        Bin b = bins[k * kRbRows + rr];
+        Bin b = bins[rb_slot_of(k, p.W) * kRbRows + rr];
         if constexpr (CLS <= RB_VAR) {
             if (p.priv) {
                 for (int s2 = 1; s2 < kRbSub; s2++) b.merge(bins[(size_t)s2 * K * kRbRows + k * kRbRows + rr]);
@@ -751,7 +778,8 @@ static int rb_launch(const V *values, const L *labels, void *ws_ch[3], int64_t w
     auto pk = group_plan_kernel<L>;
     int rc = allow_big_smem(pk, "nbg_group(plan): cudaFuncSetAttribute");
     if (rc) return rc;
-    pk<<<(unsigned)g.ntiles, 256, plan_smem, stream>>>(labels, n, (int)K, g.C, g.priv, plan);
+    const int W = rb_nominal_width<V, CLS>((int)K, g.priv);
+    pk<<<(unsigned)g.ntiles, 256, plan_smem, stream>>>(labels, n, (int)K, g.C, g.priv, W, plan);
     rc = check_launch("nbg_group(plan)");
     if (rc) return rc;
     RbParams p;
@@ -760,6 +788,7 @@ static int rb_launch(const V *values, const L *labels, void *ws_ch[3], int64_t w
     p.ws_ch[0] = ws_ch[0], p.ws_ch[1] = ws_ch[1], p.ws_ch[2] = ws_ch[2];
     p.ws_stride = ws_stride;
     p.index_offset = index_offset;
+    p.W = W;
     p.rows = rows, p.n = n, p.K = (int)K, p.C = g.C;
     p.ntiles = g.ntiles, p.tiles_per_seg = g.tiles_per_seg, p.nseg = g.nseg, p.priv = g.priv;
     const int64_t groups = (rows + kRbRows - 1) / kRbRows;
