@@ -126,3 +126,49 @@ def test_group_validation():
         nb.group_nansum(v, np.zeros((3, 3), dtype=np.int64), axis=(0, 1))
     with pytest.raises(TypeError, match="does not support boolean input"):
         nb.group_nanvar(np.array([True, False]), np.array([0, 0]))
+
+
+def test_c_abi_rejects_bad_arguments_without_a_device():
+    """Argument errors are reported through return codes + nbg_last_error() before any CUDA
+    call is made (numbagg raises Python exceptions before dispatch; the C layer never throws)."""
+    L = _lib.lib()
+    err = lambda: L.nbg_last_error().decode()
+    dummy = ctypes.c_void_p(256)
+    # window must be positive; dtype must be a float type; negative sizes
+    assert L.nbg_move(0, _lib.NBG_F64, dummy, None, dummy, 1, 10, 1, 0, 1, None, None, 0, None) == -3 and "window" in err()
+    assert L.nbg_move(0, _lib.NBG_I32, dummy, None, dummy, 1, 10, 1, 3, 1, None, None, 0, None) == -1 and "dtype" in err()
+    assert L.nbg_move(0, _lib.NBG_F64, dummy, None, dummy, -1, 10, 1, 3, 1, None, None, 0, None) == -3
+    assert L.nbg_move(4, _lib.NBG_F64, dummy, None, dummy, 1, 10, 1, 3, 1, None, None, 0, None) == -3  # cov needs b
+    assert L.nbg_move(99, _lib.NBG_F64, dummy, None, dummy, 1, 10, 1, 3, 1, None, None, 0, None) == -2
+    assert L.nbg_move(0, _lib.NBG_F64, dummy, None, dummy, 1, 10, 1, 3, 1, None, None, 5, None) == -3  # halo_len without halo
+    # empty problems are fine and launch nothing
+    before = L.nbg_launch_count()
+    assert L.nbg_move(0, _lib.NBG_F64, None, None, None, 0, 10, 1, 3, 1, None, None, 0, None) == 0
+    assert L.nbg_launch_count() == before
+    assert L.nbg_fill(7, 8, dummy, dummy, 1, 10, 1, 3, None, None, None, 0, None) == -2
+    assert L.nbg_fill(0, 2, dummy, dummy, 1, 10, 1, 3, None, None, None, 0, None) == -1 and "itemsize" in err()
+    assert L.nbg_fill(0, 8, dummy, dummy, 1, 10, 1, -1, None, None, None, 0, None) == -3 and "limit" in err()
+    assert L.nbg_fill(0, 8, dummy, None, 1, 10, 1, 3, None, None, None, 0, None) == -3  # neither out nor agg_out
+    assert L.nbg_move_exp(0, _lib.NBG_I64, dummy, None, None, 0, 0.5, 0.0, dummy, 1, 10, 1, None, None, None, 0, None) == -1
+    assert L.nbg_move_exp(5, _lib.NBG_F64, dummy, None, None, 0, 0.5, 0.0, dummy, 1, 10, 1, None, None, None, 0, None) == -3  # cov needs a2
+    # grouped: float-only ops refuse integer values; workspace size is checked
+    assert L.nbg_group_accumulate(_lib.GROUP_OPS["group_nanvar"], _lib.NBG_I32, _lib.NBG_I64, dummy, dummy, 0, dummy,
+                                  1 << 30, 1, 10, 4, 0, None) == -1
+    assert L.nbg_group(_lib.GROUP_OPS["group_nansum"], _lib.NBG_F64, _lib.NBG_I64, dummy, dummy, 0, dummy, 1, 10, 4, 1,
+                       dummy, 8, None) == -6 and "workspace" in err()
+    assert L.nbg_group_record_words(_lib.GROUP_OPS["group_nanvar"]) == 4
+    assert L.nbg_group_record_words(_lib.GROUP_OPS["group_nansum"]) == 1
+    assert L.nbg_group_workspace_bytes(1, _lib.NBG_F32, 10, 1000, 7) >= 10 * 7 * 8
+
+
+def test_c_abi_header_constants_match_python_binding():
+    text = open(os.path.join(ROOT, "include", "nbg_b200.h")).read()
+    for name, value in (("NBG_EXP_STATE", _lib.NBG_EXP_STATE), ("NBG_FILL_STATE", _lib.NBG_FILL_STATE),
+                        ("NBG_GROUP_WS_CHANNELS", _lib.NBG_GROUP_WS_CHANNELS), ("NBG_ABI_VERSION", 1)):
+        m = re.search(rf"#define\s+{name}\s+(\d+)", text)
+        assert m and int(m.group(1)) == value, name
+    for table, prefix in ((_lib.MOVE_OPS, "NBG_"), (_lib.EXP_OPS, "NBG_"), (_lib.GROUP_OPS, "NBG_")):
+        for fname, code in table.items():
+            enum = prefix + fname.upper().replace("MOVE_EXP_", "EXP_")
+            m = re.search(rf"\b{enum}\s*=\s*(\d+)", text)
+            assert m and int(m.group(1)) == code, enum
