@@ -187,6 +187,49 @@ int nbg_group(int op, int vdtype, int ldtype, const void *values, const void *la
               int labels_per_row, void *out, int64_t rows, int64_t n, int64_t num_labels,
               int64_t ddof, void *workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * Plain NaN-aware reductions (the first row past the hot path): allnan, anynan,
+ * nancount, nansum, nanmean, nanvar, nanstd behind ndaggregate (numbagg/decorators.py:188-260)
+ * and nanargmax, nanargmin, nanmax, nanmin behind ndreduce (decorators.py:906-1031), bodies
+ * in numbagg/funcs.py:23-242.  `a` is a C-contiguous (outer, n, inner) array and the middle
+ * axis is reduced (the dispatchers' move_axes/moveaxis + flatten of the reduced axes, which
+ * the caller does by choosing outer/n/inner or by permuting); `out` has outer*inner
+ * elements of:  uint8 (ALLNAN, ANYNAN) | int64 (NANCOUNT, NANARGMAX, NANARGMIN) | the input
+ * dtype (NANSUM; NANMEAN, NANVAR, NANSTD -- float inputs only; NANMAX, NANMIN on floats) |
+ * int64 (NANMAX, NANMIN on ints, as numba types them).  NANARG* write -1 for a slice without
+ * a non-NaN element and NANMAX/NANMIN write NaN; the reference raises ValueError for the
+ * former and for n == 0 -- that check belongs to the caller.  ddof: NANVAR / NANSTD only.
+ *
+ * Element-sharded form (multi-GPU): nbg_reduce_partial writes one record of
+ * NBG_REDUCE_STATE_WORDS 8-byte words per output, states[word][j] (index_offset = position
+ * of the shard's first element along the reduced axis, used by NANARG*); the caller gathers
+ * the records of all shards into states[part][word][j] and nbg_reduce_merge folds and
+ * finalizes them (n_total: reduced length over all shards, for ANYNAN).
+ */
+typedef enum {
+    NBG_RED_ALLNAN = 0,
+    NBG_RED_ANYNAN = 1,
+    NBG_RED_NANCOUNT = 2,
+    NBG_RED_NANSUM = 3,
+    NBG_RED_NANMEAN = 4,
+    NBG_RED_NANVAR = 5,
+    NBG_RED_NANSTD = 6,
+    NBG_RED_NANARGMAX = 7,
+    NBG_RED_NANARGMIN = 8,
+    NBG_RED_NANMAX = 9,
+    NBG_RED_NANMIN = 10
+} nbg_reduce_op;
+#define NBG_REDUCE_STATE_WORDS 3
+size_t nbg_reduce_workspace_bytes(int op, int dtype, int64_t outer, int64_t n, int64_t inner);
+int nbg_reduce(int op, int dtype, const void *a, void *out, int64_t outer, int64_t n,
+               int64_t inner, int64_t ddof, void *workspace, size_t workspace_bytes,
+               void *stream);
+int nbg_reduce_partial(int op, int dtype, const void *a, void *states, int64_t outer,
+                       int64_t n, int64_t inner, int64_t index_offset, void *workspace,
+                       size_t workspace_bytes, void *stream);
+int nbg_reduce_merge(int op, int dtype, const void *states, int64_t parts, int64_t outs,
+                     void *out, int64_t n_total, int64_t ddof, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

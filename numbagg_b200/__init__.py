@@ -1,6 +1,7 @@
 """numbagg_b200 -- B200-native (sm_100a) implementation of numbagg's data-parallel hot path.
 
-Drop-in for the moving-window, exponential-moving, grouped and fill functions of numbagg
+Drop-in for the moving-window, exponential-moving, grouped, fill and plain NaN-reduction
+functions of numbagg
 (same names, keyword-only parameters, axis semantics and validation errors; see
 numbagg/__init__.py:3-62).  Everything is computed by hand-written CUDA kernels in
 libnbg_b200.so through the C ABI in include/nbg_b200.h; there is no CPU fallback.
@@ -8,7 +9,21 @@ libnbg_b200.so through the C ABI in include/nbg_b200.h; there is no CPU fallback
 
 from ._device import empty_pinned
 from ._lib import LIB_PATH, NbgError, launch_count
-from .funcs import bfill, ffill
+from .funcs import (
+    allnan,
+    anynan,
+    bfill,
+    ffill,
+    nanargmax,
+    nanargmin,
+    nancount,
+    nanmax,
+    nanmean,
+    nanmin,
+    nanstd,
+    nansum,
+    nanvar,
+)
 from .grouped import (
     group_nanall,
     group_nanany,
@@ -48,11 +63,14 @@ MOVE_EXP_FUNCS = [
 ]
 MOVE_FUNCS = [move_corr, move_cov, move_mean, move_std, move_sum, move_var]
 OTHER_FUNCS = [bfill, ffill]
+AGGREGATION_FUNCS = [
+    allnan, anynan, nancount, nansum, nanmean, nanvar, nanstd, nanargmax, nanargmin, nanmax, nanmin,
+]
 
 __version__ = "0.1.0"
 
 __all__ = [
-    *(f.__name__ for f in GROUPED_FUNCS + MOVE_EXP_FUNCS + MOVE_FUNCS + OTHER_FUNCS),
-    "GROUPED_FUNCS", "MOVE_EXP_FUNCS", "MOVE_FUNCS", "OTHER_FUNCS",
+    *(f.__name__ for f in GROUPED_FUNCS + MOVE_EXP_FUNCS + MOVE_FUNCS + OTHER_FUNCS + AGGREGATION_FUNCS),
+    "AGGREGATION_FUNCS", "GROUPED_FUNCS", "MOVE_EXP_FUNCS", "MOVE_FUNCS", "OTHER_FUNCS",
     "empty_pinned", "launch_count", "NbgError", "LIB_PATH",
 ]

@@ -23,6 +23,11 @@ GROUP_OPS = dict(
     group_nanvar=9, group_nanstd=10, group_nanmin=11, group_nanmax=12, group_nanany=13,
     group_nanall=14,
 )
+REDUCE_OPS = dict(
+    allnan=0, anynan=1, nancount=2, nansum=3, nanmean=4, nanvar=5, nanstd=6, nanargmax=7,
+    nanargmin=8, nanmax=9, nanmin=10,
+)
+NBG_REDUCE_STATE_WORDS = 3
 NBG_EXP_STATE = 11
 NBG_FILL_STATE = 3
 NBG_GROUP_WS_CHANNELS = 4
@@ -52,6 +57,10 @@ _SIGNATURES = {
     "nbg_group_combine": (_int, [_int, _int, _vp, _vp, _i64, _i64, _vp]),
     "nbg_group_finalize": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _vp]),
     "nbg_group": (_int, [_int, _int, _int, _vp, _vp, _int, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "nbg_reduce_workspace_bytes": (_sz, [_int, _int, _i64, _i64, _i64]),
+    "nbg_reduce": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "nbg_reduce_partial": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "nbg_reduce_merge": (_int, [_int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,0 +1,778 @@
+// nbg_reduce.cu -- plain NaN-aware reductions over the middle axis of an (outer, n, inner)
+// array: allnan, anynan, nancount, nansum, nanmean, nanvar, nanstd, nanargmax, nanargmin,
+// nanmax, nanmin (numbagg/funcs.py:23-242 behind ndaggregate / ndreduce,
+// numbagg/decorators.py:188-260, 906-1031).
+//
+// All of it is one streaming pass at HBM speed.  Every op is a "reducer": a small state, an
+// `add` for one element, an order-independent `merge`, and a `finalize`.  Three kernels walk
+// the data, chosen by shape (red_geometry):
+//   rows_cta   inner == 1, long rows: one CTA per (row, segment), 16-byte streaming loads;
+//   group      short rows / few elements per output: G lanes per output (G = 1..32);
+//   cols       inner > 1: the CTA reads a contiguous (segment rows x w columns) tile with
+//              consecutive threads on consecutive addresses, so a thread always sees one
+//              column; threads that share a column merge through shared memory.
+// Segments exist only to fill the machine when there are few outputs; their states go to the
+// workspace as 3-word records and a merge kernel folds them.  The same records are the
+// exchange format for element-sharded (multi-GPU) reductions: nbg_reduce_partial /
+// nbg_reduce_merge.
+//
+// Numerics: sums of floats accumulate in double (the reference accumulates nansum in the
+// input dtype sequentially; ours is at least as accurate), variance is a batched two-pass in
+// registers folded with Chan's pairwise update (robust like the reference's two loops, one
+// read of the data).  Counts, flags, extrema and arg-extrema are exact.
+#include "nbg_common.cuh"
+
+#include <type_traits>
+
+namespace nbg {
+namespace {
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+constexpr int kRedThreads = 256;
+constexpr int kStateWords = NBG_REDUCE_STATE_WORDS;
+
+// Where a kernel's result goes: the typed output (finalize) or 3-word state records
+// states[(part * 3 + word) * outs + j] (a segment of this launch, or a caller's shard).
+struct RedOut {
+    void *out;
+    u64 *states;
+    i64 outs;
+    i64 part;
+    int emit_state;
+    i64 n_total;
+    i64 ddof;
+};
+
+__device__ __forceinline__ u64 d2w(double x) { return (u64)__double_as_longlong(x); }
+__device__ __forceinline__ double w2d(u64 w) { return __longlong_as_double((i64)w); }
+
+template <typename T>
+__device__ __forceinline__ T shfl_xor_t(T v, int m) {
+    return __shfl_xor_sync(0xffffffffu, v, m);
+}
+
+// ------------------------------------------------------------------------------- reducers
+// MODE 0 allnan, 1 anynan, 2 nancount -- funcs.py:23-68.
+template <typename T, int MODE>
+struct RCount {
+    using In = T;
+    static constexpr bool BATCHED = false;
+    struct State {
+        i64 c;
+    };
+    static __device__ __forceinline__ State init() { return {0}; }
+    static __device__ __forceinline__ void add(State &s, T v, i64) { s.c += is_nan(v) ? 0 : 1; }
+    static __device__ __forceinline__ void merge(State &a, const State &b) { a.c += b.c; }
+    static __device__ __forceinline__ State shfl(const State &s, int m) { return {shfl_xor_t(s.c, m)}; }
+    static __device__ __forceinline__ void pack(const State &s, u64 (&w)[3]) {
+        w[0] = (u64)s.c;
+        w[1] = 0;
+        w[2] = 0;
+    }
+    static __device__ __forceinline__ State unpack(const u64 (&w)[3]) { return {(i64)w[0]}; }
+    static __device__ __forceinline__ void finalize(const State &s, const RedOut &o, i64 j) {
+        if (MODE == 0)
+            ((uint8_t *)o.out)[j] = s.c == 0;
+        else if (MODE == 1)
+            ((uint8_t *)o.out)[j] = s.c < o.n_total;
+        else
+            ((i64 *)o.out)[j] = s.c;
+    }
+};
+
+// nansum -- funcs.py:71-85.  Floats: double accumulator; ints: int64 (wraps like the int32
+// loop after the final narrowing).
+template <typename T>
+struct RSum {
+    using In = T;
+    static constexpr bool BATCHED = false;
+    static constexpr bool IS_INT = std::is_integral<T>::value;
+    using Acc = typename std::conditional<IS_INT, i64, double>::type;
+    struct State {
+        Acc s;
+    };
+    static __device__ __forceinline__ State init() { return {Acc(0)}; }
+    static __device__ __forceinline__ void add(State &s, T v, i64) { s.s += is_nan(v) ? Acc(0) : (Acc)v; }
+    static __device__ __forceinline__ void merge(State &a, const State &b) { a.s += b.s; }
+    static __device__ __forceinline__ State shfl(const State &s, int m) { return {shfl_xor_t(s.s, m)}; }
+    static __device__ __forceinline__ void pack(const State &s, u64 (&w)[3]) {
+        if constexpr (IS_INT)
+            w[0] = (u64)s.s;
+        else
+            w[0] = d2w(s.s);
+        w[1] = 0;
+        w[2] = 0;
+    }
+    static __device__ __forceinline__ State unpack(const u64 (&w)[3]) {
+        if constexpr (IS_INT)
+            return {(i64)w[0]};
+        else
+            return {w2d(w[0])};
+    }
+    static __device__ __forceinline__ void finalize(const State &s, const RedOut &o, i64 j) {
+        ((T *)o.out)[j] = (T)s.s;
+    }
+};
+
+// nanmean -- funcs.py:88-104 (double sum, int64 count, one division).
+template <typename T>
+struct RMean {
+    using In = T;
+    static constexpr bool BATCHED = false;
+    struct State {
+        double s;
+        i64 c;
+    };
+    static __device__ __forceinline__ State init() { return {0.0, 0}; }
+    static __device__ __forceinline__ void add(State &s, T v, i64) {
+        const bool ok = !is_nan(v);
+        s.s += ok ? (double)v : 0.0;
+        s.c += ok ? 1 : 0;
+    }
+    static __device__ __forceinline__ void merge(State &a, const State &b) {
+        a.s += b.s;
+        a.c += b.c;
+    }
+    static __device__ __forceinline__ State shfl(const State &s, int m) {
+        return {shfl_xor_t(s.s, m), shfl_xor_t(s.c, m)};
+    }
+    static __device__ __forceinline__ void pack(const State &s, u64 (&w)[3]) {
+        w[0] = (u64)s.c;
+        w[1] = d2w(s.s);
+        w[2] = 0;
+    }
+    static __device__ __forceinline__ State unpack(const u64 (&w)[3]) { return {w2d(w[1]), (i64)w[0]}; }
+    static __device__ __forceinline__ void finalize(const State &s, const RedOut &o, i64 j) {
+        ((T *)o.out)[j] = s.c > 0 ? (T)(s.s / (double)s.c) : quiet_nan<T>();
+    }
+};
+
+// nanvar / nanstd -- funcs.py:107-158.  The reference makes two passes (mean, then squared
+// deviations).  We read once: each register batch is reduced two-pass (batch mean, then
+// centred squares), and batches / threads / segments fold with Chan's update
+//   mean = mean_a + d * cb / c,  M2 = M2_a + M2_b + d^2 * ca * cb / c,   d = mean_b - mean_a
+// whose terms are all centred, so no cancellation arises wherever the data sits.
+template <typename T, bool SQRT>
+struct RVar {
+    using In = T;
+    static constexpr bool BATCHED = true;
+    struct State {
+        i64 c;
+        double mean, m2;
+    };
+    static __device__ __forceinline__ State init() { return {0, 0.0, 0.0}; }
+    static __device__ __forceinline__ void merge(State &a, const State &b) {
+        if (b.c == 0) return;
+        if (a.c == 0) {
+            a = b;
+            return;
+        }
+        const double ca = (double)a.c, cb = (double)b.c;
+        const double c = ca + cb;
+        const double r = cb / c;
+        const double d = b.mean - a.mean;
+        a.mean = fma(d, r, a.mean);
+        a.m2 = a.m2 + b.m2 + d * d * ca * r;
+        a.c += b.c;
+    }
+    static __device__ __forceinline__ void add(State &s, T v, i64) {
+        if (!is_nan(v)) merge(s, State{1, (double)v, 0.0});
+    }
+    template <int B, bool FULL>
+    static __device__ __forceinline__ void add_batch(State &s, const T (&v)[B], uint32_t mask) {
+        double x[B];
+        uint32_t okm = 0;
+        double sum = 0.0;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const bool ok = (FULL || ((mask >> b) & 1u)) && !is_nan(v[b]);
+            x[b] = ok ? (double)v[b] : 0.0;
+            okm |= (ok ? 1u : 0u) << b;
+            sum += x[b];
+        }
+        const int cb = __popc(okm);
+        if (cb == 0) return;
+        const double rb = 1.0 / (double)cb;
+        const double k = sum * rb;  // batch centre (within an ulp of the batch mean)
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const double d = ((okm >> b) & 1u) ? x[b] - k : 0.0;
+            s1 += d;
+            s2 = fma(d, d, s2);
+        }
+        State bs;
+        bs.c = cb;
+        bs.mean = fma(s1, rb, k);
+        bs.m2 = fmax(s2 - s1 * s1 * rb, 0.0);
+        if (s2 != s2) bs.m2 = s2;  // keep NaN (inf - inf) like the reference
+        merge(s, bs);
+    }
+    static __device__ __forceinline__ State shfl(const State &s, int m) {
+        return {shfl_xor_t(s.c, m), shfl_xor_t(s.mean, m), shfl_xor_t(s.m2, m)};
+    }
+    static __device__ __forceinline__ void pack(const State &s, u64 (&w)[3]) {
+        w[0] = (u64)s.c;
+        w[1] = d2w(s.mean);
+        w[2] = d2w(s.m2);
+    }
+    static __device__ __forceinline__ State unpack(const u64 (&w)[3]) { return {(i64)w[0], w2d(w[1]), w2d(w[2])}; }
+    static __device__ __forceinline__ void finalize(const State &s, const RedOut &o, i64 j) {
+        double r = quiet_nan<double>();
+        if (s.c > o.ddof) {
+            r = s.m2 / (double)(s.c - o.ddof);
+            if (SQRT) r = sqrt(r);
+        }
+        ((T *)o.out)[j] = (T)r;
+    }
+};
+
+// nanmax / nanmin -- funcs.py:200-242: `if ai >= amax` from -inf, NaN when nothing passed.
+// Floats stay in their type; ints compare as ints (the reference compares them as doubles,
+// a monotone map) and come back as int64 through the same double round trip.
+template <typename T, bool MAX>
+struct RExt {
+    using In = T;
+    static constexpr bool BATCHED = false;
+    static constexpr bool IS_INT = std::is_integral<T>::value;
+    struct State {
+        T m;
+        int any;
+    };
+    static __device__ __forceinline__ T lowest() {
+        if constexpr (IS_INT)
+            return MAX ? (sizeof(T) == 4 ? (T)INT32_MIN : (T)INT64_MIN) : (sizeof(T) == 4 ? (T)INT32_MAX : (T)INT64_MAX);
+        else
+            return MAX ? (T)-INFINITY : (T)INFINITY;
+    }
+    static __device__ __forceinline__ State init() { return {lowest(), 0}; }
+    static __device__ __forceinline__ void add(State &s, T v, i64) {
+        const bool ok = MAX ? v >= s.m : v <= s.m;
+        s.m = ok ? v : s.m;
+        s.any |= ok ? 1 : 0;
+    }
+    static __device__ __forceinline__ void merge(State &a, const State &b) {
+        if (b.any) add(a, b.m, 0);
+    }
+    static __device__ __forceinline__ State shfl(const State &s, int m) {
+        return {shfl_xor_t(s.m, m), shfl_xor_t(s.any, m)};
+    }
+    static __device__ __forceinline__ void pack(const State &s, u64 (&w)[3]) {
+        w[0] = (u64)s.any;
+        if constexpr (IS_INT)
+            w[1] = (u64)(i64)s.m;
+        else
+            w[1] = d2w((double)s.m);
+        w[2] = 0;
+    }
+    static __device__ __forceinline__ State unpack(const u64 (&w)[3]) {
+        if constexpr (IS_INT)
+            return {(T)(i64)w[1], (int)w[0]};
+        else
+            return {(T)w2d(w[1]), (int)w[0]};
+    }
+    static __device__ __forceinline__ void finalize(const State &s, const RedOut &o, i64 j) {
+        if constexpr (IS_INT) {
+            // int64(float64(amax)); an empty slice is rejected by the caller beforehand
+            ((i64 *)o.out)[j] = s.any ? __double2ll_rz((double)s.m) : (i64)0;
+        } else {
+            ((T *)o.out)[j] = s.any ? s.m : quiet_nan<T>();
+        }
+    }
+};
+
+// nanargmax / nanargmin -- funcs.py:161-197: strict compare from -inf, or the first non-NaN
+// while nothing was taken; so the first occurrence of the extreme wins.  Ints are compared
+// as doubles, exactly as numba types `ai > amax` with amax = -np.inf.  idx = -1: nothing
+// taken (the caller raises ValueError like the reference).
+template <typename T, bool MAX>
+struct RArg {
+    using In = T;
+    static constexpr bool BATCHED = false;
+    static constexpr bool IS_INT = std::is_integral<T>::value;
+    using K = typename std::conditional<IS_INT, double, T>::type;
+    struct State {
+        K key;
+        i64 idx;
+    };
+    static __device__ __forceinline__ State init() { return {MAX ? (K)-INFINITY : (K)INFINITY, -1}; }
+    static __device__ __forceinline__ bool better(K a, K b) { return MAX ? a > b : a < b; }
+    // elements reach one thread in increasing index order
+    static __device__ __forceinline__ void add(State &s, T v, i64 idx) {
+        const K k = (K)v;
+        const bool take = better(k, s.key) || (s.idx < 0 && !is_nan(k));
+        s.key = take ? k : s.key;
+        s.idx = take ? idx : s.idx;
+    }
+    static __device__ __forceinline__ void merge(State &a, const State &b) {
+        const bool take =
+            b.idx >= 0 && (a.idx < 0 || better(b.key, a.key) || (b.key == a.key && b.idx < a.idx));
+        a.key = take ? b.key : a.key;
+        a.idx = take ? b.idx : a.idx;
+    }
+    static __device__ __forceinline__ State shfl(const State &s, int m) {
+        return {shfl_xor_t(s.key, m), shfl_xor_t(s.idx, m)};
+    }
+    static __device__ __forceinline__ void pack(const State &s, u64 (&w)[3]) {
+        w[0] = (u64)s.idx;
+        w[1] = d2w((double)s.key);
+        w[2] = 0;
+    }
+    static __device__ __forceinline__ State unpack(const u64 (&w)[3]) { return {(K)w2d(w[1]), (i64)w[0]}; }
+    static __device__ __forceinline__ void finalize(const State &s, const RedOut &o, i64 j) {
+        ((i64 *)o.out)[j] = s.idx;
+    }
+};
+
+// B elements at once.  Element b has index idx0 + (b / V) * kstride + (b % V); `mask` (used
+// when !FULL) says which elements exist.
+template <typename R, int B, int V, bool FULL>
+__device__ __forceinline__ void add_batch(typename R::State &s, const typename R::In (&v)[B], uint32_t mask,
+                                          i64 idx0, i64 kstride) {
+    if constexpr (R::BATCHED) {
+        R::template add_batch<B, FULL>(s, v, mask);
+    } else {
+#pragma unroll
+        for (int b = 0; b < B; b++)
+            if (FULL || ((mask >> b) & 1u)) R::add(s, v[b], idx0 + (i64)(b / V) * kstride + (b % V));
+    }
+}
+
+template <typename R>
+__device__ __forceinline__ void emit(const typename R::State &s, const RedOut &o, i64 j) {
+    if (o.emit_state) {
+        u64 w[3];
+        R::pack(s, w);
+#pragma unroll
+        for (int k = 0; k < kStateWords; k++) o.states[(o.part * kStateWords + k) * o.outs + j] = w[k];
+    } else {
+        R::finalize(s, o, j);
+    }
+}
+
+// 16-byte streaming load of V = 16 / sizeof(T) elements
+template <typename T>
+__device__ __forceinline__ void load16(const T *p, T *dst) {
+    const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(p));
+    *reinterpret_cast<uint4 *>(dst) = q;
+}
+
+// ---------------------------------------------------------------------- rows_cta (inner == 1)
+// grid.x = rows * segs.  The CTA reduces positions [seg * seg_len, min(n, ...)) of one row.
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) red_rows_cta_kernel(const typename R::In *__restrict__ a, RedOut o,
+                                                                    i64 n, i64 segs, i64 seg_len, i64 index_offset) {
+    using T = typename R::In;
+    using State = typename R::State;
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int U = 4;
+    constexpr int B = U * V;
+    const int tid = threadIdx.x;
+    const i64 row = blockIdx.x / segs, seg = blockIdx.x % segs;
+    const i64 lo = seg * seg_len;
+    const i64 hi = lo + seg_len < n ? lo + seg_len : n;
+    const T *p = a + row * n;
+    State s = R::init();
+    if (hi > lo) {
+        const int mis = (int)(((uintptr_t)(p + lo) & 15) / sizeof(T));
+        i64 head = mis ? V - mis : 0;
+        if (head > hi - lo) head = hi - lo;
+        if (tid < head) R::add(s, p[lo + tid], index_offset + lo + tid);
+        const i64 vlo = lo + head;
+        const i64 nvec = (hi - vlo) / V;
+        const T *pv = p + vlo;
+        i64 j = tid;
+        for (; j + (U - 1) * kRedThreads < nvec; j += U * kRedThreads) {
+            alignas(16) T v[B];
+#pragma unroll
+            for (int u = 0; u < U; u++) load16(pv + (j + u * kRedThreads) * V, v + u * V);
+            add_batch<R, B, V, true>(s, v, 0xffffffffu, index_offset + vlo + j * V, (i64)kRedThreads * V);
+        }
+        for (; j < nvec; j += kRedThreads) {
+            alignas(16) T v[V];
+            load16(pv + j * V, v);
+            add_batch<R, V, V, true>(s, v, 0xffffffffu, index_offset + vlo + j * V, 0);
+        }
+        const i64 tlo = vlo + nvec * V;
+        if (tid < hi - tlo) R::add(s, p[tlo + tid], index_offset + tlo + tid);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) R::merge(s, R::shfl(s, m));
+    __shared__ State sm[kRedThreads / 32];
+    if ((tid & 31) == 0) sm[tid >> 5] = s;
+    __syncthreads();
+    if (tid < 32) {
+        s = tid < kRedThreads / 32 ? sm[tid] : R::init();
+#pragma unroll
+        for (int m = (kRedThreads / 32) / 2; m >= 1; m >>= 1) R::merge(s, R::shfl(s, m));
+        if (tid == 0) {
+            RedOut oo = o;
+            if (segs > 1) oo.part = seg;
+            emit<R>(s, oo, row);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ group (G lanes / output)
+// Output j = (o, c) reduces a[o, :, c]: element i sits at base + i * inner.  G > 1 only with
+// inner == 1 (the lanes of a group then read consecutive addresses).
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) red_group_kernel(const typename R::In *__restrict__ a, RedOut o, i64 n,
+                                                                 i64 inner, int G, i64 index_offset) {
+    using T = typename R::In;
+    using State = typename R::State;
+    constexpr int B = 8;
+    const i64 gid = (i64)blockIdx.x * kRedThreads + threadIdx.x;
+    const i64 j = gid / G;
+    const int g = (int)(gid % G);
+    const bool active = j < o.outs;
+    const i64 nn = active ? n : 0;
+    const i64 jo = active ? j : 0;
+    const T *p = a + (jo / inner) * n * inner + (jo % inner);
+    State s = R::init();
+    i64 i = g;
+    for (; i + (i64)(B - 1) * G < nn; i += (i64)B * G) {
+        T v[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) v[b] = p[(i + (i64)b * G) * inner];
+        add_batch<R, B, 1, true>(s, v, 0xffffffffu, index_offset + i, G);
+    }
+    if (i < nn) {
+        T v[B];
+        uint32_t mask = 0;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const bool in = i + (i64)b * G < nn;
+            v[b] = in ? p[(i + (i64)b * G) * inner] : T(0);
+            mask |= (in ? 1u : 0u) << b;
+        }
+        add_batch<R, B, 1, false>(s, v, mask, index_offset + i, G);
+    }
+    for (int m = G >> 1; m >= 1; m >>= 1) R::merge(s, R::shfl(s, m));
+    if (active && g == 0) emit<R>(s, o, j);
+}
+
+// ------------------------------------------------------------------------- cols (inner > 1)
+// grid = (outer * segs, column tiles).  Thread tid < tprime = w * rps handles column
+// col0 + tid % w and rows lo + tid / w + k * rps: consecutive threads, consecutive addresses.
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) red_cols_kernel(const typename R::In *__restrict__ a, RedOut o, i64 n,
+                                                                i64 inner, i64 segs, i64 seg_len, int w, int rps,
+                                                                i64 index_offset) {
+    using T = typename R::In;
+    using State = typename R::State;
+    constexpr int B = 8;
+    const int tid = threadIdx.x;
+    const i64 oi = blockIdx.x / segs, seg = blockIdx.x % segs;
+    const i64 col = (i64)blockIdx.y * w + tid % w;
+    const int r0 = tid / w;
+    const bool active = tid < w * rps && col < inner;
+    const i64 lo = seg * seg_len;
+    i64 hi = lo + seg_len < n ? lo + seg_len : n;
+    if (!active) hi = lo;
+    const T *p = a + oi * n * inner + (active ? col : 0);
+    State s = R::init();
+    i64 i = lo + r0;
+    for (; i + (i64)(B - 1) * rps < hi; i += (i64)B * rps) {
+        T v[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) v[b] = __ldcs(p + (i + (i64)b * rps) * inner);
+        add_batch<R, B, 1, true>(s, v, 0xffffffffu, index_offset + i, rps);
+    }
+    if (i < hi) {
+        T v[B];
+        uint32_t mask = 0;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const bool in = i + (i64)b * rps < hi;
+            v[b] = in ? __ldcs(p + (i + (i64)b * rps) * inner) : T(0);
+            mask |= (in ? 1u : 0u) << b;
+        }
+        add_batch<R, B, 1, false>(s, v, mask, index_offset + i, rps);
+    }
+    if (rps > 1) {
+        __shared__ State sm[kRedThreads];
+        sm[tid] = s;
+        __syncthreads();
+        if (r0 == 0)
+            for (int r = 1; r < rps; r++) R::merge(s, sm[tid + r * w]);
+    }
+    if (active && r0 == 0) {
+        RedOut oo = o;
+        if (segs > 1) oo.part = seg;
+        emit<R>(s, oo, oi * inner + col);
+    }
+}
+
+// --------------------------------------------------------------------------------- merge
+// Fold `parts` state records per output (segments of one launch, or shards of several
+// devices: states[(part * 3 + word) * outs + j]).  lanes = 1: a thread per output (coalesced
+// over j); lanes = 32: a warp per output (few outputs, many parts).
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) red_merge_kernel(const u64 *__restrict__ states, i64 parts, RedOut o,
+                                                                 int lanes) {
+    using State = typename R::State;
+    const i64 gid = (i64)blockIdx.x * kRedThreads + threadIdx.x;
+    const i64 j = gid / lanes;
+    const int g = (int)(gid % lanes);
+    const bool active = j < o.outs;
+    State s = R::init();
+    if (active)
+        for (i64 p = g; p < parts; p += lanes) {
+            u64 w[3];
+#pragma unroll
+            for (int k = 0; k < kStateWords; k++) w[k] = states[(p * kStateWords + k) * o.outs + j];
+            R::merge(s, R::unpack(w));
+        }
+    for (int m = lanes >> 1; m >= 1; m >>= 1) R::merge(s, R::shfl(s, m));
+    if (active && g == 0) emit<R>(s, o, j);
+}
+
+// Integer inputs hold no NaN: allnan / anynan / nancount are constants of the shape.
+__global__ void red_const_kernel(RedOut o, int mode, i64 n) {
+    const i64 j = (i64)blockIdx.x * kRedThreads + threadIdx.x;
+    if (j >= o.outs) return;
+    if (o.emit_state) {
+        o.states[(o.part * kStateWords + 0) * o.outs + j] = (u64)n;
+        o.states[(o.part * kStateWords + 1) * o.outs + j] = 0;
+        o.states[(o.part * kStateWords + 2) * o.outs + j] = 0;
+    } else if (mode == 0) {
+        ((uint8_t *)o.out)[j] = n == 0;
+    } else if (mode == 1) {
+        ((uint8_t *)o.out)[j] = 0;
+    } else {
+        ((i64 *)o.out)[j] = n;
+    }
+}
+
+// ------------------------------------------------------------------------------ geometry
+enum RedMode { RED_ROWS_CTA = 0, RED_GROUP = 1, RED_COLS = 2 };
+struct RedGeom {
+    int mode;
+    i64 segs, seg_len;
+    int G;         // group
+    int w, rps;    // cols
+    i64 coltiles;  // cols
+};
+
+constexpr i64 kTargetCtas = (i64)kNumSMs * 8;
+
+inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
+
+RedGeom red_geometry(i64 outer, i64 n, i64 inner) {
+    RedGeom g{};
+    g.segs = 1;
+    g.seg_len = n > 0 ? n : 1;
+    g.G = 1;
+    if (inner == 1) {
+        if (n <= 4096) {
+            g.mode = RED_GROUP;
+            int G = 1;
+            while (G < 32 && (i64)G * 16 < n) G <<= 1;
+            g.G = G;
+            return g;
+        }
+        g.mode = RED_ROWS_CTA;
+        i64 segs = ceil_div(kTargetCtas, outer > 0 ? outer : 1);
+        const i64 max_segs = ceil_div(n, 4096);
+        if (segs > max_segs) segs = max_segs;
+        if (segs < 1) segs = 1;
+        i64 seg_len = ceil_div(ceil_div(n, segs), 1024) * 1024;
+        g.seg_len = seg_len;
+        g.segs = ceil_div(n, seg_len);
+        return g;
+    }
+    const i64 w = inner <= kRedThreads ? inner : kRedThreads;
+    if (n * w < 2048) {  // too little work per (outer, column tile) for a CTA: thread per output
+        g.mode = RED_GROUP;
+        return g;
+    }
+    g.mode = RED_COLS;
+    g.w = (int)w;
+    g.rps = inner <= kRedThreads ? (int)(kRedThreads / inner) : 1;
+    g.coltiles = ceil_div(inner, w);
+    const i64 base = g.coltiles * (outer > 0 ? outer : 1);
+    i64 segs = ceil_div(kTargetCtas, base);
+    const i64 max_segs = ceil_div(n, (i64)16 * g.rps);
+    if (segs > max_segs) segs = max_segs;
+    if (segs < 1) segs = 1;
+    g.seg_len = ceil_div(n, segs);
+    g.segs = ceil_div(n, g.seg_len);
+    return g;
+}
+
+// ------------------------------------------------------------------------------ launching
+struct RedArgs {
+    const void *a;
+    void *out;
+    u64 *states;  // partial mode: caller's record array (part 0 of 1)
+    i64 outer, n, inner, ddof, index_offset;
+    void *workspace;
+    size_t workspace_bytes;
+    cudaStream_t stream;
+    bool partial;
+};
+
+template <typename R>
+int launch_merge(const u64 *states, i64 parts, const RedOut &o, cudaStream_t stream) {
+    if (o.outs <= 0) return NBG_OK;
+    const int lanes = (o.outs < 2048 && parts > 4) ? 32 : 1;
+    const i64 threads = o.outs * lanes;
+    red_merge_kernel<R><<<(unsigned)ceil_div(threads, kRedThreads), kRedThreads, 0, stream>>>(states, parts, o, lanes);
+    return check_launch("nbg_reduce merge");
+}
+
+template <typename R>
+int launch_reduce(const RedArgs &x) {
+    using T = typename R::In;
+    const i64 outs = x.outer * x.inner;
+    if (outs <= 0) return NBG_OK;
+    const RedGeom g = red_geometry(x.outer, x.n, x.inner);
+    RedOut fin{x.out, x.states, outs, 0, x.partial ? 1 : 0, x.n, x.ddof};
+    RedOut first = fin;
+    if (g.segs > 1) {
+        const size_t need = (size_t)g.segs * kStateWords * outs * sizeof(u64);
+        if (x.workspace == nullptr || x.workspace_bytes < need)
+            return fail(NBG_ERR_WORKSPACE, "nbg_reduce: workspace smaller than nbg_reduce_workspace_bytes()");
+        first.states = (u64 *)x.workspace;
+        first.emit_state = 1;
+    }
+    const T *a = (const T *)x.a;
+    int rc;
+    if (g.mode == RED_ROWS_CTA) {
+        const i64 ctas = x.outer * g.segs;
+        if (ctas > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_reduce: too many rows");
+        red_rows_cta_kernel<R><<<(unsigned)ctas, kRedThreads, 0, x.stream>>>(a, first, x.n, g.segs, g.seg_len,
+                                                                             x.index_offset);
+        rc = check_launch("nbg_reduce rows");
+    } else if (g.mode == RED_GROUP) {
+        const i64 ctas = ceil_div(outs * g.G, kRedThreads);
+        if (ctas > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_reduce: too many outputs");
+        red_group_kernel<R><<<(unsigned)ctas, kRedThreads, 0, x.stream>>>(a, first, x.n, x.inner, g.G, x.index_offset);
+        rc = check_launch("nbg_reduce group");
+    } else {
+        const i64 gx = x.outer * g.segs;
+        if (gx > 0x7fffffff || g.coltiles > 65535) return fail(NBG_ERR_BAD_ARG, "nbg_reduce: shape too large");
+        red_cols_kernel<R><<<dim3((unsigned)gx, (unsigned)g.coltiles), kRedThreads, 0, x.stream>>>(
+            a, first, x.n, x.inner, g.segs, g.seg_len, g.w, g.rps, x.index_offset);
+        rc = check_launch("nbg_reduce cols");
+    }
+    if (rc) return rc;
+    if (g.segs > 1) return launch_merge<R>((const u64 *)x.workspace, g.segs, fin, x.stream);
+    return NBG_OK;
+}
+
+// op x dtype -> reducer.  F is a generic callable taking a reducer tag.
+template <typename R>
+struct Tag {
+    using type = R;
+};
+
+template <typename T, typename F>
+int with_reducer_t(int op, F &&f) {
+    constexpr bool is_int = std::is_integral<T>::value;
+    switch (op) {
+        case NBG_RED_ALLNAN: return f(Tag<RCount<T, 0>>{});
+        case NBG_RED_ANYNAN: return f(Tag<RCount<T, 1>>{});
+        case NBG_RED_NANCOUNT: return f(Tag<RCount<T, 2>>{});
+        case NBG_RED_NANSUM: return f(Tag<RSum<T>>{});
+        case NBG_RED_NANARGMAX: return f(Tag<RArg<T, true>>{});
+        case NBG_RED_NANARGMIN: return f(Tag<RArg<T, false>>{});
+        case NBG_RED_NANMAX: return f(Tag<RExt<T, true>>{});
+        case NBG_RED_NANMIN: return f(Tag<RExt<T, false>>{});
+        default: break;
+    }
+    if constexpr (!is_int) {
+        switch (op) {
+            case NBG_RED_NANMEAN: return f(Tag<RMean<T>>{});
+            case NBG_RED_NANVAR: return f(Tag<RVar<T, false>>{});
+            case NBG_RED_NANSTD: return f(Tag<RVar<T, true>>{});
+            default: break;
+        }
+    } else if (op == NBG_RED_NANMEAN || op == NBG_RED_NANVAR || op == NBG_RED_NANSTD) {
+        return fail(NBG_ERR_BAD_DTYPE, "nbg_reduce: nanmean/nanvar/nanstd take float32/float64 (cast integers first)");
+    }
+    return fail(NBG_ERR_BAD_OP, "nbg_reduce: unknown op");
+}
+
+template <typename F>
+int with_reducer(int op, int dtype, F &&f) {
+    switch (dtype) {
+        case NBG_F32: return with_reducer_t<float>(op, f);
+        case NBG_F64: return with_reducer_t<double>(op, f);
+        case NBG_I32: return with_reducer_t<int32_t>(op, f);
+        case NBG_I64: return with_reducer_t<int64_t>(op, f);
+        default: return fail(NBG_ERR_BAD_DTYPE, "nbg_reduce: dtype must be NBG_F32|F64|I32|I64");
+    }
+}
+
+int check_shape(i64 outer, i64 n, i64 inner) {
+    if (outer < 0 || n < 0 || inner < 0) return fail(NBG_ERR_BAD_ARG, "nbg_reduce: negative extent");
+    return NBG_OK;
+}
+
+int reduce_entry(int op, int dtype, const RedArgs &x) {
+    if (int rc = check_shape(x.outer, x.n, x.inner)) return rc;
+    const bool is_int = dtype == NBG_I32 || dtype == NBG_I64;
+    if (is_int && op >= NBG_RED_ALLNAN && op <= NBG_RED_NANCOUNT) {
+        const i64 outs = x.outer * x.inner;
+        if (outs <= 0) return NBG_OK;
+        RedOut o{x.out, x.states, outs, 0, x.partial ? 1 : 0, x.n, x.ddof};
+        red_const_kernel<<<(unsigned)ceil_div(outs, kRedThreads), kRedThreads, 0, x.stream>>>(o, op, x.n);
+        return check_launch("nbg_reduce const");
+    }
+    return with_reducer(op, dtype, [&](auto tag) {
+        using R = typename decltype(tag)::type;
+        return launch_reduce<R>(x);
+    });
+}
+
+}  // namespace
+}  // namespace nbg
+
+using namespace nbg;
+
+extern "C" size_t nbg_reduce_workspace_bytes(int op, int dtype, int64_t outer, int64_t n, int64_t inner) {
+    (void)op;
+    (void)dtype;
+    if (outer <= 0 || n <= 0 || inner <= 0) return 0;
+    const RedGeom g = red_geometry(outer, n, inner);
+    if (g.segs <= 1) return 0;
+    return (size_t)g.segs * kStateWords * (size_t)(outer * inner) * sizeof(u64);
+}
+
+extern "C" int nbg_reduce(int op, int dtype, const void *a, void *out, int64_t outer, int64_t n, int64_t inner,
+                          int64_t ddof, void *workspace, size_t workspace_bytes, void *stream) {
+    RedArgs x{a, out, nullptr, outer, n, inner, ddof, 0, workspace, workspace_bytes, (cudaStream_t)stream, false};
+    if (outer * inner > 0 && (out == nullptr || (a == nullptr && n > 0)))
+        return fail(NBG_ERR_BAD_ARG, "nbg_reduce: null pointer");
+    return reduce_entry(op, dtype, x);
+}
+
+extern "C" int nbg_reduce_partial(int op, int dtype, const void *a, void *states, int64_t outer, int64_t n,
+                                  int64_t inner, int64_t index_offset, void *workspace, size_t workspace_bytes,
+                                  void *stream) {
+    RedArgs x{a,         nullptr,         (u64 *)states,        outer, n,   inner, 0, index_offset,
+              workspace, workspace_bytes, (cudaStream_t)stream, true};
+    if (outer * inner > 0 && (states == nullptr || (a == nullptr && n > 0)))
+        return fail(NBG_ERR_BAD_ARG, "nbg_reduce_partial: null pointer");
+    return reduce_entry(op, dtype, x);
+}
+
+extern "C" int nbg_reduce_merge(int op, int dtype, const void *states, int64_t parts, int64_t outs, void *out,
+                                int64_t n_total, int64_t ddof, void *stream) {
+    if (parts < 0 || outs < 0) return fail(NBG_ERR_BAD_ARG, "nbg_reduce_merge: negative extent");
+    if (outs == 0) return NBG_OK;
+    if (out == nullptr || (states == nullptr && parts > 0))
+        return fail(NBG_ERR_BAD_ARG, "nbg_reduce_merge: null pointer");
+    RedOut o{out, nullptr, outs, 0, 0, n_total, ddof};
+    const bool is_int = dtype == NBG_I32 || dtype == NBG_I64;
+    // counts of integer shards are plain counts too: fold them with the float counter
+    if (is_int && op >= NBG_RED_ALLNAN && op <= NBG_RED_NANCOUNT) dtype = NBG_F64;
+    return with_reducer(op, dtype, [&](auto tag) {
+        using R = typename decltype(tag)::type;
+        return launch_merge<R>((const u64 *)states, parts, o, (cudaStream_t)stream);
+    });
+}

@@ -596,3 +596,205 @@ def run_group_finalize(name: str, vdtype: np.dtype, state: torch.Tensor, ddof: i
                                        out.data_ptr(), rows, K, int(ddof), dev.stream_ptr())
     _lib.check(rc, f"nbg_group_finalize({name})")
     return out
+
+
+# ------------------------------------------------------------------- plain reductions
+_REDUCE_FLOAT_ONLY = ("nanmean", "nanvar", "nanstd")
+_REDUCE_EMPTY_ERRORS = {
+    "nanargmax": "All-NaN slice encountered",
+    "nanargmin": "All-NaN slice encountered",
+    "nanmax": "zero-size array to reduction operation fmax which has no identity",
+    "nanmin": "zero-size array to reduction operation fmin which has no identity",
+}
+
+
+def _reduce_loop_dtype(name: str, dt: np.dtype) -> np.dtype:
+    """The gufunc loop NumPy would pick among the reference's signatures (funcs.py:23-242):
+    int32 / int64 / float32 / float64, or float32 / float64 only for nanmean/nanvar/nanstd."""
+    if dt.kind == "f":
+        return _F32 if dt.itemsize <= 4 else _F64
+    if name in _REDUCE_FLOAT_ONLY:
+        return _F64
+    if dt.kind == "b" or (dt.kind in "iu" and dt.itemsize < 4) or dt == np.dtype(np.int32):
+        return np.dtype(np.int32)
+    if dt.kind in "iu" and dt != np.dtype(np.uint64):
+        return np.dtype(np.int64)
+    if dt == np.dtype(np.uint64):
+        return _F64
+    raise TypeError(f"Unsupported dtype for {name}: {dt}")
+
+
+def _reduce_out_dtype(name: str, work: np.dtype) -> torch.dtype:
+    if name in ("allnan", "anynan"):
+        return torch.uint8
+    if name in ("nancount", "nanargmax", "nanargmin"):
+        return torch.int64
+    if name in ("nanmax", "nanmin") and work.kind == "i":
+        return torch.int64
+    return dev._NP_TO_TORCH[work]
+
+
+class ReduceView:
+    """(outer, n, inner) C-contiguous view of `t` whose middle axis is the flattened block of
+    reduced axes, taken in the order given (that order defines the flat index nanarg* return
+    and the reference's accumulation order).  No copy when the reduced axes are adjacent in
+    memory in that order -- axis=None, one axis, or a run of neighbouring axes of a C-, F- or
+    otherwise permuted-contiguous array; anything else is permuted with one copy."""
+
+    def __init__(self, t: torch.Tensor, axes: tuple[int, ...]):
+        nd = t.dim()
+        # memory order of the dims, outermost first; size-1 dims sort anywhere
+        perm = sorted(range(nd), key=lambda d: (-t.stride(d) if t.shape[d] > 1 else 0, d))
+        if nd and not t.permute(perm).is_contiguous():
+            t = t.contiguous()
+            perm = list(range(nd))
+        pos = {d: i for i, d in enumerate(perm)}
+        red = [pos[ax] for ax in axes]
+        batch_dims = [d for d in range(nd) if d not in axes]  # output dims, original order
+        shape_p = [t.shape[d] for d in perm]
+        adjacent = all(red[i + 1] == red[i] + 1 for i in range(len(red) - 1))
+        # size-1 dims can be anywhere in `perm`; the batch dims must keep a consistent order
+        batch_p = [d for d in perm if d not in axes]
+        if red and adjacent:
+            self.t = t.permute(perm)
+            self.outer = math.prod(shape_p[: red[0]])
+            self.n = math.prod(shape_p[red[0] : red[-1] + 1])
+            self.inner = math.prod(shape_p[red[-1] + 1 :])
+        else:
+            self.t = t.permute(batch_p + list(axes)).contiguous()
+            self.outer = math.prod(t.shape[d] for d in batch_p)
+            self.n = math.prod(t.shape[ax] for ax in axes)
+            self.inner = 1
+        self._batch_shape_p = [t.shape[d] for d in batch_p]
+        # permutation taking the (memory-ordered) batch dims back to their original order
+        self._back = [batch_p.index(d) for d in batch_dims]
+
+    def restore(self, flat: torch.Tensor) -> torch.Tensor:
+        out = flat.reshape(self._batch_shape_p)
+        return out.permute(self._back) if self._back else out
+
+
+def run_reduce(name: str, t: torch.Tensor, axes: tuple[int, ...], ddof: int = 1) -> torch.Tensor:
+    """Device-level entry: reduce `axes` (in that order) of a CUDA tensor whose dtype is one
+    of the loop dtypes; returns a CUDA tensor of the batch shape."""
+    work = dev._TORCH_TO_NP[t.dtype]
+    view = ReduceView(t, axes)
+    L = _lib.lib()
+    op = _lib.REDUCE_OPS[name]
+    outs = view.outer * view.inner
+    out = torch.empty(outs, dtype=_reduce_out_dtype(name, work), device=t.device)
+    ws_bytes = L.nbg_reduce_workspace_bytes(op, _NBG_DTYPE[work], view.outer, view.n, view.inner)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=t.device)
+    rc = L.nbg_reduce(op, _NBG_DTYPE[work], dev.ptr(view.t), dev.ptr(out), view.outer, view.n, view.inner,
+                      int(ddof), ws.data_ptr(), ws_bytes, dev.stream_ptr())
+    _lib.check(rc, f"nbg_reduce({name})")
+    if name in ("allnan", "anynan"):
+        out = out.view(torch.bool)
+    return view.restore(out)
+
+
+def run_reduce_partial(name: str, t: torch.Tensor, axes: tuple[int, ...], index_offset: int = 0):
+    """Element shard -> (3, outs) int64 state records (include/nbg_b200.h) + the view."""
+    work = dev._TORCH_TO_NP[t.dtype]
+    view = ReduceView(t, axes)
+    L = _lib.lib()
+    op = _lib.REDUCE_OPS[name]
+    outs = view.outer * view.inner
+    states = torch.empty((_lib.NBG_REDUCE_STATE_WORDS, outs), dtype=torch.int64, device=t.device)
+    ws_bytes = L.nbg_reduce_workspace_bytes(op, _NBG_DTYPE[work], view.outer, view.n, view.inner)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=t.device)
+    rc = L.nbg_reduce_partial(op, _NBG_DTYPE[work], dev.ptr(view.t), dev.ptr(states), view.outer, view.n,
+                              view.inner, int(index_offset), ws.data_ptr(), ws_bytes, dev.stream_ptr())
+    _lib.check(rc, f"nbg_reduce_partial({name})")
+    return states, view
+
+
+def run_reduce_merge(name: str, work: np.dtype, states: torch.Tensor, n_total: int, ddof: int = 1) -> torch.Tensor:
+    """Fold (parts, 3, outs) gathered state records and finalize -> flat (outs,) result."""
+    parts, _, outs = states.shape
+    L = _lib.lib()
+    out = torch.empty(outs, dtype=_reduce_out_dtype(name, work), device=states.device)
+    rc = L.nbg_reduce_merge(_lib.REDUCE_OPS[name], _NBG_DTYPE[work], dev.ptr(states), parts, outs, dev.ptr(out),
+                            int(n_total), int(ddof), dev.stream_ptr())
+    _lib.check(rc, f"nbg_reduce_merge({name})")
+    return out.view(torch.bool) if name in ("allnan", "anynan") else out
+
+
+def _normalize_axes(axis, nd: int) -> tuple[int, ...]:
+    if axis is None:
+        return tuple(range(nd))
+    if not isinstance(axis, tuple):
+        axis = (axis,)
+    return tuple(np.lib.array_utils.normalize_axis_tuple(axis, nd))
+
+
+def _reduce_result(res: torch.Tensor, as_tensor: bool):
+    if as_tensor:
+        return res
+    host = dev.to_host(res)
+    return host[()] if host.ndim == 0 else host
+
+
+class ndaggregate(NumbaBase):
+    """Simple aggregations over one or more axes (numbagg ``ndaggregate``,
+    decorators.py:188-260): allnan, anynan, nancount, nansum, nanmean, nanvar, nanstd."""
+
+    def __init__(self, name: str, supports_ddof: bool = False, doc: str | None = None):
+        self.supports_ddof = supports_ddof
+        super().__init__(name, doc)
+        if not supports_ddof:
+            params = [p for p in self.__signature__.parameters.values() if p.name != "ddof"]
+            self.__signature__ = self.__signature__.replace(parameters=params)
+
+    def __call__(self, *arrays, ddof: int = 1, axis: int | tuple[int, ...] | None = None):
+        if not all(isinstance(a, np.ndarray) or dev.is_tensor(a) for a in arrays):
+            raise TypeError(f"All positional arguments to {self} must be arrays: {arrays}")
+        if len(arrays) != 1:
+            raise TypeError(f"{self.__name__}() takes exactly one array ({len(arrays)} given)")
+        (arr,) = arrays
+        as_tensor = dev.is_tensor(arr)
+        nd = arr.dim() if as_tensor else arr.ndim
+        axes = _normalize_axes(axis, nd)
+        dt = dev.np_dtype_of(arr)
+        work = _reduce_loop_dtype(self.__name__, dt)
+        t = dev.to_device(arr, work)
+        if len(axes) > 1:
+            # decorators.py:211-230: reduce in memory order, largest stride first
+            order = np.argsort([t.stride(ax) for ax in axes], kind="stable")[::-1]
+            axes = tuple(axes[i] for i in order)
+        res = run_reduce(self.__name__, t, axes, ddof if self.supports_ddof else 1)
+        return _reduce_result(res, as_tensor)
+
+
+class ndreduce(NumbaBase):
+    """Reductions written as scalar-returning loops (numbagg ``ndreduce``,
+    decorators.py:906-1031): nanargmax, nanargmin, nanmax, nanmin.  A tuple `axis` is reduced
+    in the order given; nanarg* return the flat index within those axes."""
+
+    def __call__(self, arr, *args, axis: tuple[int, ...] | int | None = None):
+        if args:
+            raise TypeError(f"{self.__name__}() takes one positional argument")
+        as_tensor = dev.is_tensor(arr)
+        if not as_tensor:
+            arr = np.asarray(arr)
+        nd = arr.dim() if as_tensor else arr.ndim
+        axes = _normalize_axes(axis, nd)
+        name = self.__name__
+        shape = tuple(arr.shape)
+        n = math.prod(shape[ax] for ax in axes)
+        rows = math.prod(s for d, s in enumerate(shape) if d not in axes)
+        if n == 0 and rows > 0:
+            raise ValueError(_REDUCE_EMPTY_ERRORS[name])
+        work = _reduce_loop_dtype(name, dev.np_dtype_of(arr))
+        t = dev.to_device(arr, work)
+        res = run_reduce(name, t, axes)
+        if name in ("nanargmax", "nanargmin"):
+            if as_tensor:
+                if bool((res < 0).any()):
+                    raise ValueError("All-NaN slice encountered")
+                return res
+            host = dev.to_host(res)
+            if (host < 0).any():
+                raise ValueError("All-NaN slice encountered")
+            return host[()] if host.ndim == 0 else host
+        return _reduce_result(res, as_tensor)

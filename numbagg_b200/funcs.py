@@ -1,8 +1,24 @@
-"""ffill / bfill (numbagg/funcs.py:294-326), computed by nbg_fill on the GPU."""
+"""Plain functions of numbagg/funcs.py on the GPU: ffill / bfill (:294-326, nbg_fill) and the
+NaN-aware reductions (:23-242, nbg_reduce)."""
 
-from .decorators import ndfill
+from .decorators import ndaggregate, ndfill, ndreduce
 
 ffill = ndfill("ffill", doc="Forward fill missing values.")
 bfill = ndfill("bfill", doc="Backward fill missing values.")
 
-__all__ = ["ffill", "bfill"]
+allnan = ndaggregate("allnan", doc="True where every element along `axis` is NaN.")
+anynan = ndaggregate("anynan", doc="True where any element along `axis` is NaN.")
+nancount = ndaggregate("nancount", doc="Number of non-NaN elements along `axis`.")
+nansum = ndaggregate("nansum", doc="Sum of the non-NaN elements along `axis`.")
+nanmean = ndaggregate("nanmean", doc="Mean of the non-NaN elements along `axis`.")
+nanvar = ndaggregate("nanvar", supports_ddof=True, doc="Variance of the non-NaN elements along `axis`.")
+nanstd = ndaggregate("nanstd", supports_ddof=True, doc="Standard deviation of the non-NaN elements along `axis`.")
+nanargmax = ndreduce("nanargmax", doc="Flat index of the first maximum, ignoring NaN.")
+nanargmin = ndreduce("nanargmin", doc="Flat index of the first minimum, ignoring NaN.")
+nanmax = ndreduce("nanmax", doc="Maximum, ignoring NaN.")
+nanmin = ndreduce("nanmin", doc="Minimum, ignoring NaN.")
+
+__all__ = [
+    "ffill", "bfill", "allnan", "anynan", "nancount", "nansum", "nanmean", "nanvar", "nanstd",
+    "nanargmax", "nanargmin", "nanmax", "nanmin",
+]

@@ -52,8 +52,12 @@ class Suite:
             self.arrays[key] = arr
         return self._by_hash[h]
 
-    def add(self, func, args, kwargs=None, note=""):
+    def add(self, func, args, kwargs=None, note="", layout=None):
+        """layout: memory order of args[0] as a permutation of its axes (npz files store
+        C-order only; tests/_golden.py re-creates the strides before replaying the case)."""
         kwargs = kwargs or {}
+        if layout is not None:
+            args = [np.ascontiguousarray(args[0].transpose(layout)).transpose(np.argsort(layout))] + list(args[1:])
         idx = len(self.manifest)
         arr_kwargs = {}
         plain_kwargs = {}
@@ -73,7 +77,7 @@ class Suite:
             arg_keys.append(self._store(a))
         self.manifest.append(
             dict(func=func, args=arg_keys, kwargs=plain_kwargs, array_kwargs=arr_kwargs,
-                 out=self._store(out), note=note)
+                 out=self._store(out), note=note, **({"layout": list(layout)} if layout is not None else {}))
         )
 
     def save(self):
@@ -322,7 +326,75 @@ def gen_grouped():
     s.save()
 
 
+def gen_reduce():
+    """Plain NaN reductions (numbagg/funcs.py:23-242): SURVEY 8(f) rank 1."""
+    s = Suite("reduce")
+    funcs = ["allnan", "anynan", "nancount", "nansum", "nanmean", "nanvar", "nanstd",
+             "nanargmax", "nanargmin", "nanmax", "nanmin"]
+    float_only = {"nanmean", "nanvar", "nanstd"}
+    raises_on_allnan = {"nanargmax", "nanargmin"}
+    rs = np.random.RandomState(5)
+    _add = s.add
+
+    def add(f, args, kwargs=None, note="", layout=None):
+        try:
+            _add(f, args, kwargs, note, layout)
+        except ValueError as e:  # nanarg* on a slice without data: covered by the error tests
+            assert "All-NaN" in str(e), e
+
+    s.add = add
+    for dtype in (np.float64, np.float32):
+        a1 = fixture_array((2000,), dtype=dtype, seed=21)
+        a2 = fixture_array((7, 300), nan_frac=0.3, dtype=dtype, seed=22)
+        a3 = fixture_array((4, 6, 50), dtype=dtype, seed=23)
+        signed = np.round((fixture_array((5, 400), dtype=dtype, seed=24) - 0.5) * 8)  # ties, zeros, negatives
+        withrow = a2.copy()
+        withrow[2] = nan  # an all-NaN row
+        special = np.array([[np.inf, nan, 1.0, -np.inf], [nan, -np.inf, nan, -np.inf],
+                            [0.0, -0.0, nan, 0.0], [3.0, 3.0, 3.0, 3.0]], dtype=dtype)
+        big = (fixture_array((3, 30000), dtype=dtype, seed=25) * 1e3 + 1e6).astype(dtype)  # mean >> spread
+        for f in funcs:
+            s.add(f, [a1], {})
+            s.add(f, [a1], dict(axis=0))
+            for axis in (None, -1, 0):
+                s.add(f, [a2], dict(axis=axis))
+                s.add(f, [signed], dict(axis=axis))
+            for axis in (None, 0, 1, 2, (0, 1), (1, 2), (0, 2), (2, 0)):
+                s.add(f, [a3], dict(axis=axis))
+            for axis in (None, 1, (0, 1), (1, 2)):
+                s.add(f, [a3], dict(axis=axis), "permuted memory layout", layout=(2, 0, 1))
+            s.add(f, [big], dict(axis=-1))
+            if f not in raises_on_allnan:
+                s.add(f, [withrow], dict(axis=-1), "all-NaN row")
+                s.add(f, [special], dict(axis=-1), "inf / signed zero / constant rows")
+            else:
+                s.add(f, [special[[0, 2, 3]]], dict(axis=-1), "inf / signed zero / constant rows")
+                s.add(f, [special[[0, 1, 3]]], dict(axis=0))
+        for f in ("nanvar", "nanstd"):
+            for ddof in (0, 1, 2, 5):
+                s.add(f, [a2], dict(axis=-1, ddof=ddof))
+            s.add(f, [a2[:, :2]], dict(axis=-1, ddof=2), "count <= ddof")
+    for dtype in (np.int32, np.int64):
+        i2 = rs.randint(-50, 50, size=(6, 250)).astype(dtype)
+        i3 = rs.randint(-5, 6, size=(3, 5, 40)).astype(dtype)
+        wide = rs.randint(np.iinfo(dtype).min // 4, np.iinfo(dtype).max // 4, size=(4, 300)).astype(dtype)
+        for f in funcs:
+            if f in float_only:
+                continue
+            for axis in (None, -1, 0):
+                s.add(f, [i2], dict(axis=axis))
+            for axis in (1, (0, 2), (2, 1)):
+                s.add(f, [i3], dict(axis=axis))
+            s.add(f, [wide], dict(axis=-1), "wide integers (int64 compares as float64)")
+    # integers through the float-only loops (NumPy casts to float64)
+    ii = rs.randint(-9, 10, size=(5, 60)).astype(np.int64)
+    for f in sorted(float_only):
+        s.add(f, [ii], dict(axis=-1))
+    s.save()
+
+
 if __name__ == "__main__":
+    gen_reduce()
     gen_moving()
     gen_moving_exp()
     gen_fill()

@@ -305,3 +305,109 @@ GROUPED_FUNCS = [
     "group_nanany",
     "group_nanall",
 ]
+
+
+# -------------------------------------------------- plain reductions
+def _reduce_rows(a, axis, by_stride):
+    """Move the reduced axes last (numbagg.utils.move_axes / np.moveaxis) and flatten them.
+    by_stride: ndaggregate first sorts the axes by stride, largest first
+    (decorators.py:211-230 _optimize_axis_order); ndreduce keeps the caller's order."""
+    a = np.asarray(a)
+    if axis is None:
+        axis = tuple(range(a.ndim))
+    elif not isinstance(axis, tuple):
+        axis = (axis,)
+    axis = tuple(ax % a.ndim for ax in axis)
+    if by_stride and len(axis) > 1:
+        order = np.argsort([a.strides[ax] for ax in axis])[::-1]
+        axis = tuple(axis[i] for i in order)
+    moved = np.moveaxis(a, axis, range(a.ndim - len(axis), a.ndim))
+    bshape = moved.shape[: a.ndim - len(axis)]
+    n = int(np.prod(moved.shape[a.ndim - len(axis):], dtype=np.int64))
+    return moved, bshape, n
+
+
+_EMPTY_ERRORS = {
+    "nanargmax": "All-NaN slice encountered",
+    "nanargmin": "All-NaN slice encountered",
+    "nanmax": "zero-size array to reduction operation fmax which has no identity",
+    "nanmin": "zero-size array to reduction operation fmin which has no identity",
+}
+
+
+def _reduce(name, a, out_dtype, *, axis=None, extra=(), by_stride=True):
+    moved, bshape, n = _reduce_rows(a, axis, by_stride)
+    dt = moved.dtype
+    if dt == np.float16:
+        dt = np.dtype(np.float32)
+    if dt not in _SUFFIX:
+        dt = np.dtype(np.float64) if dt.kind == "f" else np.dtype(np.int64)
+    rows = int(np.prod(bshape, dtype=np.int64))
+    if rows > 0 and n == 0 and name in _EMPTY_ERRORS:  # funcs.py:168-169,205-208: `if not a.size: raise`
+        raise ValueError(_EMPTY_ERRORS[name])
+    flat = np.ascontiguousarray(moved, dtype=dt).reshape(rows, n)
+    out = np.empty(rows, dtype=out_dtype(dt) if isinstance(out_dtype, type(lambda: 0)) else out_dtype)
+    fn = getattr(lib(), f"orc_{name}_{_SUFFIX[dt]}")
+    fn.restype = None
+    if rows > 0:
+        fn(_ptr(flat), _ptr(out), _i64(rows), _i64(n), *extra)
+    return out.reshape(bshape)[()] if bshape == () else out.reshape(bshape)
+
+
+def allnan(a, *, axis=None):
+    return _reduce("allnan", a, np.uint8, axis=axis).astype(np.bool_)
+
+
+def anynan(a, *, axis=None):
+    return _reduce("anynan", a, np.uint8, axis=axis).astype(np.bool_)
+
+
+def nancount(a, *, axis=None):
+    return _reduce("nancount", a, np.int64, axis=axis)
+
+
+def nansum(a, *, axis=None):
+    return _reduce("nansum", a, lambda dt: dt, axis=axis)
+
+
+def nanmean(a, *, axis=None):
+    return _reduce("nanmean", np.asarray(a, dtype=_float_loop_dtype(a)), lambda dt: dt, axis=axis)
+
+
+def nanvar(a, *, ddof=1, axis=None):
+    return _reduce("nanvarstd", np.asarray(a, dtype=_float_loop_dtype(a)), lambda dt: dt, axis=axis,
+                   extra=(_i64(ddof), ctypes.c_int(0)))
+
+
+def nanstd(a, *, ddof=1, axis=None):
+    return _reduce("nanvarstd", np.asarray(a, dtype=_float_loop_dtype(a)), lambda dt: dt, axis=axis,
+                   extra=(_i64(ddof), ctypes.c_int(1)))
+
+
+def _arg(name, a, axis):
+    res = _reduce(name, a, np.int64, axis=axis, by_stride=False)
+    if np.any(np.asarray(res) < 0):
+        raise ValueError("All-NaN slice encountered")
+    return res
+
+
+def nanargmax(a, *, axis=None):
+    return _arg("nanargmax", a, axis)
+
+
+def nanargmin(a, *, axis=None):
+    return _arg("nanargmin", a, axis)
+
+
+def nanmax(a, *, axis=None):
+    return _reduce("nanmax", a, lambda dt: dt if dt.kind == "f" else np.dtype(np.int64), axis=axis,
+                   by_stride=False)
+
+
+def nanmin(a, *, axis=None):
+    return _reduce("nanmin", a, lambda dt: dt if dt.kind == "f" else np.dtype(np.int64), axis=axis,
+                   by_stride=False)
+
+
+AGGREGATION_FUNCS = ["allnan", "anynan", "nancount", "nansum", "nanmean", "nanvar", "nanstd",
+                     "nanargmax", "nanargmin", "nanmax", "nanmin"]

@@ -19,6 +19,9 @@ class Case:
         self.suite, self.idx, self.entry = suite, idx, entry
         self.func = entry["func"]
         self.args = [data[k] for k in entry["args"]]
+        if "layout" in entry:  # re-create the strides the reference saw (npz stores C order)
+            perm = entry["layout"]
+            self.args[0] = np.ascontiguousarray(self.args[0].transpose(perm)).transpose(np.argsort(perm))
         self.kwargs = {}
         for k, v in entry["kwargs"].items():
             if isinstance(v, dict) and "np_scalar" in v:
