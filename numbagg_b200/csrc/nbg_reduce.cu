@@ -53,17 +53,43 @@ __device__ __forceinline__ T shfl_xor_t(T v, int m) {
     return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
+// NaN-ignoring extreme of B (a power of two) values as a balanced tree: NaN only if all are
+__device__ __forceinline__ float ext2(float a, float b, bool mx) { return mx ? fmaxf(a, b) : fminf(a, b); }
+__device__ __forceinline__ double ext2(double a, double b, bool mx) { return mx ? fmax(a, b) : fmin(a, b); }
+template <bool MAX, typename K, int B>
+__device__ __forceinline__ K tree_extreme(const K (&x)[B]) {
+    static_assert((B & (B - 1)) == 0, "batch sizes are powers of two");
+    K t[B];
+#pragma unroll
+    for (int b = 0; b < B; b++) t[b] = x[b];
+#pragma unroll
+    for (int w = B / 2; w >= 1; w /= 2)
+#pragma unroll
+        for (int b = 0; b < w; b++) t[b] = ext2(t[b], t[b + w], MAX);
+    return t[0];
+}
+
 // ------------------------------------------------------------------------------- reducers
 // MODE 0 allnan, 1 anynan, 2 nancount -- funcs.py:23-68.
 template <typename T, int MODE>
 struct RCount {
     using In = T;
-    static constexpr bool BATCHED = false;
+    static constexpr bool TWO_PASS = false;
+    static constexpr bool ORDERED = false;
+    static constexpr int MIN_CTAS = 6;  // resident 256-thread CTAs per SM the kernels are compiled for
+    static constexpr bool BATCHED = true;
     struct State {
         i64 c;
     };
     static __device__ __forceinline__ State init() { return {0}; }
     static __device__ __forceinline__ void add(State &s, T v, i64) { s.c += is_nan(v) ? 0 : 1; }
+    template <int B, int V, bool FULL>
+    static __device__ __forceinline__ void add_batch(State &s, const T (&v)[B], uint32_t mask, i64, i64) {
+        int c = 0;  // 32-bit inside the batch, one 64-bit add per batch
+#pragma unroll
+        for (int b = 0; b < B; b++) c += ((FULL || ((mask >> b) & 1u)) && !is_nan(v[b])) ? 1 : 0;
+        s.c += c;
+    }
     static __device__ __forceinline__ void merge(State &a, const State &b) { a.c += b.c; }
     static __device__ __forceinline__ State shfl(const State &s, int m) { return {shfl_xor_t(s.c, m)}; }
     static __device__ __forceinline__ void pack(const State &s, u64 (&w)[3]) {
@@ -87,6 +113,9 @@ struct RCount {
 template <typename T>
 struct RSum {
     using In = T;
+    static constexpr bool TWO_PASS = false;
+    static constexpr bool ORDERED = false;
+    static constexpr int MIN_CTAS = 6;  // resident 256-thread CTAs per SM the kernels are compiled for
     static constexpr bool BATCHED = false;
     static constexpr bool IS_INT = std::is_integral<T>::value;
     using Acc = typename std::conditional<IS_INT, i64, double>::type;
@@ -120,7 +149,10 @@ struct RSum {
 template <typename T>
 struct RMean {
     using In = T;
-    static constexpr bool BATCHED = false;
+    static constexpr bool TWO_PASS = false;
+    static constexpr bool ORDERED = false;
+    static constexpr int MIN_CTAS = 6;  // resident 256-thread CTAs per SM the kernels are compiled for
+    static constexpr bool BATCHED = true;
     struct State {
         double s;
         i64 c;
@@ -130,6 +162,17 @@ struct RMean {
         const bool ok = !is_nan(v);
         s.s += ok ? (double)v : 0.0;
         s.c += ok ? 1 : 0;
+    }
+    template <int B, int V, bool FULL>
+    static __device__ __forceinline__ void add_batch(State &s, const T (&v)[B], uint32_t mask, i64, i64) {
+        int c = 0;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const bool ok = (FULL || ((mask >> b) & 1u)) && !is_nan(v[b]);
+            s.s += ok ? (double)v[b] : 0.0;
+            c += ok ? 1 : 0;
+        }
+        s.c += c;
     }
     static __device__ __forceinline__ void merge(State &a, const State &b) {
         a.s += b.s;
@@ -157,6 +200,9 @@ struct RMean {
 template <typename T, bool SQRT>
 struct RVar {
     using In = T;
+    static constexpr bool TWO_PASS = true;  // rows_tile: mean first, then centred squares
+    static constexpr bool ORDERED = false;
+    static constexpr int MIN_CTAS = 4;  // resident 256-thread CTAs per SM the kernels are compiled for
     static constexpr bool BATCHED = true;
     struct State {
         i64 c;
@@ -180,8 +226,8 @@ struct RVar {
     static __device__ __forceinline__ void add(State &s, T v, i64) {
         if (!is_nan(v)) merge(s, State{1, (double)v, 0.0});
     }
-    template <int B, bool FULL>
-    static __device__ __forceinline__ void add_batch(State &s, const T (&v)[B], uint32_t mask) {
+    template <int B, int V, bool FULL>
+    static __device__ __forceinline__ void add_batch(State &s, const T (&v)[B], uint32_t mask, i64, i64) {
         double x[B];
         uint32_t okm = 0;
         double sum = 0.0;
@@ -235,7 +281,10 @@ struct RVar {
 template <typename T, bool MAX>
 struct RExt {
     using In = T;
-    static constexpr bool BATCHED = false;
+    static constexpr bool TWO_PASS = false;
+    static constexpr bool ORDERED = false;
+    static constexpr int MIN_CTAS = 6;  // resident 256-thread CTAs per SM the kernels are compiled for
+    static constexpr bool BATCHED = true;
     static constexpr bool IS_INT = std::is_integral<T>::value;
     struct State {
         T m;
@@ -252,6 +301,28 @@ struct RExt {
         const bool ok = MAX ? v >= s.m : v <= s.m;
         s.m = ok ? v : s.m;
         s.any |= ok ? 1 : 0;
+    }
+    // a batch folds to its own extreme first (one min/max per element, NaN ignored by the
+    // hardware min/max), then meets the running value once
+    template <int B, int V, bool FULL>
+    static __device__ __forceinline__ void add_batch(State &s, const T (&v)[B], uint32_t mask, i64, i64) {
+        if constexpr (IS_INT) {
+            T m = lowest();
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const T x = (FULL || ((mask >> b) & 1u)) ? v[b] : lowest();
+                m = MAX ? (x > m ? x : m) : (x < m ? x : m);
+            }
+            s.m = MAX ? (m > s.m ? m : s.m) : (m < s.m ? m : s.m);
+            s.any |= (FULL || mask != 0) ? 1 : 0;
+        } else {
+            T x[B];
+#pragma unroll
+            for (int b = 0; b < B; b++) x[b] = (FULL || ((mask >> b) & 1u)) ? v[b] : quiet_nan<T>();
+            const T m = tree_extreme<MAX>(x);
+            s.m = ext2(s.m, m, MAX);
+            s.any |= m == m ? 1 : 0;
+        }
     }
     static __device__ __forceinline__ void merge(State &a, const State &b) {
         if (b.any) add(a, b.m, 0);
@@ -290,7 +361,10 @@ struct RExt {
 template <typename T, bool MAX>
 struct RArg {
     using In = T;
-    static constexpr bool BATCHED = false;
+    static constexpr bool TWO_PASS = false;
+    static constexpr bool ORDERED = true;  // add() needs increasing indices per thread
+    static constexpr int MIN_CTAS = 5;  // resident 256-thread CTAs per SM the kernels are compiled for
+    static constexpr bool BATCHED = true;
     static constexpr bool IS_INT = std::is_integral<T>::value;
     using K = typename std::conditional<IS_INT, double, T>::type;
     struct State {
@@ -305,6 +379,23 @@ struct RArg {
         const bool take = better(k, s.key) || (s.idx < 0 && !is_nan(k));
         s.key = take ? k : s.key;
         s.idx = take ? idx : s.idx;
+    }
+    // The running extreme changes O(log n) times per thread, so a batch is folded to its
+    // extreme with one min/max per element and only a batch that beats the running value
+    // (or is the first with data) looks for the position of its first extreme.
+    template <int B, int V, bool FULL>
+    static __device__ __forceinline__ void add_batch(State &s, const T (&v)[B], uint32_t mask, i64 idx0, i64 kstride) {
+        K x[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) x[b] = (FULL || ((mask >> b) & 1u)) ? (K)v[b] : quiet_nan<K>();
+        const K m = tree_extreme<MAX>(x);
+        if (better(m, s.key) || (s.idx < 0 && m == m)) {
+            int first = 0;
+#pragma unroll
+            for (int b = B - 1; b >= 0; b--) first = x[b] == m ? b : first;
+            s.key = m;
+            s.idx = idx0 + (i64)(first / V) * kstride + (first % V);
+        }
     }
     static __device__ __forceinline__ void merge(State &a, const State &b) {
         const bool take =
@@ -332,7 +423,7 @@ template <typename R, int B, int V, bool FULL>
 __device__ __forceinline__ void add_batch(typename R::State &s, const typename R::In (&v)[B], uint32_t mask,
                                           i64 idx0, i64 kstride) {
     if constexpr (R::BATCHED) {
-        R::template add_batch<B, FULL>(s, v, mask);
+        R::template add_batch<B, V, FULL>(s, v, mask, idx0, kstride);
     } else {
 #pragma unroll
         for (int b = 0; b < B; b++)
@@ -362,7 +453,7 @@ __device__ __forceinline__ void load16(const T *p, T *dst) {
 // ---------------------------------------------------------------------- rows_cta (inner == 1)
 // grid.x = rows * segs.  The CTA reduces positions [seg * seg_len, min(n, ...)) of one row.
 template <typename R>
-__global__ void __launch_bounds__(kRedThreads) red_rows_cta_kernel(const typename R::In *__restrict__ a, RedOut o,
+__global__ void __launch_bounds__(kRedThreads, R::MIN_CTAS) red_rows_cta_kernel(const typename R::In *__restrict__ a, RedOut o,
                                                                     i64 n, i64 segs, i64 seg_len, i64 index_offset) {
     using T = typename R::In;
     using State = typename R::State;
@@ -417,53 +508,178 @@ __global__ void __launch_bounds__(kRedThreads) red_rows_cta_kernel(const typenam
 
 // ------------------------------------------------------------------ group (G lanes / output)
 // Output j = (o, c) reduces a[o, :, c]: element i sits at base + i * inner.  G > 1 only with
-// inner == 1 (the lanes of a group then read consecutive addresses).
-template <typename R>
-__global__ void __launch_bounds__(kRedThreads) red_group_kernel(const typename R::In *__restrict__ a, RedOut o, i64 n,
-                                                                 i64 inner, int G, i64 index_offset) {
+// inner == 1: the lanes of a group then read consecutive VEC-element vectors, so one group
+// moves G * VEC * sizeof(T) contiguous bytes per load (VEC > 1 needs rows that start on a
+// vector boundary: base aligned and n % VEC == 0).
+template <typename T, int VEC>
+__device__ __forceinline__ void load_vec(const T *p, T *dst) {
+    if constexpr (VEC == 1) {
+        dst[0] = *p;
+    } else if constexpr (VEC * sizeof(T) == 8) {
+        *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(p);
+    } else {
+        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(p);
+    }
+}
+
+template <typename R, int VEC>
+__global__ void __launch_bounds__(kRedThreads, R::MIN_CTAS) red_group_kernel(const typename R::In *__restrict__ a, RedOut o,
+                                                                    i64 n, i64 inner, int G, i64 index_offset) {
     using T = typename R::In;
     using State = typename R::State;
-    constexpr int B = 8;
+    constexpr int BV = VEC == 1 ? 8 : 4;  // vectors per batch
+    constexpr int B = BV * VEC;
     const i64 gid = (i64)blockIdx.x * kRedThreads + threadIdx.x;
     const i64 j = gid / G;
     const int g = (int)(gid % G);
     const bool active = j < o.outs;
-    const i64 nn = active ? n : 0;
+    const int nv = active ? (int)(n / VEC) : 0;  // n <= 4096 here: 32-bit positions
     const i64 jo = active ? j : 0;
     const T *p = a + (jo / inner) * n * inner + (jo % inner);
+    const i64 estride = VEC == 1 ? inner : 1;  // element stride (VEC > 1 implies inner == 1)
     State s = R::init();
-    i64 i = g;
-    for (; i + (i64)(B - 1) * G < nn; i += (i64)B * G) {
-        T v[B];
+    int iv = g;
+    for (; iv + (BV - 1) * G < nv; iv += BV * G) {
+        alignas(16) T v[B];
 #pragma unroll
-        for (int b = 0; b < B; b++) v[b] = p[(i + (i64)b * G) * inner];
-        add_batch<R, B, 1, true>(s, v, 0xffffffffu, index_offset + i, G);
+        for (int u = 0; u < BV; u++) load_vec<T, VEC>(p + (i64)(iv + u * G) * VEC * estride, v + u * VEC);
+        add_batch<R, B, VEC, true>(s, v, 0xffffffffu, index_offset + iv * VEC, (i64)G * VEC);
     }
-    if (i < nn) {
-        T v[B];
+    if (iv < nv) {
+        // the last, partial batch: missing float elements become NaN (every reducer skips
+        // NaN), so the mask-free path serves; integers carry a mask
+        alignas(16) T v[B];
         uint32_t mask = 0;
 #pragma unroll
-        for (int b = 0; b < B; b++) {
-            const bool in = i + (i64)b * G < nn;
-            v[b] = in ? p[(i + (i64)b * G) * inner] : T(0);
-            mask |= (in ? 1u : 0u) << b;
+        for (int u = 0; u < BV; u++) {
+            const bool in = iv + u * G < nv;
+            if (in) {
+                load_vec<T, VEC>(p + (i64)(iv + u * G) * VEC * estride, v + u * VEC);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; e++) {
+                    if constexpr (std::is_integral<T>::value)
+                        v[u * VEC + e] = T(0);
+                    else
+                        v[u * VEC + e] = quiet_nan<T>();
+                }
+            }
+            mask |= (in ? ((1u << VEC) - 1u) : 0u) << (u * VEC);
         }
-        add_batch<R, B, 1, false>(s, v, mask, index_offset + i, G);
+        if constexpr (std::is_integral<T>::value)
+            add_batch<R, B, VEC, false>(s, v, mask, index_offset + iv * VEC, (i64)G * VEC);
+        else
+            add_batch<R, B, VEC, true>(s, v, 0xffffffffu, index_offset + iv * VEC, (i64)G * VEC);
     }
     for (int m = G >> 1; m >= 1; m >>= 1) R::merge(s, R::shfl(s, m));
     if (active && g == 0) emit<R>(s, o, j);
+}
+
+// ------------------------------------------------------------- rows_tile (inner == 1, short rows)
+// Short rows cannot be read efficiently one row per thread or per sub-warp: a warp's load
+// then touches many separate 32-byte pieces.  Here the CTA takes a CONTIGUOUS run of rows
+// (<= 32 KB), brings it in with one bulk async copy (TMA engine, full-width DRAM bursts
+// whatever n is), and G lanes per row reduce it out of shared memory.  With one lane per row
+// and an even n the lanes start at rotated positions so that they fall on distinct banks.
+constexpr int kTileBytes = 32 * 1024;
+
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads, R::MIN_CTAS) red_rows_tile_kernel(const typename R::In *__restrict__ a,
+                                                                                  RedOut o, int n, i64 rows, int tile_rows,
+                                                                                  int log2g, i64 index_offset) {
+    using T = typename R::In;
+    using State = typename R::State;
+    extern __shared__ __align__(128) unsigned char red_smem[];
+    T *s = reinterpret_cast<T *>(red_smem);
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const i64 row0 = (i64)blockIdx.x * tile_rows;
+    const int nrows = (int)(rows - row0 < tile_rows ? rows - row0 : tile_rows);
+    const int elems = nrows * n;
+    const T *src = a + row0 * n;
+    const uint32_t bytes = ((uint32_t)elems * (uint32_t)sizeof(T)) & ~15u;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0 && bytes) {
+        mbar_arrive_expect_tx(&bar, bytes);
+        bulk_g2s(s, src, bytes, &bar);
+    }
+    const int tail0 = (int)(bytes / sizeof(T));
+    if (tid < elems - tail0) s[tail0 + tid] = src[tail0 + tid];
+    if (bytes) mbar_wait(&bar, 0);
+    __syncthreads();
+
+    const int G = 1 << log2g;
+    const int rpp = kRedThreads >> log2g;  // rows per pass
+    const int g = tid & (G - 1), rl = tid >> log2g;
+    // one lane per row and an even n: lane l starts at element l % n, which spreads the
+    // lanes over the banks (rpp is a multiple of 32, so the offset is fixed per thread)
+    const int rot = (!R::ORDERED && G == 1 && (n & 1) == 0) ? (tid & 31) % n : 0;
+    for (int r0 = 0; r0 < nrows; r0 += rpp) {
+        const int r = r0 + rl;
+        const bool act = r < nrows;
+        const T *row = s + (act ? r : 0) * n;
+        const int nn = act ? n : 0;
+        State st = R::init();
+        // f(value, element index) over this lane's elements g, g + G, ...
+        auto lane_elements = [&](auto &&f) {
+            if (rot) {
+#pragma unroll 4
+                for (int e = g; e < nn; e += G) {
+                    int pos = e + rot;
+                    pos = pos >= n ? pos - n : pos;
+                    f(row[pos], pos);
+                }
+            } else {
+#pragma unroll 4
+                for (int e = g; e < nn; e += G) f(row[e], e);
+            }
+        };
+        if constexpr (R::TWO_PASS) {
+            // the tile sits in shared memory, so the reference's own two loops (funcs.py:
+            // 118-133) cost no second DRAM read: sum & count, then centred squares
+            double sum = 0.0;
+            int c = 0;
+            lane_elements([&](T v, int) {
+                const bool ok = !is_nan(v);
+                sum += ok ? (double)v : 0.0;
+                c += ok ? 1 : 0;
+            });
+            for (int m = G >> 1; m >= 1; m >>= 1) {
+                sum += shfl_xor_t(sum, m);
+                c += shfl_xor_t(c, m);
+            }
+            const double mean = c > 0 ? sum / (double)c : 0.0;
+            double m2 = 0.0;
+            lane_elements([&](T v, int) {
+                const double d = is_nan(v) ? 0.0 : (double)v - mean;
+                m2 = fma(d, d, m2);
+            });
+            for (int m = G >> 1; m >= 1; m >>= 1) m2 += shfl_xor_t(m2, m);
+            st.c = c;
+            st.mean = mean;
+            st.m2 = m2;
+        } else {
+            lane_elements([&](T v, int e) { R::add(st, v, index_offset + e); });
+            for (int m = G >> 1; m >= 1; m >>= 1) R::merge(st, R::shfl(st, m));
+        }
+        if (act && g == 0) emit<R>(st, o, row0 + r);
+    }
 }
 
 // ------------------------------------------------------------------------- cols (inner > 1)
 // grid = (outer * segs, column tiles).  Thread tid < tprime = w * rps handles column
 // col0 + tid % w and rows lo + tid / w + k * rps: consecutive threads, consecutive addresses.
 template <typename R>
-__global__ void __launch_bounds__(kRedThreads) red_cols_kernel(const typename R::In *__restrict__ a, RedOut o, i64 n,
-                                                                i64 inner, i64 segs, i64 seg_len, int w, int rps,
-                                                                i64 index_offset) {
+__global__ void __launch_bounds__(kRedThreads, R::MIN_CTAS) red_cols_kernel(const typename R::In *__restrict__ a, RedOut o,
+                                                                   i64 n, i64 inner, i64 segs, i64 seg_len, int w,
+                                                                   int rps, i64 index_offset) {
     using T = typename R::In;
     using State = typename R::State;
-    constexpr int B = 8;
+    constexpr int B = (sizeof(T) == 4 && R::MIN_CTAS >= 6 && !std::is_integral<T>::value) ? 16 : 8;
     const int tid = threadIdx.x;
     const i64 oi = blockIdx.x / segs, seg = blockIdx.x % segs;
     const i64 col = (i64)blockIdx.y * w + tid % w;
@@ -548,37 +764,69 @@ __global__ void red_const_kernel(RedOut o, int mode, i64 n) {
 }
 
 // ------------------------------------------------------------------------------ geometry
-enum RedMode { RED_ROWS_CTA = 0, RED_GROUP = 1, RED_COLS = 2 };
+enum RedMode { RED_ROWS_CTA = 0, RED_GROUP = 1, RED_COLS = 2, RED_ROWS_TILE = 3 };
 struct RedGeom {
     int mode;
     i64 segs, seg_len;
-    int G;         // group
+    int G, vec;    // group
     int w, rps;    // cols
     i64 coltiles;  // cols
+    int tile_rows;  // rows_tile
 };
 
-constexpr i64 kTargetCtas = (i64)kNumSMs * 8;
+// CTAs of one full wave for an op (its reducer's MIN_CTAS): segment counts aim at exactly that
+inline i64 target_ctas(int op) {
+    const int per_sm = (op == NBG_RED_NANVAR || op == NBG_RED_NANSTD) ? 4 : (op == NBG_RED_NANARGMAX || op == NBG_RED_NANARGMIN) ? 5 : 6;
+    return (i64)kNumSMs * per_sm;
+}
 
 inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
 
-RedGeom red_geometry(i64 outer, i64 n, i64 inner) {
+// itemsize / addr: element size and address of the input (vector width of the group kernel)
+// Segments per slice for `slices` independent slices: with few slices, as many as fill ONE
+// wave of resident CTAs (equal work, no tail); otherwise at least four waves in total.
+inline i64 pick_segs(i64 slices, i64 wave, i64 max_segs) {
+    if (slices < 1) slices = 1;
+    i64 segs;
+    if (slices * 4 <= wave)
+        segs = wave / slices;
+    else if (slices >= 8 * wave)
+        segs = 1;
+    else
+        segs = ceil_div(4 * wave, slices);
+    if (segs > max_segs) segs = max_segs;
+    return segs < 1 ? 1 : segs;
+}
+
+RedGeom red_geometry(int op, i64 outer, i64 n, i64 inner, int itemsize = 4, uintptr_t addr = 0) {
+    const i64 kTargetCtas = target_ctas(op);
     RedGeom g{};
     g.segs = 1;
     g.seg_len = n > 0 ? n : 1;
     g.G = 1;
+    g.vec = 1;
     if (inner == 1) {
-        if (n <= 4096) {
-            g.mode = RED_GROUP;
+        if (n > 0 && n * itemsize <= 4096 && outer >= 64 && addr % 16 == 0) {
+            g.mode = RED_ROWS_TILE;
+            g.tile_rows = (int)((kTileBytes / (n * itemsize)) & ~(i64)3);
             int G = 1;
             while (G < 32 && (i64)G * 16 < n) G <<= 1;
             g.G = G;
             return g;
         }
+        if (n <= 4096) {
+            g.mode = RED_GROUP;
+            int vec = 16 / itemsize;
+            while (vec > 1 && (n % vec != 0 || addr % (uintptr_t)(vec * itemsize) != 0)) vec >>= 1;
+            g.vec = vec;
+            const i64 nv = n / vec;  // each lane should own >= 2 vectors
+            int G = 1;
+            while (G < 32 && (i64)G * 4 <= nv) G <<= 1;
+            g.G = G;
+            return g;
+        }
         g.mode = RED_ROWS_CTA;
-        i64 segs = ceil_div(kTargetCtas, outer > 0 ? outer : 1);
-        const i64 max_segs = ceil_div(n, 4096);
-        if (segs > max_segs) segs = max_segs;
-        if (segs < 1) segs = 1;
+        const i64 segs = pick_segs(outer, kTargetCtas, ceil_div(n, 4096));
         i64 seg_len = ceil_div(ceil_div(n, segs), 1024) * 1024;
         g.seg_len = seg_len;
         g.segs = ceil_div(n, seg_len);
@@ -594,10 +842,7 @@ RedGeom red_geometry(i64 outer, i64 n, i64 inner) {
     g.rps = inner <= kRedThreads ? (int)(kRedThreads / inner) : 1;
     g.coltiles = ceil_div(inner, w);
     const i64 base = g.coltiles * (outer > 0 ? outer : 1);
-    i64 segs = ceil_div(kTargetCtas, base);
-    const i64 max_segs = ceil_div(n, (i64)16 * g.rps);
-    if (segs > max_segs) segs = max_segs;
-    if (segs < 1) segs = 1;
+    const i64 segs = pick_segs(base, kTargetCtas, ceil_div(n, (i64)16 * g.rps));
     g.seg_len = ceil_div(n, segs);
     g.segs = ceil_div(n, g.seg_len);
     return g;
@@ -605,6 +850,7 @@ RedGeom red_geometry(i64 outer, i64 n, i64 inner) {
 
 // ------------------------------------------------------------------------------ launching
 struct RedArgs {
+    int op;
     const void *a;
     void *out;
     u64 *states;  // partial mode: caller's record array (part 0 of 1)
@@ -629,7 +875,7 @@ int launch_reduce(const RedArgs &x) {
     using T = typename R::In;
     const i64 outs = x.outer * x.inner;
     if (outs <= 0) return NBG_OK;
-    const RedGeom g = red_geometry(x.outer, x.n, x.inner);
+    const RedGeom g = red_geometry(x.op, x.outer, x.n, x.inner, (int)sizeof(T), (uintptr_t)x.a);
     RedOut fin{x.out, x.states, outs, 0, x.partial ? 1 : 0, x.n, x.ddof};
     RedOut first = fin;
     if (g.segs > 1) {
@@ -647,10 +893,25 @@ int launch_reduce(const RedArgs &x) {
         red_rows_cta_kernel<R><<<(unsigned)ctas, kRedThreads, 0, x.stream>>>(a, first, x.n, g.segs, g.seg_len,
                                                                              x.index_offset);
         rc = check_launch("nbg_reduce rows");
+    } else if (g.mode == RED_ROWS_TILE) {
+        const i64 ctas = ceil_div(x.outer, g.tile_rows);
+        if (ctas > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_reduce: too many rows");
+        red_rows_tile_kernel<R><<<(unsigned)ctas, kRedThreads, (size_t)g.tile_rows * x.n * sizeof(T), x.stream>>>(
+            a, first, (int)x.n, x.outer, g.tile_rows, __builtin_ctz((unsigned)g.G), x.index_offset);
+        rc = check_launch("nbg_reduce rows_tile");
     } else if (g.mode == RED_GROUP) {
         const i64 ctas = ceil_div(outs * g.G, kRedThreads);
         if (ctas > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_reduce: too many outputs");
-        red_group_kernel<R><<<(unsigned)ctas, kRedThreads, 0, x.stream>>>(a, first, x.n, x.inner, g.G, x.index_offset);
+        constexpr int VMAX = 16 / (int)sizeof(T);
+        if (g.vec == VMAX)
+            red_group_kernel<R, VMAX><<<(unsigned)ctas, kRedThreads, 0, x.stream>>>(a, first, x.n, x.inner, g.G,
+                                                                                  x.index_offset);
+        else if (g.vec == 2 && VMAX > 2)
+            red_group_kernel<R, (VMAX > 2 ? 2 : 1)><<<(unsigned)ctas, kRedThreads, 0, x.stream>>>(
+                a, first, x.n, x.inner, g.G, x.index_offset);
+        else
+            red_group_kernel<R, 1><<<(unsigned)ctas, kRedThreads, 0, x.stream>>>(a, first, x.n, x.inner, g.G,
+                                                                               x.index_offset);
         rc = check_launch("nbg_reduce group");
     } else {
         const i64 gx = x.outer * g.segs;
@@ -735,17 +996,16 @@ int reduce_entry(int op, int dtype, const RedArgs &x) {
 using namespace nbg;
 
 extern "C" size_t nbg_reduce_workspace_bytes(int op, int dtype, int64_t outer, int64_t n, int64_t inner) {
-    (void)op;
     (void)dtype;
     if (outer <= 0 || n <= 0 || inner <= 0) return 0;
-    const RedGeom g = red_geometry(outer, n, inner);
+    const RedGeom g = red_geometry(op, outer, n, inner);
     if (g.segs <= 1) return 0;
     return (size_t)g.segs * kStateWords * (size_t)(outer * inner) * sizeof(u64);
 }
 
 extern "C" int nbg_reduce(int op, int dtype, const void *a, void *out, int64_t outer, int64_t n, int64_t inner,
                           int64_t ddof, void *workspace, size_t workspace_bytes, void *stream) {
-    RedArgs x{a, out, nullptr, outer, n, inner, ddof, 0, workspace, workspace_bytes, (cudaStream_t)stream, false};
+    RedArgs x{op, a, out, nullptr, outer, n, inner, ddof, 0, workspace, workspace_bytes, (cudaStream_t)stream, false};
     if (outer * inner > 0 && (out == nullptr || (a == nullptr && n > 0)))
         return fail(NBG_ERR_BAD_ARG, "nbg_reduce: null pointer");
     return reduce_entry(op, dtype, x);
@@ -754,7 +1014,7 @@ extern "C" int nbg_reduce(int op, int dtype, const void *a, void *out, int64_t o
 extern "C" int nbg_reduce_partial(int op, int dtype, const void *a, void *states, int64_t outer, int64_t n,
                                   int64_t inner, int64_t index_offset, void *workspace, size_t workspace_bytes,
                                   void *stream) {
-    RedArgs x{a,         nullptr,         (u64 *)states,        outer, n,   inner, 0, index_offset,
+    RedArgs x{op, a,         nullptr,         (u64 *)states,        outer, n,   inner, 0, index_offset,
               workspace, workspace_bytes, (cudaStream_t)stream, true};
     if (outer * inner > 0 && (states == nullptr || (a == nullptr && n > 0)))
         return fail(NBG_ERR_BAD_ARG, "nbg_reduce_partial: null pointer");
