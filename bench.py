@@ -81,6 +81,20 @@ WORKLOADS = {
     "cfg5_group_nanfirst": ("group1d", "group_nanfirst", "f64", 1, 2_000_000_000, dict(num_labels=10_000_000)),
     "cfg5_group_nanvar": ("group1d", "group_nanvar", "f64", 1, 2_000_000_000, dict(num_labels=10_000_000)),
 }
+# SURVEY 8(f) rank 1 (plain NaN reductions) on the config-2 / config-4 shapes
+WORKLOADS.update({
+    "red_nansum_f32": ("reduce", "nansum", "f32", 10_000, 1_000_000, dict(axis=-1)),
+    "red_nanmean_f32": ("reduce", "nanmean", "f32", 10_000, 1_000_000, dict(axis=-1)),
+    "red_nanvar_f32": ("reduce", "nanvar", "f32", 10_000, 1_000_000, dict(axis=-1)),
+    "red_nanmax_f32": ("reduce", "nanmax", "f32", 10_000, 1_000_000, dict(axis=-1)),
+    "red_nanargmax_f32": ("reduce", "nanargmax", "f32", 10_000, 1_000_000, dict(axis=-1)),
+    "red_nansum_f64": ("reduce", "nansum", "f64", 2000, 1_000_000, dict(axis=-1)),
+    "red_nanstd_f64": ("reduce", "nanstd", "f64", 2000, 1_000_000, dict(axis=-1)),
+    "red_nansum_f32_axis0": ("reduce", "nansum", "f32", 1_000_000, 1000, dict(axis=0)),
+    "red_nanvar_f64_axis0": ("reduce", "nanvar", "f64", 1_000_000, 1000, dict(axis=0)),
+    "red_nanmean_f32_short": ("reduce", "nanmean", "f32", 10_000_000, 100, dict(axis=-1)),
+    "red_nansum_f64_all": ("reduce", "nansum", "f64", 1, 1_000_000_000, dict(axis=None)),
+})
 DEFAULT_WORKLOAD = "cfg2_group_nansum"
 TWO_INPUT = {"move_cov", "move_corr", "move_exp_nancov", "move_exp_nancorr"}
 NP_DT = {"f32": np.float32, "f64": np.float64}
@@ -95,6 +109,9 @@ def alg_bytes(family, func, dt, rows, n, params):
     s = 4 if dt == "f32" else 8
     if family in ("move", "exp", "fill"):
         return rows * n * s * (3 if func in TWO_INPUT else 2)
+    if family == "reduce":
+        outs = {None: 1, -1: rows, 0: n}[params["axis"]]
+        return rows * n * s + outs * 8
     K = params["num_labels"]
     if family == "group":
         return rows * n * s + n * 8 + rows * K * s
@@ -110,6 +127,8 @@ def host_batch(family, func, dt, rows, n, params, seed=0):
     if func in TWO_INPUT:
         args.append((a.astype(np.float64) ** 2 + 1).astype(NP_DT[dt]))
     kwargs = dict(params)
+    if family == "reduce" and rows == 1:
+        args = [a.reshape(-1)]
     if family == "group":
         args.append(np.random.RandomState(0).randint(0, params["num_labels"], size=n).astype(np.int64))
         kwargs["axis"] = -1
@@ -262,6 +281,9 @@ def run_ours(args, wl):
             return D.run_move_exp(func, tensors, al, 0.0, -1)[0]
         if family == "fill":
             return D.run_fill(func, a, n, -1)[0]
+        if family == "reduce":
+            axes = (0, 1) if params["axis"] is None else (params["axis"] % 2,)
+            return D.run_reduce(func, a, axes)
         v2 = a if family == "group" else a.view(1, -1)
         return D.run_group(func, v2, labels, params["num_labels"], 1)
 

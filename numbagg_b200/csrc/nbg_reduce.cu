@@ -22,6 +22,8 @@
 // read of the data).  Counts, flags, extrema and arg-extrema are exact.
 #include "nbg_common.cuh"
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 namespace nbg {
@@ -51,6 +53,16 @@ __device__ __forceinline__ double w2d(u64 w) { return __longlong_as_double((i64)
 template <typename T>
 __device__ __forceinline__ T shfl_xor_t(T v, int m) {
     return __shfl_xor_sync(0xffffffffu, v, m);
+}
+
+// 1 / c for a positive count c: hardware float reciprocal + two Newton steps in double
+// (relative error ~1e-29 before the final rounding) instead of the ~25-instruction division.
+__device__ __forceinline__ double fast_rcp(double c) {
+    double y = (double)__frcp_rn((float)c);
+    double e = fma(-c, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-c, y, 1.0);
+    return fma(y, e, y);
 }
 
 // NaN-ignoring extreme of B (a power of two) values as a balanced tree: NaN only if all are
@@ -216,8 +228,7 @@ struct RVar {
             return;
         }
         const double ca = (double)a.c, cb = (double)b.c;
-        const double c = ca + cb;
-        const double r = cb / c;
+        const double r = cb * fast_rcp(ca + cb);
         const double d = b.mean - a.mean;
         a.mean = fma(d, r, a.mean);
         a.m2 = a.m2 + b.m2 + d * d * ca * r;
@@ -226,34 +237,38 @@ struct RVar {
     static __device__ __forceinline__ void add(State &s, T v, i64) {
         if (!is_nan(v)) merge(s, State{1, (double)v, 0.0});
     }
+    // One register batch, two passes.  Pass 1 runs in the INPUT type: all it must deliver is
+    // a centre K near the batch mean (any K works; the closer, the smaller s1).  Missing
+    // elements are replaced by K itself, so pass 2 needs no masks: their deviation is 0.
     template <int B, int V, bool FULL>
     static __device__ __forceinline__ void add_batch(State &s, const T (&v)[B], uint32_t mask, i64, i64) {
-        double x[B];
         uint32_t okm = 0;
-        double sum = 0.0;
+        T sum = T(0);
 #pragma unroll
         for (int b = 0; b < B; b++) {
             const bool ok = (FULL || ((mask >> b) & 1u)) && !is_nan(v[b]);
-            x[b] = ok ? (double)v[b] : 0.0;
             okm |= (ok ? 1u : 0u) << b;
-            sum += x[b];
+            sum += ok ? v[b] : T(0);
         }
         const int cb = __popc(okm);
         if (cb == 0) return;
-        const double rb = 1.0 / (double)cb;
-        const double k = sum * rb;  // batch centre (within an ulp of the batch mean)
+        const double rb = fast_rcp((double)cb);
+        T k = sum * (T)rb;
+        if (!(fabs((double)k) <= 1.7e308)) k = T(0);  // overflowed / infinite sum: any finite centre
+        const double kd = (double)k;
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
         for (int b = 0; b < B; b++) {
-            const double d = ((okm >> b) & 1u) ? x[b] - k : 0.0;
+            const T x = ((okm >> b) & 1u) ? v[b] : k;
+            const double d = (double)x - kd;
             s1 += d;
             s2 = fma(d, d, s2);
         }
         State bs;
         bs.c = cb;
-        bs.mean = fma(s1, rb, k);
-        bs.m2 = fmax(s2 - s1 * s1 * rb, 0.0);
-        if (s2 != s2) bs.m2 = s2;  // keep NaN (inf - inf) like the reference
+        bs.mean = fma(s1, rb, kd);
+        bs.m2 = s2 - s1 * s1 * rb;
+        if (bs.m2 < 0.0) bs.m2 = 0.0;  // rounding only; NaN (inf - inf, as in the reference) stays NaN
         merge(s, bs);
     }
     static __device__ __forceinline__ State shfl(const State &s, int m) {
@@ -584,7 +599,7 @@ __global__ void __launch_bounds__(kRedThreads, R::MIN_CTAS) red_group_kernel(con
 constexpr int kTileBytes = 32 * 1024;
 
 template <typename R>
-__global__ void __launch_bounds__(kRedThreads, R::MIN_CTAS) red_rows_tile_kernel(const typename R::In *__restrict__ a,
+__global__ void __launch_bounds__(kRedThreads, 6) red_rows_tile_kernel(const typename R::In *__restrict__ a,
                                                                                   RedOut o, int n, i64 rows, int tile_rows,
                                                                                   int log2g, i64 index_offset) {
     using T = typename R::In;
@@ -652,7 +667,7 @@ __global__ void __launch_bounds__(kRedThreads, R::MIN_CTAS) red_rows_tile_kernel
                 sum += shfl_xor_t(sum, m);
                 c += shfl_xor_t(c, m);
             }
-            const double mean = c > 0 ? sum / (double)c : 0.0;
+            const double mean = c > 0 ? sum * fast_rcp((double)c) : 0.0;
             double m2 = 0.0;
             lane_elements([&](T v, int) {
                 const double d = is_nan(v) ? 0.0 : (double)v - mean;
@@ -722,6 +737,135 @@ __global__ void __launch_bounds__(kRedThreads, R::MIN_CTAS) red_cols_kernel(cons
     }
 }
 
+// ----------------------------------------------------------------------------------- stream
+// The main kernel for long reductions: rows (inner == 1, w = 1), narrow columns (inner <=
+// 256, w = inner) and 16-byte-aligned wide columns (w = 256 of inner).  The CTA owns rows
+// [lo, hi) x w columns of one outer slice and pulls them through a 3-stage shared-memory ring
+// with bulk async copies (one copy per chunk when the tile is contiguous, one per row piece
+// otherwise), so the bytes in flight live in shared memory, not in registers, and DRAM
+// latency is hidden whatever the reducer costs.  Thread tid < w * rps reads ring positions
+// tid + b * (w * rps): consecutive threads, consecutive words, always the same column.
+// Threads that share a column merge through a shared-memory tree at the end.
+constexpr int kStreamStages = 3;
+constexpr int kStreamCtasPerSM = 4;
+
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads, kStreamCtasPerSM) red_stream_kernel(
+    const typename R::In *__restrict__ a, RedOut o, i64 n, i64 inner, i64 segs, i64 seg_len, int w, int rps,
+    i64 index_offset) {
+    using T = typename R::In;
+    using State = typename R::State;
+    constexpr int EPT = sizeof(T) == 4 ? 16 : 8;  // elements per thread per chunk (<= 16 KB chunks)
+    extern __shared__ __align__(128) unsigned char red_smem[];
+    __shared__ uint64_t full[kStreamStages];
+    __shared__ State sm[kRedThreads];
+    const int tid = threadIdx.x;
+    const i64 oi = blockIdx.x / segs, seg = blockIdx.x % segs;
+    const i64 col0 = (i64)blockIdx.y * w;
+    const int tprime = w * rps;
+    const int cw = (int)(inner - col0 < w ? inner - col0 : w);  // live columns of this tile
+    const int col = tid % w, r0 = tid / w;
+    const bool active = tid < tprime && col < cw;
+    const i64 lo = seg * seg_len;
+    const i64 hi = lo + seg_len < n ? lo + seg_len : n;
+    const i64 nrows = hi > lo ? hi - lo : 0;
+    const int chunk_rows = EPT * rps;
+    const i64 nchunks = (nrows + chunk_rows - 1) / chunk_rows;
+    const T *region = a + (oi * n + lo) * inner + col0;
+    const bool contiguous = w == inner;
+    constexpr uint32_t STAGE_BYTES = EPT * kRedThreads * sizeof(T);
+
+    if (tid == 0) {
+        for (int st = 0; st < kStreamStages; st++) mbar_init(&full[st], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // all threads call; chunk k goes to stage k % kStreamStages
+    auto produce = [&](i64 k) {
+        if (k >= nchunks) return;
+        const int stg = (int)(k % kStreamStages);
+        T *dst = reinterpret_cast<T *>(red_smem + (size_t)stg * STAGE_BYTES);
+        const i64 rb = k * chunk_rows;
+        const int rc = (int)(nrows - rb < chunk_rows ? nrows - rb : chunk_rows);
+        if (contiguous) {
+            if (tid == 0) {
+                const uint32_t bytes = ((uint32_t)rc * (uint32_t)w * (uint32_t)sizeof(T)) & ~15u;
+                mbar_arrive_expect_tx(&full[stg], bytes);
+                if (bytes) bulk_g2s(dst, region + rb * inner, bytes, &full[stg]);
+            }
+        } else {
+            const uint32_t row_bytes = (uint32_t)cw * (uint32_t)sizeof(T);
+            if (tid == 0) mbar_arrive_expect_tx(&full[stg], row_bytes * (uint32_t)rc);
+            if (tid < rc) bulk_g2s(dst + (size_t)tid * w, region + (rb + tid) * inner, row_bytes, &full[stg]);
+        }
+    };
+    for (int k = 0; k < kStreamStages; k++) produce(k);
+
+    State s = R::init();
+    for (i64 k = 0; k < nchunks; k++) {
+        const int stg = (int)(k % kStreamStages);
+        const T *src = reinterpret_cast<const T *>(red_smem + (size_t)stg * STAGE_BYTES);
+        mbar_wait(&full[stg], (uint32_t)((k / kStreamStages) & 1));
+        const i64 rb = k * chunk_rows;
+        const int rc = (int)(nrows - rb < chunk_rows ? nrows - rb : chunk_rows);
+        if (active) {
+            T v[EPT];
+            if (rc == chunk_rows) {
+#pragma unroll
+                for (int b = 0; b < EPT; b++) v[b] = src[tid + b * tprime];
+                add_batch<R, EPT, 1, true>(s, v, 0xffffffffu, index_offset + lo + rb + r0, rps);
+            } else {
+                // last chunk: rows past the end are NaN (floats) or masked (ints); a row tail
+                // the 16-byte-granular copy left behind (contiguous tiles) comes from global
+                const int copied = contiguous ? (int)((((uint32_t)rc * w * sizeof(T)) & ~15u) / sizeof(T)) : rc * w;
+                uint32_t mask = 0;
+#pragma unroll
+                for (int b = 0; b < EPT; b++) {
+                    const int pos = tid + b * tprime;
+                    const bool in = r0 + b * rps < rc;
+                    T x;
+                    if constexpr (std::is_integral<T>::value)
+                        x = T(0);
+                    else
+                        x = quiet_nan<T>();
+                    if (in) x = pos < copied ? src[pos] : region[rb * inner + pos];
+                    v[b] = x;
+                    mask |= (in ? 1u : 0u) << b;
+                }
+                if constexpr (std::is_integral<T>::value)
+                    add_batch<R, EPT, 1, false>(s, v, mask, index_offset + lo + rb + r0, rps);
+                else
+                    add_batch<R, EPT, 1, true>(s, v, 0xffffffffu, index_offset + lo + rb + r0, rps);
+            }
+        }
+        __syncthreads();  // everyone is done with this stage: refill it
+        produce(k + kStreamStages);
+    }
+
+    // merge the rps threads of each column (tree over r0), owner r0 == 0 emits
+    if (rps > 1) {
+        sm[tid] = s;
+        __syncthreads();
+        int span = 1;
+        while (span < rps) span <<= 1;
+        for (int h = span >> 1; h >= 1; h >>= 1) {
+            if (tid < tprime && r0 < h && r0 + h < rps) {
+                State mine = sm[tid];
+                R::merge(mine, sm[tid + h * w]);
+                sm[tid] = mine;
+            }
+            __syncthreads();
+        }
+        s = sm[tid];
+    }
+    if (active && r0 == 0) {
+        RedOut oo = o;
+        if (segs > 1) oo.part = seg;
+        emit<R>(s, oo, oi * inner + col0 + col);
+    }
+}
+
 // --------------------------------------------------------------------------------- merge
 // Fold `parts` state records per output (segments of one launch, or shards of several
 // devices: states[(part * 3 + word) * outs + j]).  lanes = 1: a thread per output (coalesced
@@ -764,7 +908,7 @@ __global__ void red_const_kernel(RedOut o, int mode, i64 n) {
 }
 
 // ------------------------------------------------------------------------------ geometry
-enum RedMode { RED_ROWS_CTA = 0, RED_GROUP = 1, RED_COLS = 2, RED_ROWS_TILE = 3 };
+enum RedMode { RED_ROWS_CTA = 0, RED_GROUP = 1, RED_COLS = 2, RED_ROWS_TILE = 3, RED_STREAM = 4 };
 struct RedGeom {
     int mode;
     i64 segs, seg_len;
@@ -783,19 +927,33 @@ inline i64 target_ctas(int op) {
 inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
 
 // itemsize / addr: element size and address of the input (vector width of the group kernel)
+constexpr i64 kStreamWave = (i64)kNumSMs * kStreamCtasPerSM;
+
 // Segments per slice for `slices` independent slices: with few slices, as many as fill ONE
 // wave of resident CTAs (equal work, no tail); otherwise at least four waves in total.
 inline i64 pick_segs(i64 slices, i64 wave, i64 max_segs) {
     if (slices < 1) slices = 1;
-    i64 segs;
-    if (slices * 4 <= wave)
-        segs = wave / slices;
-    else if (slices >= 8 * wave)
-        segs = 1;
-    else
-        segs = ceil_div(4 * wave, slices);
-    if (segs > max_segs) segs = max_segs;
-    return segs < 1 ? 1 : segs;
+    if (max_segs < 1) max_segs = 1;
+    if (slices * 4 <= wave) {
+        const i64 segs = wave / slices;
+        return segs > max_segs ? max_segs : segs;
+    }
+    if (slices >= 8 * wave) return 1;
+    // a few candidates past four waves: take the one whose last wave is fullest
+    i64 best = 1;
+    double best_eff = -1.0;
+    const i64 s0 = ceil_div(4 * wave, slices);
+    for (i64 segs = s0; segs < s0 + 4; segs++) {
+        const i64 sg = segs > max_segs ? max_segs : segs;
+        const i64 ctas = slices * sg;
+        // fuller last wave, but every extra segment costs a prologue and a merge record
+        const double eff = (double)ctas / (double)(ceil_div(ctas, wave) * wave) - 0.02 * (double)(segs - s0);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = sg;
+        }
+    }
+    return best;
 }
 
 RedGeom red_geometry(int op, i64 outer, i64 n, i64 inner, int itemsize = 4, uintptr_t addr = 0) {
@@ -825,8 +983,15 @@ RedGeom red_geometry(int op, i64 outer, i64 n, i64 inner, int itemsize = 4, uint
             g.G = G;
             return g;
         }
-        g.mode = RED_ROWS_CTA;
-        const i64 segs = pick_segs(outer, kTargetCtas, ceil_div(n, 4096));
+        // (the stream kernel handles rows too -- w = 1 -- but measured ~8% slower than direct
+        // 16-byte loads on this fully coalesced shape; NBG_RED_STREAM_ROWS=1 selects it)
+        static const bool stream_rows = getenv("NBG_RED_STREAM_ROWS") != nullptr;
+        const bool stream = stream_rows && addr % 16 == 0 && (outer == 1 || (n * itemsize) % 16 == 0);
+        g.mode = stream ? RED_STREAM : RED_ROWS_CTA;
+        g.w = 1;
+        g.rps = kRedThreads;
+        g.coltiles = 1;
+        const i64 segs = pick_segs(outer, stream ? kStreamWave : kTargetCtas, ceil_div(n, 16384));
         i64 seg_len = ceil_div(ceil_div(n, segs), 1024) * 1024;
         g.seg_len = seg_len;
         g.segs = ceil_div(n, seg_len);
@@ -842,6 +1007,23 @@ RedGeom red_geometry(int op, i64 outer, i64 n, i64 inner, int itemsize = 4, uint
     g.rps = inner <= kRedThreads ? (int)(kRedThreads / inner) : 1;
     g.coltiles = ceil_div(inner, w);
     const i64 base = g.coltiles * (outer > 0 ? outer : 1);
+    // bulk copies need 16-byte aligned tiles: every outer slice and every row piece
+    const bool stream = addr % 16 == 0 && (inner * itemsize) % 16 == 0 ||
+                        (addr % 16 == 0 && inner <= kRedThreads && (n * inner * itemsize) % 16 == 0);
+    if (stream) {
+        // worth it only if a segment spans enough ring chunks to amortise the pipeline fill
+        const i64 chunk_rows = (i64)(itemsize == 4 ? 16 : 8) * g.rps;
+        const i64 segs = pick_segs(base, kStreamWave, n / (8 * chunk_rows));
+        const i64 seg_len = ceil_div(ceil_div(n, segs), 4) * 4;  // segment starts stay 16-byte aligned
+        if (seg_len >= 8 * chunk_rows || seg_len >= n) {
+            if (n >= 6 * chunk_rows) {
+                g.mode = RED_STREAM;
+                g.seg_len = seg_len;
+                g.segs = ceil_div(n, seg_len);
+                return g;
+            }
+        }
+    }
     const i64 segs = pick_segs(base, kTargetCtas, ceil_div(n, (i64)16 * g.rps));
     g.seg_len = ceil_div(n, segs);
     g.segs = ceil_div(n, g.seg_len);
@@ -887,7 +1069,15 @@ int launch_reduce(const RedArgs &x) {
     }
     const T *a = (const T *)x.a;
     int rc;
-    if (g.mode == RED_ROWS_CTA) {
+    if (g.mode == RED_STREAM) {
+        const i64 gx = x.outer * g.segs;
+        if (gx > 0x7fffffff || g.coltiles > 65535) return fail(NBG_ERR_BAD_ARG, "nbg_reduce: shape too large");
+        if (int rc2 = allow_big_smem(red_stream_kernel<R>, "nbg_reduce stream smem")) return rc2;
+        constexpr size_t kSmem = (size_t)kStreamStages * (sizeof(T) == 4 ? 16 : 8) * kRedThreads * sizeof(T);
+        red_stream_kernel<R><<<dim3((unsigned)gx, (unsigned)g.coltiles), kRedThreads, kSmem, x.stream>>>(
+            a, first, x.n, x.inner, g.segs, g.seg_len, g.w, g.rps, x.index_offset);
+        rc = check_launch("nbg_reduce stream");
+    } else if (g.mode == RED_ROWS_CTA) {
         const i64 ctas = x.outer * g.segs;
         if (ctas > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_reduce: too many rows");
         red_rows_cta_kernel<R><<<(unsigned)ctas, kRedThreads, 0, x.stream>>>(a, first, x.n, g.segs, g.seg_len,
@@ -996,11 +1186,14 @@ int reduce_entry(int op, int dtype, const RedArgs &x) {
 using namespace nbg;
 
 extern "C" size_t nbg_reduce_workspace_bytes(int op, int dtype, int64_t outer, int64_t n, int64_t inner) {
-    (void)dtype;
     if (outer <= 0 || n <= 0 || inner <= 0) return 0;
-    const RedGeom g = red_geometry(op, outer, n, inner);
-    if (g.segs <= 1) return 0;
-    return (size_t)g.segs * kStateWords * (size_t)(outer * inner) * sizeof(u64);
+    const int itemsize = (dtype == NBG_F64 || dtype == NBG_I64) ? 8 : 4;
+    // the kernel choice depends on the input's alignment, unknown here: size for either
+    const i64 s0 = red_geometry(op, outer, n, inner, itemsize, 0).segs;
+    const i64 s1 = red_geometry(op, outer, n, inner, itemsize, 4).segs;
+    const i64 segs = s0 > s1 ? s0 : s1;
+    if (segs <= 1) return 0;
+    return (size_t)segs * kStateWords * (size_t)(outer * inner) * sizeof(u64);
 }
 
 extern "C" int nbg_reduce(int op, int dtype, const void *a, void *out, int64_t outer, int64_t n, int64_t inner,

@@ -78,14 +78,16 @@ def _data(shape, dtype, seed=0, nan_frac=0.15):
 FUNCS = oracle.AGGREGATION_FUNCS
 FLOAT_ONLY = {"nanmean", "nanvar", "nanstd"}
 
-# every kernel and geometry of nbg_reduce.cu: group (G = 1..32), rows_cta with and without
-# segments, unaligned rows, cols (narrow, wide, segmented), thread-per-output
+# every kernel and geometry of nbg_reduce.cu: rows_tile and group (G = 1..32), stream (rows,
+# narrow and wide columns, partial tiles, unaligned tails), rows_cta / cols for unaligned
+# shapes, with and without segments, thread-per-output
 SHAPES = [
     ((1000, 3), -1), ((500, 17), -1), ((300, 100), -1), ((64, 1000), -1), ((40, 4096), -1),
     ((700, 4099), -1), ((3, 70001), -1), ((1, 300007), -1), ((300007,), None),
     ((5000, 6), 0), ((20000, 3), 0), ((3000, 300), 0), ((9, 257, 130), 1), ((40, 12, 33), 1),
     ((50000, 4, 3), 1), ((2, 100000, 2), 1), ((70, 70, 70), (0, 1)), ((70, 70, 70), (1, 2)),
     ((30, 40, 50), (0, 2)), ((30, 40, 50), None),
+    ((5, 40000), -1), ((33, 1024, 512), 1), ((4, 999, 64), 1), ((2, 33333, 8), 1), ((1, 50001, 4), 1),
 ]
 
 
