@@ -10,7 +10,9 @@ arithmetic.  SURVEY.md 8(e):
       the aggregates are all-gathered, each rank folds its predecessors' into a carry and
       then scans its shard with that carry (``carry_in`` of the C ABI);
     - grouped reductions over element shards: per-label partial states are combined --
-      ``all_reduce(SUM)`` for the additive ops, all-gather + ordered merge for the rest.
+      ``all_reduce(SUM)`` for the additive ops, all-gather + ordered merge for the rest;
+    - plain reductions over element shards: 3-word state records per output are
+      all-gathered and folded by ``nbg_reduce_merge``.
 
 `backend` (default: the CUDA kernels) exists so that the exchange logic can be exercised by
 world_size-2 gloo tests on CPU-only machines; the product itself has no CPU path.
@@ -46,6 +48,12 @@ class CudaBackend:
     group_partial = staticmethod(D.run_group_partial)
     group_combine = staticmethod(D.run_group_combine)
     group_finalize = staticmethod(D.run_group_finalize)
+    reduce_merge = staticmethod(D.run_reduce_merge)
+
+    @staticmethod
+    def reduce_partial(name, shard, axes, index_offset):
+        states, view = D.run_reduce_partial(name, shard, axes, index_offset)
+        return states, view.restore
 
 
 def _world(group):
@@ -202,3 +210,29 @@ def group_sharded(name: str, values: torch.Tensor, labels: torch.Tensor, *, num_
         for r in range(1, world):
             backend.group_combine(name, vdtype, total, states[r])
     return backend.group_finalize(name, vdtype, total, ddof)
+
+
+def reduce_sharded(name: str, shard: torch.Tensor, *, axis: int = -1, ddof: int = 1, group=None,
+                   backend=CudaBackend) -> torch.Tensor:
+    """Plain NaN reduction (allnan ... nanmin) of an array sharded along the ONE reduced axis
+    `axis`: `shard` is this rank's contiguous piece, ranks in order (pieces may differ in
+    length).  One exchange: the per-output state records (3 words each) are all-gathered and
+    every rank folds them, so every rank returns the full result.  nanarg* return positions in
+    the unsharded axis.  Raises like the reference on all-NaN / empty slices."""
+    rank, world = _world(group)
+    axis %= shard.dim()
+    vdtype = D.dev.np_dtype_of(shard)
+    lens = [torch.zeros(1, dtype=torch.int64, device=shard.device) for _ in range(world)]
+    dist.all_gather(lens, torch.tensor([shard.shape[axis]], dtype=torch.int64, device=shard.device), group=group)
+    lens = [int(x.item()) for x in lens]
+    n_total = sum(lens)
+    batch = [s for d, s in enumerate(shard.shape) if d != axis]
+    if n_total == 0 and int(np.prod(batch)) > 0 and name in D._REDUCE_EMPTY_ERRORS:
+        raise ValueError(D._REDUCE_EMPTY_ERRORS[name])
+    states, restore = backend.reduce_partial(name, shard, (axis,), sum(lens[:rank]))
+    gathered = [torch.empty_like(states) for _ in range(world)]
+    dist.all_gather(gathered, states.contiguous(), group=group)
+    out = restore(backend.reduce_merge(name, vdtype, torch.stack(gathered), n_total, ddof))
+    if name in ("nanargmax", "nanargmin") and bool((out < 0).any()):
+        raise ValueError("All-NaN slice encountered")
+    return out

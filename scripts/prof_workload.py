@@ -28,6 +28,8 @@ for _ in range(3):
         D.run_move_exp(func, tensors, params["alpha"], 0.0, -1)
     elif family == "fill":
         D.run_fill(func, a, n, -1)
+    elif family == "reduce":
+        D.run_reduce(func, a, (0, 1) if params["axis"] is None else (params["axis"] % 2,))
     else:
         D.run_group(func, a if family == "group" else a.view(1, -1), labels, params["num_labels"], 1)
 torch.cuda.synchronize()

@@ -261,3 +261,88 @@ class OracleBackend:
             else:
                 out = np.where(k0 == 0, np.nan, st[1].astype(np.float64))
         return torch.from_numpy(out.astype(vdtype))
+
+    # ---- plain-reduction state records (include/nbg_b200.h: NBG_REDUCE_STATE_WORDS), float64
+    @staticmethod
+    def reduce_partial(name, shard, axes, index_offset):
+        (axis,) = axes
+        a = np.moveaxis(shard.numpy().astype(np.float64), axis, -1)
+        bshape = a.shape[:-1]
+        flat = a.reshape(-1, a.shape[-1])
+        outs, n = flat.shape
+        st = np.zeros((3, outs), dtype=np.int64)
+        f1, f2 = st[1].view(np.float64), st[2].view(np.float64)
+        for j in range(outs):
+            x = flat[j]
+            ok = ~np.isnan(x)
+            v = x[ok]
+            if name in ("allnan", "anynan", "nancount"):
+                st[0, j] = ok.sum()
+            elif name == "nansum":
+                st[0, j] = np.array([v.sum()]).view(np.int64)[0]
+            elif name == "nanmean":
+                st[0, j] = ok.sum()
+                f1[j] = v.sum()
+            elif name in ("nanvar", "nanstd"):
+                st[0, j] = ok.sum()
+                f1[j] = v.mean() if v.size else 0.0
+                f2[j] = ((v - v.mean()) ** 2).sum() if v.size else 0.0
+            elif name in ("nanmax", "nanmin"):
+                st[0, j] = 1 if v.size else 0
+                f1[j] = (v.max() if name == "nanmax" else v.min()) if v.size else (-np.inf if name == "nanmax" else np.inf)
+            elif name in ("nanargmax", "nanargmin"):
+                if v.size:
+                    i = int(np.nanargmax(x) if name == "nanargmax" else np.nanargmin(x))
+                    st[0, j] = index_offset + i
+                    f1[j] = x[i]
+                else:
+                    st[0, j] = -1
+                    f1[j] = -np.inf if name == "nanargmax" else np.inf
+            else:
+                raise AssertionError(name)
+        return torch.from_numpy(st), (lambda out: out.reshape(bshape))
+
+    @staticmethod
+    def reduce_merge(name, vdtype, states, n_total, ddof):
+        st = states.numpy()
+        parts, _, outs = st.shape
+        w0 = st[:, 0, :]
+        f1, f2 = st[:, 1, :].view(np.float64), st[:, 2, :].view(np.float64)
+        with np.errstate(all="ignore"):
+            if name == "allnan":
+                out = w0.sum(0) == 0
+            elif name == "anynan":
+                out = w0.sum(0) < n_total
+            elif name == "nancount":
+                out = w0.sum(0)
+            elif name == "nansum":
+                out = st[:, 0, :].view(np.float64).sum(0)
+            elif name == "nanmean":
+                c = w0.sum(0)
+                out = np.where(c > 0, f1.sum(0) / c, np.nan)
+            elif name in ("nanvar", "nanstd"):
+                c = np.zeros(outs)
+                mean = np.zeros(outs)
+                m2 = np.zeros(outs)
+                for p in range(parts):  # Chan's update, as in nbg_reduce.cu
+                    cb = w0[p].astype(np.float64)
+                    tot = np.where(c + cb > 0, c + cb, 1.0)
+                    d = f1[p] - mean
+                    m2 = np.where(cb > 0, m2 + f2[p] + d * d * c * cb / tot, m2)
+                    mean = np.where(cb > 0, mean + d * cb / tot, mean)
+                    c = c + cb
+                out = np.where(c > ddof, m2 / (c - ddof), np.nan)
+                if name == "nanstd":
+                    out = np.sqrt(out)
+            elif name in ("nanmax", "nanmin"):
+                ext = (np.max if name == "nanmax" else np.min)(f1, axis=0)
+                out = np.where(w0.sum(0) > 0, ext, np.nan)
+            else:  # nanargmax / nanargmin: best key, smallest index among ties
+                out = np.full(outs, -1, dtype=np.int64)
+                key = np.full(outs, -np.inf if name == "nanargmax" else np.inf)
+                for p in range(parts):
+                    better = (f1[p] > key) if name == "nanargmax" else (f1[p] < key)
+                    take = (w0[p] >= 0) & ((out < 0) | better | ((f1[p] == key) & (w0[p] < out)))
+                    out = np.where(take, w0[p], out)
+                    key = np.where(take, f1[p], key)
+        return torch.from_numpy(np.asarray(out))

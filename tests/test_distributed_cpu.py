@@ -80,6 +80,20 @@ def _worker(rank, world, port, case, uneven, results):
             tv, tl = torch.from_numpy(v[:, lo:hi].copy()), torch.from_numpy(labels[lo:hi].copy())
             for f in oracle.GROUPED_FUNCS:
                 out[f] = nd.group_sharded(f, tv, tl, num_labels=6, ddof=1, index_offset=lo, backend=B).numpy()
+        elif case == "reduce":
+            x = fixture_array((4, 60), seed=8)
+            x[1, :] = np.nan  # all-NaN slice: arg* must raise on every rank
+            x[2, 30:] = np.nan
+            for f in oracle.AGGREGATION_FUNCS:
+                for ax, full in ((-1, x), (0, x.T.copy())):
+                    piece = torch.from_numpy((full[:, lo:hi] if ax == -1 else full[lo:hi]).copy())
+                    try:
+                        out[f"{f}_{ax}"] = nd.reduce_sharded(f, piece, axis=ax, ddof=1, backend=B).numpy()
+                    except ValueError as e:
+                        out[f"{f}_{ax}"] = str(e)
+            y = x[[0, 2, 3]]
+            for f in ("nanargmax", "nanargmin"):
+                out[f"{f}_ok"] = nd.reduce_sharded(f, torch.from_numpy(y[:, lo:hi].copy()), axis=-1, backend=B).numpy()
         results[rank] = (lo, hi, out)
     finally:
         dist.destroy_process_group()
@@ -143,6 +157,29 @@ def test_group_sharded_matches_unsharded(uneven):
         exp = getattr(oracle, f)(v, labels, num_labels=6, axis=-1)
         for r in res:  # every rank holds the full result
             np.testing.assert_allclose(r[2][f], exp, rtol=1e-12, equal_nan=True, err_msg=f)
+
+
+@pytest.mark.parametrize("uneven", [False, True])
+def test_reduce_sharded_matches_unsharded(uneven):
+    res = _run("reduce", uneven)
+    x = fixture_array((4, 60), seed=8)
+    x[1, :] = np.nan
+    x[2, 30:] = np.nan
+    for f in oracle.AGGREGATION_FUNCS:
+        for r in res:  # every rank holds the full result (or raised the reference's error)
+            for ax in (-1, 0):
+                got = r[2][f"{f}_{ax}"]
+                if f in ("nanargmax", "nanargmin"):
+                    assert got == "All-NaN slice encountered"
+                    continue
+                exp = getattr(oracle, f)(x, axis=-1)
+                if exp.dtype.kind == "f":
+                    np.testing.assert_allclose(got, exp, rtol=1e-12, equal_nan=True, err_msg=f)
+                else:
+                    np.testing.assert_array_equal(got, exp, err_msg=f)
+    for f in ("nanargmax", "nanargmin"):
+        for r in res:
+            np.testing.assert_array_equal(r[2][f"{f}_ok"], getattr(oracle, f)(x[[0, 2, 3]], axis=-1))
 
 
 def test_row_slice_covers_everything():

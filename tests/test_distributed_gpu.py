@@ -50,6 +50,8 @@ def _worker(rank, world, port, results):
         tl = torch.from_numpy(labels[lo:hi].copy()).cuda()
         for f in ("group_nanargmax", "group_nanfirst", "group_nanvar", "group_nansum", "group_nanlast"):
             out[f] = nd.group_sharded(f, ta, tl, num_labels=5000, index_offset=lo).cpu().numpy()
+        for f in ("nansum", "nanvar", "nanargmax", "nanmax", "nancount", "anynan"):
+            out[f] = nd.reduce_sharded(f, ta, axis=-1).cpu().numpy()
         results[rank] = out
     finally:
         dist.destroy_process_group()
@@ -73,5 +75,9 @@ def test_sharded_matches_unsharded_nccl():
     labels = np.random.RandomState(5).randint(0, 5000, size=n)
     for f in ("group_nanargmax", "group_nanfirst", "group_nanlast"):
         np.testing.assert_array_equal(results[0][f], getattr(oracle, f)(a, labels, num_labels=5000, axis=-1))
+    for f in ("nanargmax", "nanmax", "nancount", "anynan"):
+        np.testing.assert_array_equal(results[1][f], getattr(oracle, f)(a, axis=-1))
+    for f in ("nansum", "nanvar"):
+        np.testing.assert_allclose(results[0][f], getattr(oracle, f)(a, axis=-1), rtol=1e-12)
     for f in ("group_nanvar", "group_nansum"):
         np.testing.assert_allclose(results[1][f], getattr(oracle, f)(a, labels, num_labels=5000, axis=-1), rtol=1e-11, equal_nan=True)
