@@ -55,6 +55,17 @@ __device__ __forceinline__ T shfl_xor_t(T v, int m) {
     return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
+// NaN -> 0 in the input type.  Written as `nan ? 0 : v` (even through bit casts) the
+// compiler widens first and then selects both halves of the double: two FSELs per element.
+__device__ __forceinline__ float nan_to_zero(float v) {
+    float r;  // inline PTX keeps the select where it is written
+    asm("{ .reg .pred p; setp.nan.f32 p, %1, %1; selp.f32 %0, 0f00000000, %1, p; }" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ double nan_to_zero(double v) { return v != v ? 0.0 : v; }
+__device__ __forceinline__ int32_t nan_to_zero(int32_t v) { return v; }
+__device__ __forceinline__ int64_t nan_to_zero(int64_t v) { return v; }
+
 // 1 / c for a positive count c: hardware float reciprocal + two Newton steps in double
 // (relative error ~1e-29 before the final rounding) instead of the ~25-instruction division.
 __device__ __forceinline__ double fast_rcp(double c) {
@@ -135,7 +146,7 @@ struct RSum {
         Acc s;
     };
     static __device__ __forceinline__ State init() { return {Acc(0)}; }
-    static __device__ __forceinline__ void add(State &s, T v, i64) { s.s += is_nan(v) ? Acc(0) : (Acc)v; }
+    static __device__ __forceinline__ void add(State &s, T v, i64) { s.s += (Acc)nan_to_zero(v); }
     static __device__ __forceinline__ void merge(State &a, const State &b) { a.s += b.s; }
     static __device__ __forceinline__ State shfl(const State &s, int m) { return {shfl_xor_t(s.s, m)}; }
     static __device__ __forceinline__ void pack(const State &s, u64 (&w)[3]) {
@@ -171,18 +182,17 @@ struct RMean {
     };
     static __device__ __forceinline__ State init() { return {0.0, 0}; }
     static __device__ __forceinline__ void add(State &s, T v, i64) {
-        const bool ok = !is_nan(v);
-        s.s += ok ? (double)v : 0.0;
-        s.c += ok ? 1 : 0;
+        s.s += (double)nan_to_zero(v);
+        s.c += is_nan(v) ? 0 : 1;
     }
     template <int B, int V, bool FULL>
     static __device__ __forceinline__ void add_batch(State &s, const T (&v)[B], uint32_t mask, i64, i64) {
         int c = 0;
 #pragma unroll
         for (int b = 0; b < B; b++) {
-            const bool ok = (FULL || ((mask >> b) & 1u)) && !is_nan(v[b]);
-            s.s += ok ? (double)v[b] : 0.0;
-            c += ok ? 1 : 0;
+            const bool in = FULL || ((mask >> b) & 1u);
+            s.s += (double)nan_to_zero(in ? v[b] : T(0));
+            c += (in && !is_nan(v[b])) ? 1 : 0;
         }
         s.c += c;
     }
@@ -641,16 +651,17 @@ __global__ void __launch_bounds__(kRedThreads, 6) red_rows_tile_kernel(const typ
         State st = R::init();
         // f(value, element index) over this lane's elements g, g + G, ...
         auto lane_elements = [&](auto &&f) {
-            if (rot) {
-#pragma unroll 4
-                for (int e = g; e < nn; e += G) {
-                    int pos = e + rot;
-                    pos = pos >= n ? pos - n : pos;
+            if (rot) {  // G == 1: all n elements, starting at `rot`, wrapping once
+                int pos = rot;
+#pragma unroll 2
+                for (int e = 0; e < nn; e++) {
                     f(row[pos], pos);
+                    pos = pos + 1 == n ? 0 : pos + 1;
                 }
             } else {
+                const T *q = row + g;
 #pragma unroll 4
-                for (int e = g; e < nn; e += G) f(row[e], e);
+                for (int e = g; e < nn; e += G, q += G) f(*q, e);
             }
         };
         if constexpr (R::TWO_PASS) {
@@ -659,9 +670,8 @@ __global__ void __launch_bounds__(kRedThreads, 6) red_rows_tile_kernel(const typ
             double sum = 0.0;
             int c = 0;
             lane_elements([&](T v, int) {
-                const bool ok = !is_nan(v);
-                sum += ok ? (double)v : 0.0;
-                c += ok ? 1 : 0;
+                sum += (double)nan_to_zero(v);
+                c += is_nan(v) ? 0 : 1;
             });
             for (int m = G >> 1; m >= 1; m >>= 1) {
                 sum += shfl_xor_t(sum, m);
