@@ -69,7 +69,9 @@ __device__ __forceinline__ int64_t nan_to_zero(int64_t v) { return v; }
 // 1 / c for a positive count c: hardware float reciprocal + two Newton steps in double
 // (relative error ~1e-29 before the final rounding) instead of the ~25-instruction division.
 __device__ __forceinline__ double fast_rcp(double c) {
-    double y = (double)__frcp_rn((float)c);
+    float y0;  // MUFU.RCP only: the correctly rounded __frcp_rn drags in a slow-path call
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)c));
+    double y = (double)y0;
     double e = fma(-c, y, 1.0);
     y = fma(y, e, y);
     e = fma(-c, y, 1.0);
@@ -253,26 +255,63 @@ struct RVar {
     template <int B, int V, bool FULL>
     static __device__ __forceinline__ void add_batch(State &s, const T (&v)[B], uint32_t mask, i64, i64) {
         uint32_t okm = 0;
-        T sum = T(0);
+        T sum0 = T(0), sum1 = T(0);  // two chains per pass: half the dependent latency
 #pragma unroll
         for (int b = 0; b < B; b++) {
             const bool ok = (FULL || ((mask >> b) & 1u)) && !is_nan(v[b]);
             okm |= (ok ? 1u : 0u) << b;
-            sum += ok ? v[b] : T(0);
+            if (b & 1)
+                sum1 += ok ? v[b] : T(0);
+            else
+                sum0 += ok ? v[b] : T(0);
         }
         const int cb = __popc(okm);
         if (cb == 0) return;
         const double rb = fast_rcp((double)cb);
-        T k = sum * (T)rb;
-        if (!(fabs((double)k) <= 1.7e308)) k = T(0);  // overflowed / infinite sum: any finite centre
+        T k = (sum0 + sum1) * (T)rb;
+        // overflowed / infinite sum: any finite centre will do
+        if constexpr (sizeof(T) == 4) {
+            if (!(fabsf((float)k) <= 3.0e38f)) k = T(0);
+        } else {
+            if (!(fabs((double)k) <= 1.7e308)) k = T(0);
+        }
         const double kd = (double)k;
-        double s1 = 0.0, s2 = 0.0;
+        double s1, s2;
+        if constexpr (sizeof(T) == 4) {
+            // float32 data: deviations from the batch centre in float32 (x - k is exact
+            // whenever x and k are within a factor of two -- Sterbenz -- and rounds at 6e-8
+            // otherwise); 16 of them are summed in float32 before joining the double state.
+            // Relative error of the variance <~ 1e-6, inside the float32 result's tolerance.
+            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
-        for (int b = 0; b < B; b++) {
-            const T x = ((okm >> b) & 1u) ? v[b] : k;
-            const double d = (double)x - kd;
-            s1 += d;
-            s2 = fma(d, d, s2);
+            for (int b = 0; b < B; b++) {
+                const float d = (((okm >> b) & 1u) ? v[b] : k) - k;
+                if (b & 1) {
+                    s1b += d;
+                    s2b = fmaf(d, d, s2b);
+                } else {
+                    s1a += d;
+                    s2a = fmaf(d, d, s2a);
+                }
+            }
+            s1 = (double)(s1a + s1b);
+            s2 = (double)s2a + (double)s2b;
+        } else {
+            double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const T x = ((okm >> b) & 1u) ? v[b] : k;
+                const double d = (double)x - kd;
+                if (b & 1) {
+                    s1b += d;
+                    s2b = fma(d, d, s2b);
+                } else {
+                    s1a += d;
+                    s2a = fma(d, d, s2a);
+                }
+            }
+            s1 = s1a + s1b;
+            s2 = s2a + s2b;
         }
         State bs;
         bs.c = cb;
@@ -670,8 +709,10 @@ __global__ void __launch_bounds__(kRedThreads, 6) red_rows_tile_kernel(const typ
             double sum = 0.0;
             int c = 0;
             lane_elements([&](T v, int) {
-                sum += (double)nan_to_zero(v);
-                c += is_nan(v) ? 0 : 1;
+                if (v == v) {
+                    sum += (double)v;
+                    c += 1;
+                }
             });
             for (int m = G >> 1; m >= 1; m >>= 1) {
                 sum += shfl_xor_t(sum, m);
@@ -680,13 +721,27 @@ __global__ void __launch_bounds__(kRedThreads, 6) red_rows_tile_kernel(const typ
             const double mean = c > 0 ? sum * fast_rcp((double)c) : 0.0;
             double m2 = 0.0;
             lane_elements([&](T v, int) {
-                const double d = is_nan(v) ? 0.0 : (double)v - mean;
-                m2 = fma(d, d, m2);
+                const double d = (double)v - mean;
+                if (v == v) m2 = fma(d, d, m2);
             });
             for (int m = G >> 1; m >= 1; m >>= 1) m2 += shfl_xor_t(m2, m);
             st.c = c;
             st.mean = mean;
             st.m2 = m2;
+        } else if constexpr (R::ORDERED) {
+            // nanarg*: 32-bit position inside the row while scanning, widened once
+            using K = decltype(st.key);
+            K key = st.key;
+            int at = -1;
+            lane_elements([&](T v, int e) {
+                const K k = (K)v;
+                const bool take = R::better(k, key) || (at < 0 && k == k);
+                key = take ? k : key;
+                at = take ? e : at;
+            });
+            st.key = key;
+            st.idx = at < 0 ? -1 : index_offset + at;
+            for (int m = G >> 1; m >= 1; m >>= 1) R::merge(st, R::shfl(st, m));
         } else {
             lane_elements([&](T v, int e) { R::add(st, v, index_offset + e); });
             for (int m = G >> 1; m >= 1; m >>= 1) R::merge(st, R::shfl(st, m));

@@ -15,12 +15,15 @@ out = [f"# profiles — round {tag}", "",
        "bandwidth (6447.8 GB/s, MEASURED_PEAKS.json).  `e2e` = public numpy API with pinned host buffers",
        "(H2D + kernels + D2H inside the timed region; row blocks are pipelined on three streams).",
        "`cpu` = oracle port (C, OpenMP over rows) on the box's 16 host cores; 1-D inputs use one core,",
-       "like the reference's gufunc.", "",
+       "like the reference's gufunc.  The `red_*` rows (plain NaN reductions, SURVEY 8(f) rank 1) only READ",
+       "(8 bytes written per output), so they can exceed the measured COPY bandwidth used as `peak` (half",
+       "reads, half writes): `roofline` above 1.0 means faster than a device-to-device copy moves the same",
+       "bytes; ncu shows ~90 % of the DRAM peak for `nansum` float32.", "",
        "| workload | shape | Gel/s | ms/step | roofline (of measured) | e2e Gel/s | cpu Gel/s (cores) | kernels/step |",
        "|---|---|---:|---:|---:|---:|---:|---:|"]
 for d in rows:
     c = d["config"]
-    out.append(f"| {c['workload']} ({c['func']}, {d['dtype']}) | {c['shape'][0]}x{c['shape'][1]} | {d['value']/1e9:.1f} | {d['ms_per_step']:.3f} | "
+    out.append(f"| {c['workload']} ({c['func']}, {d['dtype']}) | {c['shape'][0]}x{c['shape'][1]}{' axis=' + str(c['axis']) if 'axis' in c else ''} | {d['value']/1e9:.1f} | {d['ms_per_step']:.3f} | "
                f"{d['roofline']['frac']:.3f} | {d['e2e']['value']/1e9:.2f} | {d['cpu_baseline']['value']/1e9:.2f} ({d['cpu_baseline']['cores']}) | {d['gpu_launches']/d['steps']:.0f} |")
 out += ["", "Files:", "",
         "* `*_bench_all*.jsonl` — the raw bench.py JSON lines behind the table.",
