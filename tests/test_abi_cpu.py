@@ -56,7 +56,8 @@ def test_product_never_imports_oracle():
 
 def test_function_census_and_metadata():
     assert len(nb.MOVE_FUNCS) == 6 and len(nb.MOVE_EXP_FUNCS) == 7
-    assert len(nb.GROUPED_FUNCS) == 15 and len(nb.OTHER_FUNCS) == 2
+    assert len(nb.GROUPED_FUNCS) == 15 and len(nb.OTHER_FUNCS) == 2 and len(nb.AGGREGATION_FUNCS) == 11
+    assert repr(nb.nansum) == "numbagg.nansum" and nb.nanvar.supports_ddof and not nb.nansum.supports_ddof
     assert repr(nb.move_mean) == "numbagg.move_mean"  # numbagg/decorators.py:119-120
     assert nb.group_nanvar.supports_ddof and not nb.group_nanvar.supports_ints and not nb.group_nanvar.supports_bool
     assert nb.group_nanmean.supports_bool and not nb.group_nanmean.supports_ints
@@ -159,15 +160,33 @@ def test_c_abi_rejects_bad_arguments_without_a_device():
     assert L.nbg_group_record_words(_lib.GROUP_OPS["group_nanvar"]) == 4
     assert L.nbg_group_record_words(_lib.GROUP_OPS["group_nansum"]) == 1
     assert L.nbg_group_workspace_bytes(1, _lib.NBG_F32, 10, 1000, 7) >= 10 * 7 * 8
+    # plain reductions
+    R = _lib.REDUCE_OPS
+    assert L.nbg_reduce(99, _lib.NBG_F64, dummy, dummy, 1, 10, 1, 1, None, 0, None) == -2
+    assert L.nbg_reduce(R["nansum"], 7, dummy, dummy, 1, 10, 1, 1, None, 0, None) == -1
+    assert L.nbg_reduce(R["nanmean"], _lib.NBG_I64, dummy, dummy, 1, 10, 1, 1, None, 0, None) == -1 and "float" in err()
+    assert L.nbg_reduce(R["nansum"], _lib.NBG_F64, dummy, None, 1, 10, 1, 1, None, 0, None) == -3
+    assert L.nbg_reduce(R["nansum"], _lib.NBG_F64, dummy, dummy, -1, 10, 1, 1, None, 0, None) == -3
+    # one long row is cut into segments: the partial states need the advertised workspace
+    need = L.nbg_reduce_workspace_bytes(R["nansum"], _lib.NBG_F64, 1, 10_000_000, 1)
+    assert need >= 3 * 8 * 2
+    assert L.nbg_reduce(R["nansum"], _lib.NBG_F64, dummy, dummy, 1, 10_000_000, 1, 1, dummy, 8, None) == -6 and "workspace" in err()
+    assert L.nbg_reduce_workspace_bytes(R["nansum"], _lib.NBG_F64, 100_000, 100, 1) == 0  # one CTA pass, no partials
+    before = L.nbg_launch_count()
+    assert L.nbg_reduce(R["nansum"], _lib.NBG_F64, None, None, 0, 10, 1, 1, None, 0, None) == 0  # no outputs
+    assert L.nbg_reduce_merge(R["nanvar"], _lib.NBG_F64, None, 0, 0, None, 0, 1, None) == 0
+    assert L.nbg_launch_count() == before
 
 
 def test_c_abi_header_constants_match_python_binding():
     text = open(os.path.join(ROOT, "include", "nbg_b200.h")).read()
     for name, value in (("NBG_EXP_STATE", _lib.NBG_EXP_STATE), ("NBG_FILL_STATE", _lib.NBG_FILL_STATE),
-                        ("NBG_GROUP_WS_CHANNELS", _lib.NBG_GROUP_WS_CHANNELS), ("NBG_ABI_VERSION", 1)):
+                        ("NBG_GROUP_WS_CHANNELS", _lib.NBG_GROUP_WS_CHANNELS), ("NBG_ABI_VERSION", 1),
+                        ("NBG_REDUCE_STATE_WORDS", _lib.NBG_REDUCE_STATE_WORDS)):
         m = re.search(rf"#define\s+{name}\s+(\d+)", text)
         assert m and int(m.group(1)) == value, name
-    for table, prefix in ((_lib.MOVE_OPS, "NBG_"), (_lib.EXP_OPS, "NBG_"), (_lib.GROUP_OPS, "NBG_")):
+    for table, prefix in ((_lib.MOVE_OPS, "NBG_"), (_lib.EXP_OPS, "NBG_"), (_lib.GROUP_OPS, "NBG_"),
+                          (_lib.REDUCE_OPS, "NBG_RED_")):
         for fname, code in table.items():
             enum = prefix + fname.upper().replace("MOVE_EXP_", "EXP_")
             m = re.search(rf"\b{enum}\s*=\s*(\d+)", text)

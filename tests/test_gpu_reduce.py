@@ -239,3 +239,27 @@ def test_full_size_properties():
     am = nb.nanargmax(t, axis=-1)
     assert torch.equal(t.gather(1, am[:, None])[:, 0], nb.nanmax(t, axis=-1))
     assert torch.equal(nb.nanmax(t), nb.nanmax(nb.nanmax(t, axis=0)))
+
+
+def test_billion_element_consistency():
+    """10^9 float32 elements (BASELINE config-3 scale): the one-row segmented path, the
+    many-rows path and the column path must agree with each other and with the construction."""
+    import torch
+
+    import numbagg_b200 as nb
+
+    g = torch.Generator(device="cuda").manual_seed(7)
+    t = torch.rand((1000, 1_000_000), generator=g, device="cuda", dtype=torch.float32)
+    t[t < 0.05] = float("nan")
+    n_valid = int(torch.count_nonzero(~torch.isnan(t)))
+    assert int(nb.nancount(t)) == n_valid
+    assert int(nb.nancount(t, axis=-1).sum()) == n_valid and int(nb.nancount(t, axis=0).sum()) == n_valid
+    total = float(nb.nansum(t.view(-1)))
+    by_rows = float(nb.nansum(t, axis=-1).double().sum())
+    by_cols = float(nb.nansum(t, axis=0).double().sum())
+    assert abs(total - by_rows) <= 1e-6 * abs(by_rows) and abs(by_cols - by_rows) <= 1e-6 * abs(by_rows)
+    flat_arg = int(nb.nanargmax(t.view(-1)))
+    assert float(t.view(-1)[flat_arg]) == float(nb.nanmax(t))
+    assert flat_arg == int(torch.nonzero(t.view(-1) == nb.nanmax(t))[0])  # the FIRST maximum
+    v_all = float(nb.nanvar(t.view(-1)))
+    assert abs(v_all - 1.0 / 12.0 * (0.95**2) - 0.0) < 0.01  # uniform(0.05, 1): var = 0.95^2 / 12
