@@ -523,14 +523,15 @@ static size_t group_state_bytes(int op, int64_t rows, int64_t num_labels) {
 }
 extern "C" int nbg_group_record_words(int op) { return nbg::ws_layout(op).words; }
 // scratch for the shared-label plan: 4 bytes per column + one header per (smallest) tile
-static size_t group_scratch_bytes(int64_t n) {
-    // widest tile is 1024 columns (a short row still needs one whole tile), narrowest 128
-    return (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * nbg::kRbHdr * 4 + 1024;
+static size_t group_scratch_bytes(int64_t n, int64_t rows) {
+    // widest tile is 1536 columns (a short row still needs one whole tile), narrowest 128;
+    // plus one lock word per group of 8 rows
+    return (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * nbg::kRbHdr * 4 + (size_t)(rows / 8 + 2) * 4 + 2048;
 }
 
 extern "C" size_t nbg_group_workspace_bytes(int op, int, int64_t rows, int64_t n, int64_t num_labels) {
     if (rows <= 0 || num_labels <= 0) return 0;
-    return group_state_bytes(op, rows, num_labels) + group_scratch_bytes(n > 0 ? n : 0);
+    return group_state_bytes(op, rows, num_labels) + group_scratch_bytes(n > 0 ? n : 0, rows > 0 ? rows : 0);
 }
 
 static void *align256(void *p) { return reinterpret_cast<void *>(((uintptr_t)p + 255) & ~(uintptr_t)255); }

@@ -309,23 +309,22 @@ template <typename V>
 struct RbBin<V, RB_MAX> : RbExtreme<V, true> {};
 template <typename V>
 struct RbBin<V, RB_MIN> : RbExtreme<V, false> {};
+// (value, position) bins: two words, `idx < 0` = nothing taken yet (idx is the column within
+// this shard: < 2^31 on this path, so it has the width of the value).
 template <typename V, bool IS_MAX>
-struct alignas(4 * sizeof(V)) RbArgExtreme {  // grouped.py:54-92
+struct alignas(2 * sizeof(V)) RbArgExtreme {  // grouped.py:54-92
     V best;
-    typename RbCounter<V>::type idx, has, pad;
+    typename RbCounter<V>::type idx;
     __device__ __forceinline__ void zero() {
         best = (V)0;
-        idx = 0;
-        has = 0;
-        pad = 0;
+        idx = -1;
     }
     template <typename I>
     __device__ __forceinline__ void add(V v, bool ok, I gi) {
         const bool better = IS_MAX ? ((double)v > (double)best) : ((double)v < (double)best);
-        const bool take = ok && (!has || better);
+        const bool take = ok && (idx < 0 || better);
         best = take ? v : best;
         idx = take ? (typename RbCounter<V>::type)gi : idx;
-        has |= ok ? 1 : 0;
     }
 };
 template <typename V>
@@ -333,21 +332,18 @@ struct RbBin<V, RB_ARGMAX> : RbArgExtreme<V, true> {};
 template <typename V>
 struct RbBin<V, RB_ARGMIN> : RbArgExtreme<V, false> {};
 template <typename V, bool FIRST>
-struct alignas(4 * sizeof(V)) RbEdge {  // grouped.py:95-121: first / last valid value (+ its index)
+struct alignas(2 * sizeof(V)) RbEdge {  // grouped.py:95-121: first / last valid value (+ its index)
     V val;
-    typename RbCounter<V>::type idx, has, pad;
+    typename RbCounter<V>::type idx;
     __device__ __forceinline__ void zero() {
         val = (V)0;
-        idx = 0;
-        has = 0;
-        pad = 0;
+        idx = -1;
     }
     template <typename I>
     __device__ __forceinline__ void add(V v, bool ok, I gi) {
-        const bool take = FIRST ? (ok && !has) : ok;
+        const bool take = FIRST ? (ok && idx < 0) : ok;
         val = take ? v : val;
         idx = take ? (typename RbCounter<V>::type)gi : idx;
-        has |= ok ? 1 : 0;
     }
 };
 template <typename V>
@@ -383,6 +379,7 @@ struct RbParams {
     int priv;  // sub-warp-private bins (few labels)
     int W;     // nominal label-range width of the slot permutation (0: identity)
     int64_t index_offset;  // flat index of column 0 of this shard (arg* / first / last)
+    int *locks;            // one per row group: serialises the record merges of (value, index) ops across column segments
 };
 
 template <typename V>
@@ -511,6 +508,18 @@ __global__ void __launch_bounds__(kRbThreads) group_rowbins_kernel(RbParams p) {
     Acc *c1p = reinterpret_cast<Acc *>(p.ws_ch[1]);
     long long *c2p = reinterpret_cast<long long *>(p.ws_ch[2]);
     const bool atomic = p.nseg > 1;
+    // (value, index) records are two words that must change together: the column segments of
+    // a row group take turns (spin lock per group; the holder is a resident CTA that needs
+    // nothing from the waiters, so this cannot deadlock).  The merge itself is order-free.
+    constexpr bool kPair = CLS == RB_ARGMAX || CLS == RB_ARGMIN || CLS == RB_FIRST || CLS == RB_LAST;
+    const bool locked = kPair && atomic;
+    if (locked) {
+        if (tid == 0) {
+            while (atomicCAS(&p.locks[g], 0, 1) != 0) __nanosleep(100);
+            __threadfence();
+        }
+        __syncthreads();
+    }
     for (int idx = tid; idx < K * kRbRows; idx += kRbThreads) {
         const int rr = idx / K, k = idx - rr * K;  // consecutive threads -> consecutive labels
         if (rr >= nrows) continue;
@@ -526,6 +535,11 @@ __global__ void __launch_bounds__(kRbThreads) group_rowbins_kernel(RbParams p) {
         } else {
             RbFlush<V, CLS>::flush(b, c0p + o, c1p + o, p.index_offset, atomic);
         }
+    }
+    if (locked) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicExch(&p.locks[g], 0);
     }
 }
 
@@ -628,16 +642,17 @@ template <typename V, int CLS>
 struct RbFlushArg {
     template <typename A>
     __device__ static __forceinline__ void flush(const RbBin<V, CLS> &b, A *c0, A *c1, int64_t off, bool) {
-        if (!b.has) return;
+        if (b.idx < 0) return;
         unsigned long long k = order_key((double)b.best);
         if (CLS == RB_ARGMIN) k = ~k;
         unsigned long long *w = reinterpret_cast<unsigned long long *>(c0);
         long long *wi = reinterpret_cast<long long *>(c1);
         const long long gi = (long long)b.idx + off;
-        if (k > *w) {
+        const unsigned long long cur = __ldcg(w);  // past L1: another SM's segment may have merged meanwhile
+        if (k > cur) {
             *w = k;
             *wi = gi;
-        } else if (k == *w && gi < *wi) {
+        } else if (k == cur && gi < __ldcg(wi)) {
             *wi = gi;
         }
     }
@@ -650,11 +665,12 @@ template <typename V, int CLS>
 struct RbFlushEdge {
     template <typename A>
     __device__ static __forceinline__ void flush(const RbBin<V, CLS> &b, A *c0, A *c1, int64_t off, bool) {
-        if (!b.has) return;
+        if (b.idx < 0) return;
         unsigned long long *w = reinterpret_cast<unsigned long long *>(c0);
         long long *wi = reinterpret_cast<long long *>(c1);
         const long long gi = (long long)b.idx + off;
-        const bool take = CLS == RB_FIRST ? (gi < *wi) : (gi > *wi);
+        const long long cur = __ldcg(wi);  // past L1, see RbFlushArg
+        const bool take = CLS == RB_FIRST ? (gi < cur) : (gi > cur);
         if (take) {
             unsigned long long bits;
             if (sizeof(V) == 8) bits = *reinterpret_cast<const unsigned long long *>(&b.val);
@@ -723,7 +739,7 @@ inline int rb_class_of(int op) {
 struct RbGeometry {
     bool ok;
     int C, priv, ntiles, nseg, tiles_per_seg;
-    size_t smem, plan_bytes;
+    size_t smem, plan_bytes, lock_bytes;
 };
 
 template <typename V, int CLS>
@@ -733,18 +749,28 @@ static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
     if (K <= 0 || K > 65535 || n <= 0 || n >= ((int64_t)1 << 31) || (n % PER16) != 0 || rows < 1) return g;
     const int words = (int)(sizeof(RbBin<V, CLS>) / sizeof(V));
     g.priv = (CLS <= RB_VAR && K * words <= 32) ? 1 : 0;
-    int candidates[3] = {sizeof(V) == 4 ? 1024 : 512, sizeof(V) == 4 ? 512 : 256, sizeof(V) == 4 ? 256 : 128};
-    if (const char *e = getenv("NBG_RB_C")) candidates[0] = candidates[1] = candidates[2] = atoi(e);  // tuning hook
-    // prefer two CTAs per SM (<= ~110 KB), else whatever fits
-    for (int pass = 0; pass < 2 && !g.ok; pass++) {
-        for (int c = 0; c < 3; c++) {
-            const size_t s = rb_smem_bytes<V, CLS>((int)K, candidates[c], g.priv);
-            if (s <= (pass == 0 ? (size_t)110 * 1024 : kMaxSmem)) {
-                g.C = candidates[c];
-                g.smem = s;
-                g.ok = true;
-                break;
-            }
+    // Tile width C (columns per stage) and CTAs per SM, in measured order of preference on
+    // config 2 (group_nansum / nanmean / nanstd float32, 10^4 x 10^6, 1000 labels):
+    // wide tiles amortise the per-tile barrier and plan header, two CTAs per SM hide the
+    // other one's pipeline bubbles -- 4 KB rows x 2 CTAs (61 %) > 6 KB x 1 (56 % sum, 46 %
+    // mean) > 2 KB x 2 (51 %, 41 %) > 4 KB x 1 (38 % mean) > ...
+    const int kb = 1024 / (int)sizeof(V);  // elements per KB of row
+    struct Cand {
+        int C;
+        bool two;
+    };
+    Cand order[7] = {{4 * kb, true}, {6 * kb, false}, {2 * kb, true}, {4 * kb, false},
+                     {2 * kb, false}, {kb, true}, {kb, false}};
+    if (const char *e = getenv("NBG_RB_C")) {  // tuning hook
+        for (auto &c : order) c.C = atoi(e);
+    }
+    for (const auto &c : order) {
+        const size_t s = rb_smem_bytes<V, CLS>((int)K, c.C, g.priv);
+        if (s <= (c.two ? (size_t)110 * 1024 : kMaxSmem)) {
+            g.C = c.C;
+            g.smem = s;
+            g.ok = true;
+            break;
         }
     }
     if (!g.ok) return g;
@@ -755,14 +781,13 @@ static RbGeometry rb_geometry(int64_t rows, int64_t n, int64_t K) {
     // partial bins with atomics.
     const int64_t slots = (int64_t)kNumSMs * 2;
     int64_t nseg = groups >= 4 * slots ? 1 : (8 * slots + groups - 1) / groups;
-    // (value, index) states are merged by the owner only: no column segments for those
-    if (CLS == RB_ARGMAX || CLS == RB_ARGMIN || CLS == RB_FIRST || CLS == RB_LAST) nseg = 1;
     if (const char *e = getenv("NBG_RB_NSEG")) nseg = atoi(e);  // tuning hook
     if (nseg > g.ntiles) nseg = g.ntiles;
     if (nseg < 1) nseg = 1;
     g.tiles_per_seg = (int)((g.ntiles + nseg - 1) / nseg);
     g.nseg = (g.ntiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
     g.plan_bytes = (size_t)g.ntiles * (kRbHdr + g.C) * 4 + 256;
+    g.lock_bytes = (size_t)(groups + 1) * sizeof(int);
     return g;
 }
 
@@ -771,7 +796,7 @@ static int rb_launch(const V *values, const L *labels, void *ws_ch[3], int64_t w
                      int64_t rows, int64_t n, int64_t K, int64_t index_offset, cudaStream_t stream, bool *handled) {
     *handled = false;
     const RbGeometry g = rb_geometry<V, CLS>(rows, n, K);
-    if (!g.ok || scratch == nullptr || scratch_bytes < g.plan_bytes) return NBG_OK;
+    if (!g.ok || scratch == nullptr || scratch_bytes < g.plan_bytes + g.lock_bytes + 256) return NBG_OK;
     if (((uintptr_t)values & 15) != 0) return NBG_OK;
     uint32_t *plan = reinterpret_cast<uint32_t *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
     const size_t plan_smem = (size_t)(2 * K + 1) * 4 + (size_t)2 * g.C * 4 + 16;
@@ -789,6 +814,12 @@ static int rb_launch(const V *values, const L *labels, void *ws_ch[3], int64_t w
     p.ws_stride = ws_stride;
     p.index_offset = index_offset;
     p.W = W;
+    p.locks = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(plan) + ((g.plan_bytes + 15) & ~(size_t)15));
+    constexpr bool kPair = CLS == RB_ARGMAX || CLS == RB_ARGMIN || CLS == RB_FIRST || CLS == RB_LAST;
+    if (kPair && g.nseg > 1) {
+        rc = check_cuda(cudaMemsetAsync(p.locks, 0, g.lock_bytes, stream), "nbg_group(rowbins): lock memset");
+        if (rc) return rc;
+    }
     p.rows = rows, p.n = n, p.K = (int)K, p.C = g.C;
     p.ntiles = g.ntiles, p.tiles_per_seg = g.tiles_per_seg, p.nseg = g.nseg, p.priv = g.priv;
     const int64_t groups = (rows + kRbRows - 1) / kRbRows;
