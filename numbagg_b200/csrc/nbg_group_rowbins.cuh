@@ -15,8 +15,9 @@
 //     update is a plain load/add/store, and every bin receives its elements in ascending
 //     column order -- the reference's own summation order (grouped.py:31-40), which makes the
 //     float32 results bit-identical to numbagg's when a CTA covers whole rows.
-//   Few labels (K * words <= 32): ranges are cut evenly instead and each sub-warp gets
-//     private bins that are summed at the end.
+//   Few labels (K * words <= 32, additive ops): ranges are cut evenly instead and each
+//     sub-warp gets private bins that are summed at the end.  (Tried for the (value, index)
+//     ops too: slower -- the private bins of a warp's four sub-warps share banks.)
 // Bins are V-typed (accumulation in the OUTPUT dtype, like the reference) and are flushed
 // into the common 8-byte workspace at the end (plain stores for one segment per row,
 // atomics otherwise).

@@ -258,6 +258,20 @@ def test_group_shared_labels_vs_oracle(nb, dtype, K):
         _group_check(nb, f, vv, labels, num_labels=K, axis=-1)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("rows,n,K", [(1, 400_000, 12), (3, 300_000, 7), (20, 200_000, 1000), (1, 250_000, 300)])
+def test_group_value_index_ops_across_column_segments(nb, dtype, rows, n, K):
+    # few rows x long core axis: the rows are cut into column segments whose (value, index)
+    # bins merge under the row-group lock; leading NaN runs make later segments win
+    rs = np.random.RandomState(rows + K)
+    v = np.round(fixture_array((rows, n), dtype=dtype, seed=K, nan_frac=0.3) * 50).astype(dtype)  # many ties
+    v[:, : n // 3] = np.nan
+    v[0, n // 3 : n // 2][::2] = np.nan
+    labels = rs.randint(-1, K, size=n)
+    for f in ("group_nanargmax", "group_nanargmin", "group_nanfirst", "group_nanlast", "group_nanmax", "group_nanmin"):
+        _group_check(nb, f, v, labels, num_labels=K, axis=-1)
+
+
 def test_group_rowbins_is_bit_exact_with_whole_rows(nb):
     # >= 4 waves of 8-row groups => one CTA per row group walks whole rows in column order:
     # float32 sums must then be IDENTICAL to the sequential reference, not just close
