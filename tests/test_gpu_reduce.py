@@ -263,3 +263,49 @@ def test_billion_element_consistency():
     assert flat_arg == int(torch.nonzero(t.view(-1) == nb.nanmax(t))[0])  # the FIRST maximum
     v_all = float(nb.nanvar(t.view(-1)))
     assert abs(v_all - 1.0 / 12.0 * (0.95**2) - 0.0) < 0.01  # uniform(0.05, 1): var = 0.95^2 / 12
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_axes_and_layouts(seed):
+    """Randomised sweep over the geometry decisions of nbg_reduce.cu (kernel choice, segment
+    counts, alignment fallbacks, tile widths at their thresholds)."""
+    import numbagg_b200 as nb
+
+    rs = np.random.RandomState(1000 + seed)
+    edge = [1, 2, 3, 4, 7, 8, 16, 17, 31, 32, 33, 63, 64, 65, 100, 255, 256, 257, 511, 512, 1000, 1023, 1024, 1025,
+            2047, 2048, 4095, 4096, 4097, 8191, 16384, 16385, 40000]
+    for _ in range(40):
+        nd = rs.randint(1, 4)
+        budget = 400_000
+        shape = []
+        for _d in range(nd):
+            s = int(edge[rs.randint(len(edge))])
+            s = max(1, min(s, budget))
+            shape.append(s)
+            budget = max(1, budget // s)
+        shape = tuple(shape)
+        dtype = [np.float64, np.float32, np.int32, np.int64][rs.randint(4)]
+        a = _data(shape, dtype, seed=rs.randint(1 << 30), nan_frac=[0.0, 0.1, 0.6][rs.randint(3)])
+        if rs.rand() < 0.3 and nd > 1:
+            perm = rs.permutation(nd)
+            a = np.ascontiguousarray(a.transpose(perm)).transpose(np.argsort(perm))
+        if rs.rand() < 0.2 and a.shape[-1] > 2:
+            a = a[..., 1:]  # unaligned, non-contiguous view
+        k = rs.randint(0, nd + 1)
+        axis = None if k == 0 else tuple(int(x) for x in rs.choice(nd, size=k, replace=False))
+        if axis is not None and len(axis) == 1:
+            axis = axis[0]
+        for func in FUNCS:
+            if np.dtype(dtype).kind != "f" and func in FLOAT_ONLY:
+                continue
+            try:
+                exp = getattr(oracle, func)(a, axis=axis)
+            except ValueError as e:
+                with pytest.raises(ValueError, match=str(e)[:20]):
+                    getattr(nb, func)(a, axis=axis)
+                continue
+            got = getattr(nb, func)(a, axis=axis)
+            try:
+                check(func, a, got, exp, dict(axis=axis))
+            except AssertionError as err:
+                raise AssertionError(f"{func} shape={a.shape} strides={a.strides} dtype={a.dtype} axis={axis}: {err}")
