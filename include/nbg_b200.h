@@ -230,6 +230,19 @@ int nbg_reduce_partial(int op, int dtype, const void *a, void *states, int64_t o
 int nbg_reduce_merge(int op, int dtype, const void *states, int64_t parts, int64_t outs,
                      void *out, int64_t n_total, int64_t ddof, void *stream);
 
+/*
+ * nanquantile / nanmedian (numbagg/funcs.py:245-291, 332-335 behind
+ * ndquantile, numbagg/decorators.py:821-901).  `a` is a C-contiguous (rows, n) float64
+ * matrix (the dispatcher's move_axes puts the reduced axes last; other dtypes are cast to
+ * float64 like NumPy does for the reference's only loop), `q` holds m <= 16 quantiles in
+ * [0, 1] (NaN allowed -> NaN result) ON THE DEVICE, `out` is (rows, m) float64.  NaN = missing
+ * value; a row without data gives NaN.  Results are bit-identical to the reference (exact
+ * selection + its interpolation arithmetic).  Rows longer than 4096 elements need a workspace.
+ */
+size_t nbg_quantile_workspace_bytes(int64_t rows, int64_t n, int64_t m);
+int nbg_quantile(const void *a, const void *q, void *out, int64_t rows, int64_t n, int64_t m,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

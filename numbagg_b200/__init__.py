@@ -19,7 +19,9 @@ from .funcs import (
     nancount,
     nanmax,
     nanmean,
+    nanmedian,
     nanmin,
+    nanquantile,
     nanstd,
     nansum,
     nanvar,
@@ -66,11 +68,12 @@ OTHER_FUNCS = [bfill, ffill]
 AGGREGATION_FUNCS = [
     allnan, anynan, nancount, nansum, nanmean, nanvar, nanstd, nanargmax, nanargmin, nanmax, nanmin,
 ]
+QUANTILE_FUNCS = [nanquantile, nanmedian]
 
 __version__ = "0.1.0"
 
 __all__ = [
     *(f.__name__ for f in GROUPED_FUNCS + MOVE_EXP_FUNCS + MOVE_FUNCS + OTHER_FUNCS + AGGREGATION_FUNCS),
-    "AGGREGATION_FUNCS", "GROUPED_FUNCS", "MOVE_EXP_FUNCS", "MOVE_FUNCS", "OTHER_FUNCS",
+    "nanquantile", "nanmedian", "AGGREGATION_FUNCS", "QUANTILE_FUNCS", "GROUPED_FUNCS", "MOVE_EXP_FUNCS", "MOVE_FUNCS", "OTHER_FUNCS",
     "empty_pinned", "launch_count", "NbgError", "LIB_PATH",
 ]

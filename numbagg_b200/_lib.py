@@ -28,6 +28,7 @@ REDUCE_OPS = dict(
     nanargmin=8, nanmax=9, nanmin=10,
 )
 NBG_REDUCE_STATE_WORDS = 3
+NBG_QUANTILE_MAX_Q = 16
 NBG_EXP_STATE = 11
 NBG_FILL_STATE = 3
 NBG_GROUP_WS_CHANNELS = 4
@@ -61,6 +62,8 @@ _SIGNATURES = {
     "nbg_reduce": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
     "nbg_reduce_partial": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _sz, _vp]),
     "nbg_reduce_merge": (_int, [_int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp]),
+    "nbg_quantile_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "nbg_quantile": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

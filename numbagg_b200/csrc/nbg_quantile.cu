@@ -1,0 +1,304 @@
+// nbg_quantile.cu -- nanquantile / nanmedian over the rows of a (rows, n) float64 matrix
+// (numbagg/funcs.py:245-291, 332-335 behind ndquantile, numbagg/decorators.py:821-901).
+//
+// The reference partitions a NaN-filled copy of every slice (np.partition) and interpolates
+// linearly between the two order statistics around rank (valid - 1) * q.  Selection is exact,
+// so only the final interpolation does arithmetic -- done here with the reference's own three
+// roundings -- and results are bit-identical.  Values travel as order-preserving 64-bit keys
+// (order_key; NaN = the largest key, so missing values sort last like the reference's fill
+// with the maximum).
+//   rows of <= 4096 elements: one CTA loads the row into shared memory, sorts the keys with a
+//     bitonic network and reads the order statistics off (quant_sort_kernel);
+//   longer rows: radix select, 8 bits per pass from the top: every pass histograms the digit
+//     of the elements that match each target's prefix so far (shared-memory histograms, warp-
+//     aggregated, flushed to global), a tiny kernel picks the bucket holding the target rank
+//     and extends the prefix; after 8 passes the prefix IS the key of the order statistic.
+//     8 reads of the data, no scratch copy, any number of rows per launch.
+#include "nbg_common.cuh"
+
+namespace nbg {
+namespace {
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+constexpr int kQThreads = 256;
+constexpr int kQSortMax = 4096;  // longest row sorted in shared memory
+constexpr int kQMaxQ = 16;       // quantiles per call (two targets each: floor and ceil rank)
+
+__device__ __forceinline__ u64 quant_key(double x) { return x != x ? ~0ull : order_key(x); }
+
+// funcs.py:268-288: rank = (valid - 1) * q; floor/ceil indexes; proportion = rank - floor;
+// floor_val + proportion * (ceil_val - floor_val)
+__device__ __forceinline__ void quant_rank(i64 valid, double q, double &rank, i64 &lo, i64 &hi) {
+    rank = __dmul_rn((double)(valid - 1), q);
+    lo = __double2ll_rd(rank);
+    hi = __double2ll_ru(rank);
+}
+__device__ __forceinline__ double quant_interpolate(double fv, double cv, double rank, i64 lo) {
+    const double proportion = __dsub_rn(rank, (double)lo);
+    return __dadd_rn(fv, __dmul_rn(proportion, __dsub_rn(cv, fv)));
+}
+
+// --------------------------------------------------------------------- short rows: sort
+__global__ void __launch_bounds__(kQThreads) quant_sort_kernel(const double *__restrict__ a,
+                                                               const double *__restrict__ q,
+                                                               double *__restrict__ out, i64 n, int npad, int m) {
+    extern __shared__ __align__(16) unsigned char quant_smem[];
+    u64 *keys = reinterpret_cast<u64 *>(quant_smem);
+    __shared__ int s_valid;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const i64 row = blockIdx.x;
+    if (tid == 0) s_valid = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < npad; i += T) {
+        u64 k = ~0ull;
+        if (i < n) {
+            const double x = a[row * n + i];
+            k = quant_key(x);
+            local += x == x ? 1 : 0;
+        }
+        keys[i] = k;
+    }
+    for (int d = 16; d >= 1; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    if ((tid & 31) == 0 && local) atomicAdd(&s_valid, local);
+    __syncthreads();
+    // bitonic sort, ascending
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (npad >> 1); t += T) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // bit log2(j) clear
+                const int p = i | j;
+                const bool up = (i & k) == 0;
+                const u64 x = keys[i], y = keys[p];
+                if ((x > y) == up) {
+                    keys[i] = y;
+                    keys[p] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const i64 valid = s_valid;
+    for (int t = tid; t < m; t += T) {
+        const double qq = q[t];
+        double r = quiet_nan<double>();
+        if (valid > 0 && qq == qq) {
+            double rank;
+            i64 lo, hi;
+            quant_rank(valid, qq, rank, lo, hi);
+            r = quant_interpolate(key_to_double(keys[lo]), key_to_double(keys[hi]), rank, lo);
+        }
+        out[row * m + t] = r;
+    }
+}
+
+// ------------------------------------------------------------------ long rows: radix select
+// Workspace per row: valid count, and per target (2 per quantile) the key prefix found so far
+// and the rank that remains inside that prefix's bucket (-1: inactive target).
+struct QuantWs {
+    i64 *valid;        // [rows]
+    u64 *prefix;       // [rows][T2]
+    i64 *remaining;    // [rows][T2]
+    unsigned *hist;    // [rows][T2][256]
+};
+
+// bin += 1 for every lane with `pred`, one shared-memory atomic per distinct digit in the warp
+__device__ __forceinline__ void warp_hist_add(unsigned *bins, unsigned digit, bool pred) {
+    const unsigned active = __ballot_sync(0xffffffffu, pred);
+    if (!pred) return;
+    const unsigned peers = __match_any_sync(active, digit);
+    if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&bins[digit], (unsigned)__popc(peers));
+}
+
+// pass = 0: one histogram of the top digit per row (+ the count of non-NaN elements);
+// pass >= 1: per target, the next digit of the elements that match the target's prefix.
+// grid = (segments, rows)
+__global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__restrict__ a, QuantWs ws, i64 n, int T2,
+                                                               int pass) {
+    extern __shared__ __align__(16) unsigned char quant_smem[];
+    unsigned *h = reinterpret_cast<unsigned *>(quant_smem);  // [ntab][256]
+    __shared__ u64 s_prefix[2 * kQMaxQ];
+    __shared__ int s_active[2 * kQMaxQ];
+    __shared__ int s_valid;
+    const int tid = threadIdx.x;
+    const i64 row = blockIdx.y;
+    const int ntab = pass == 0 ? 1 : T2;
+    for (int i = tid; i < ntab * 256; i += kQThreads) h[i] = 0;
+    if (tid < T2) {
+        s_prefix[tid] = ws.prefix[row * T2 + tid];
+        s_active[tid] = ws.remaining[row * T2 + tid] >= 0 ? 1 : 0;
+    }
+    if (tid == 0) s_valid = 0;
+    __syncthreads();
+    const double *p = a + row * n;
+    const int shift = 56 - 8 * pass;
+    int local_valid = 0;
+    // whole warps iterate together (the histogram update uses warp votes)
+    const i64 per_cta = ((n + gridDim.x - 1) / gridDim.x + 31) & ~(i64)31;
+    const i64 lo = (i64)blockIdx.x * per_cta;
+    const i64 hi = lo + per_cta < n ? lo + per_cta : n;
+    for (i64 base = lo; base < hi; base += kQThreads) {
+        const i64 i = base + tid;
+        const bool in = i < hi;
+        const double x = in ? __ldcs(p + i) : 0.0;
+        const u64 key = quant_key(x);
+        const unsigned digit = (unsigned)(key >> shift) & 255u;
+        if (pass == 0) {
+            local_valid += (in && x == x) ? 1 : 0;
+            warp_hist_add(h, digit, in);
+        } else {
+            const u64 head = key >> (shift + 8);
+            for (int t = 0; t < T2; t++) {
+                if (!s_active[t]) continue;  // uniform across the CTA
+                warp_hist_add(h + t * 256, digit, in && head == s_prefix[t]);
+            }
+        }
+    }
+    if (pass == 0) {
+        for (int d = 16; d >= 1; d >>= 1) local_valid += __shfl_xor_sync(0xffffffffu, local_valid, d);
+        if ((tid & 31) == 0 && local_valid) atomicAdd(&s_valid, local_valid);
+    }
+    __syncthreads();
+    unsigned *g = ws.hist + (size_t)row * T2 * 256;
+    for (int i = tid; i < ntab * 256; i += kQThreads)
+        if (h[i]) atomicAdd(&g[i], h[i]);
+    if (pass == 0 && tid == 0 && s_valid) atomicAdd(reinterpret_cast<u64 *>(&ws.valid[row]), (u64)s_valid);
+}
+
+// one thread per (row, target): pick the bucket that holds the remaining rank, extend the
+// prefix, clear the histogram for the next pass.  After pass 0 the targets are created first.
+__global__ void quant_select_kernel(QuantWs ws, const double *__restrict__ q, i64 rows, int T2, int pass) {
+    const i64 gid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= rows * T2) return;
+    const i64 row = gid / T2;
+    const int t = (int)(gid % T2);
+    unsigned *h = ws.hist + ((size_t)row * T2 + (pass == 0 ? 0 : t)) * 256;
+    i64 rem = ws.remaining[gid];
+    u64 prefix = ws.prefix[gid];
+    if (pass == 0) {
+        const i64 valid = ws.valid[row];
+        const double qq = q[t >> 1];
+        rem = -1;
+        prefix = 0;
+        if (valid > 0 && qq == qq) {
+            double rank;
+            i64 lo, hi;
+            quant_rank(valid, qq, rank, lo, hi);
+            rem = (t & 1) ? hi : lo;
+        }
+    }
+    if (rem >= 0) {
+        i64 cum = 0;
+        int d = 0;
+        for (; d < 255; d++) {
+            const i64 c = (i64)h[d];
+            if (rem < cum + c) break;
+            cum += c;
+        }
+        rem -= cum;
+        prefix = (prefix << 8) | (u64)d;
+    }
+    ws.remaining[gid] = rem;
+    ws.prefix[gid] = prefix;
+}
+
+__global__ void quant_clear_kernel(unsigned *hist, i64 count) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) hist[i] = 0;
+}
+
+__global__ void quant_finish_kernel(QuantWs ws, const double *__restrict__ q, double *__restrict__ out, i64 rows, int m) {
+    const i64 gid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= rows * m) return;
+    const i64 row = gid / m;
+    const int t = (int)(gid % m);
+    const i64 valid = ws.valid[row];
+    const double qq = q[t];
+    double r = quiet_nan<double>();
+    if (valid > 0 && qq == qq) {
+        double rank;
+        i64 lo, hi;
+        quant_rank(valid, qq, rank, lo, hi);
+        const double fv = key_to_double(ws.prefix[(row * m + t) * 2]);
+        const double cv = key_to_double(ws.prefix[(row * m + t) * 2 + 1]);
+        r = quant_interpolate(fv, cv, rank, lo);
+    }
+    out[gid] = r;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct QuantLayout {
+    size_t valid, prefix, remaining, hist, total;
+};
+QuantLayout quant_layout(i64 rows, i64 m) {
+    QuantLayout l;
+    const size_t T2 = 2 * (size_t)m;
+    l.valid = 0;
+    l.prefix = align256((size_t)rows * 8);
+    l.remaining = l.prefix + align256((size_t)rows * T2 * 8);
+    l.hist = l.remaining + align256((size_t)rows * T2 * 8);
+    l.total = l.hist + align256((size_t)rows * T2 * 256 * 4);
+    return l;
+}
+
+}  // namespace
+}  // namespace nbg
+
+using namespace nbg;
+
+extern "C" size_t nbg_quantile_workspace_bytes(int64_t rows, int64_t n, int64_t m) {
+    if (rows <= 0 || n <= kQSortMax || m <= 0) return 0;
+    return quant_layout(rows, m).total + 256;
+}
+
+extern "C" int nbg_quantile(const void *a, const void *q, void *out, int64_t rows, int64_t n, int64_t m,
+                            void *workspace, size_t workspace_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rows < 0 || n < 0 || m < 0) return fail(NBG_ERR_BAD_ARG, "nbg_quantile: negative extent");
+    if (m > kQMaxQ) return fail(NBG_ERR_BAD_ARG, "nbg_quantile: at most 16 quantiles per call");
+    if (rows == 0 || m == 0) return NBG_OK;
+    if (out == nullptr || q == nullptr || (a == nullptr && n > 0)) return fail(NBG_ERR_BAD_ARG, "nbg_quantile: null pointer");
+    if (rows > 0x7fffffff || n >= ((int64_t)1 << 31))
+        return fail(NBG_ERR_BAD_ARG, "nbg_quantile: rows and n must be below 2^31 (the reference indexes with int32)");
+    const double *ad = (const double *)a, *qd = (const double *)q;
+    if (n <= kQSortMax) {
+        int npad = 2;
+        while (npad < n) npad <<= 1;
+        int threads = npad / 2 < 32 ? 32 : (npad / 2 > kQThreads ? kQThreads : npad / 2);
+        quant_sort_kernel<<<(unsigned)rows, threads, (size_t)npad * 8, stream>>>(ad, qd, (double *)out, n, npad, (int)m);
+        return check_launch("nbg_quantile sort");
+    }
+    const QuantLayout l = quant_layout(rows, m);
+    if (workspace == nullptr || workspace_bytes < l.total + 256)
+        return fail(NBG_ERR_WORKSPACE, "nbg_quantile: workspace smaller than nbg_quantile_workspace_bytes()");
+    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    QuantWs ws{(i64 *)(base + l.valid), (u64 *)(base + l.prefix), (i64 *)(base + l.remaining),
+               (unsigned *)(base + l.hist)};
+    const int T2 = 2 * (int)m;
+    int rc = check_cuda(cudaMemsetAsync(base, 0, l.total, stream), "nbg_quantile: workspace memset");
+    if (rc) return rc;
+    if (rows > 65535) return fail(NBG_ERR_UNSUPPORTED, "nbg_quantile: more than 65535 rows longer than 4096 elements");
+    // about one wave of CTAs over all rows; every CTA at least 4096 elements
+    int64_t segs = ((int64_t)kNumSMs * 8 + rows - 1) / rows;
+    const int64_t max_segs = (n + 4095) / 4096;
+    if (segs > max_segs) segs = max_segs;
+    if (segs < 1) segs = 1;
+    const int64_t sel_threads = rows * T2;
+    const int64_t hist_words = rows * T2 * 256;
+    for (int pass = 0; pass < 8; pass++) {
+        const size_t smem = (size_t)(pass == 0 ? 1 : T2) * 256 * sizeof(unsigned);
+        quant_hist_kernel<<<dim3((unsigned)segs, (unsigned)rows), kQThreads, smem, stream>>>(ad, ws, n, T2, pass);
+        if ((rc = check_launch("nbg_quantile hist"))) return rc;
+        quant_select_kernel<<<(unsigned)((sel_threads + 127) / 128), 128, 0, stream>>>(ws, qd, rows, T2, pass);
+        if ((rc = check_launch("nbg_quantile select"))) return rc;
+        if (pass < 7) {
+            quant_clear_kernel<<<(unsigned)((hist_words + 255) / 256), 256, 0, stream>>>(ws.hist, hist_words);
+            if ((rc = check_launch("nbg_quantile clear"))) return rc;
+        }
+    }
+    quant_finish_kernel<<<(unsigned)((rows * m + 127) / 128), 128, 0, stream>>>(ws, qd, (double *)out, rows, (int)m);
+    return check_launch("nbg_quantile finish");
+}

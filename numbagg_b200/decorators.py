@@ -798,3 +798,61 @@ class ndreduce(NumbaBase):
                 raise ValueError("All-NaN slice encountered")
             return host[()] if host.ndim == 0 else host
         return _reduce_result(res, as_tensor)
+
+
+# ------------------------------------------------------------------------- quantiles
+def run_quantile(t: torch.Tensor, q: torch.Tensor, axes: tuple[int, ...]) -> torch.Tensor:
+    """Device-level entry: float64 CUDA tensor `t`, float64 CUDA vector `q` (quantiles in
+    [0, 1] or NaN); returns (len(q),) + batch shape."""
+    view = ReduceView(t, axes)
+    cube = view.t.reshape(view.outer, view.n, view.inner)
+    if view.inner != 1:  # selection needs each slice contiguous: one transposing copy
+        cube = cube.permute(0, 2, 1).contiguous()
+    rows = view.outer * view.inner
+    L = _lib.lib()
+    m_all = int(q.numel())
+    out = torch.empty((rows, m_all), dtype=torch.float64, device=t.device)
+    for lo in range(0, m_all, _lib.NBG_QUANTILE_MAX_Q):
+        qc = q[lo:lo + _lib.NBG_QUANTILE_MAX_Q].contiguous()
+        m = int(qc.numel())
+        part = out if m == m_all else torch.empty((rows, m), dtype=torch.float64, device=t.device)
+        ws_bytes = L.nbg_quantile_workspace_bytes(rows, view.n, m)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=t.device)
+        rc = L.nbg_quantile(dev.ptr(cube), dev.ptr(qc), dev.ptr(part), rows, view.n, m, ws.data_ptr(), ws_bytes,
+                            dev.stream_ptr())
+        _lib.check(rc, "nbg_quantile")
+        if part is not out:
+            out[:, lo:lo + m] = part
+    return torch.stack([view.restore(out[:, i].contiguous()) for i in range(m_all)]) if m_all else \
+        out.new_empty((0,) + tuple(view.restore(out.new_empty(rows)).shape))
+
+
+class ndquantile(NumbaBase):
+    """numbagg ``ndquantile`` (decorators.py:821-884): ``nanquantile(a, quantiles, axis=None)``;
+    the quantile axis comes first in the result, a scalar `quantiles` is squeezed away."""
+
+    def __call__(self, a, quantiles, axis: int | tuple[int, ...] | None = None, **kwargs):
+        from collections.abc import Iterable
+
+        if kwargs:
+            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        squeeze = not isinstance(quantiles, Iterable)
+        qs = np.asarray([quantiles] if squeeze else quantiles, dtype=np.float64)
+        if qs.ndim != 1:
+            raise ValueError("quantiles must be a scalar or one-dimensional")
+        if any(qs < 0) or any(qs > 1):
+            raise ValueError(f"quantiles must be in the range [0, 1], inclusive. Got {qs}.")
+        as_tensor = dev.is_tensor(a)
+        if not as_tensor:
+            a = np.asarray(a)
+        nd = a.dim() if as_tensor else a.ndim
+        axes = _normalize_axes(axis, nd)
+        dt = dev.np_dtype_of(a)
+        if dt.kind not in "fiub":
+            raise TypeError(f"Unsupported dtype for {self.__name__}: {dt}")
+        t = dev.to_device(a, _F64)  # the reference has a float64 loop only
+        q = torch.from_numpy(qs).to(t.device)
+        res = run_quantile(t, q, axes)
+        if squeeze:
+            res = res[0]
+        return _reduce_result(res, as_tensor)

@@ -1,7 +1,8 @@
 """Plain functions of numbagg/funcs.py on the GPU: ffill / bfill (:294-326, nbg_fill) and the
-NaN-aware reductions (:23-242, nbg_reduce)."""
+NaN-aware reductions (:23-242, nbg_reduce) and nanquantile / nanmedian (:245-291, 332-335,
+nbg_quantile)."""
 
-from .decorators import ndaggregate, ndfill, ndreduce
+from .decorators import ndaggregate, ndfill, ndquantile, ndreduce
 
 ffill = ndfill("ffill", doc="Forward fill missing values.")
 bfill = ndfill("bfill", doc="Backward fill missing values.")
@@ -18,7 +19,15 @@ nanargmin = ndreduce("nanargmin", doc="Flat index of the first minimum, ignoring
 nanmax = ndreduce("nanmax", doc="Maximum, ignoring NaN.")
 nanmin = ndreduce("nanmin", doc="Minimum, ignoring NaN.")
 
+nanquantile = ndquantile("nanquantile", doc="Quantiles of the non-NaN elements along `axis` (linear interpolation).")
+
+
+def nanmedian(a, *, axis=None, **kwargs):
+    """Median of the non-NaN elements (numbagg/funcs.py:332-335)."""
+    return nanquantile(a, quantiles=0.5, axis=axis, **kwargs)
+
+
 __all__ = [
     "ffill", "bfill", "allnan", "anynan", "nancount", "nansum", "nanmean", "nanvar", "nanstd",
-    "nanargmax", "nanargmin", "nanmax", "nanmin",
+    "nanargmax", "nanargmin", "nanmax", "nanmin", "nanquantile", "nanmedian",
 ]

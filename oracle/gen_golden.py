@@ -393,7 +393,40 @@ def gen_reduce():
     s.save()
 
 
+def gen_quantile():
+    """nanquantile / nanmedian (numbagg/funcs.py:245-291, 332-335): SURVEY 8(f) rank 3."""
+    s = Suite("quantile")
+    rs = np.random.RandomState(9)
+    qs = [0.5, 0.0, 1.0, [0.25, 0.5, 0.75], [0.1, nan, 0.9], [0.999, 0.001, 0.5, 0.5]]
+    for dtype in (np.float64, np.float32):
+        a1 = fixture_array((3000,), dtype=dtype, seed=31)
+        a2 = fixture_array((7, 300), nan_frac=0.4, dtype=dtype, seed=32)
+        a3 = fixture_array((4, 6, 50), dtype=dtype, seed=33)
+        ties = np.round((fixture_array((5, 400), dtype=dtype, seed=34) - 0.5) * 6)
+        long = rs.standard_normal((2, 20000)).astype(dtype)  # longer than one shared-memory sort
+        long[0, ::7] = nan
+        for q in qs:
+            s.add("nanquantile", [a1], dict(quantiles=q))
+            for axis in (-1, 0, None):
+                s.add("nanquantile", [a2], dict(quantiles=q, axis=axis))
+                s.add("nanquantile", [ties], dict(quantiles=q, axis=axis))
+            for axis in (1, (0, 2), (2, 1), None):
+                s.add("nanquantile", [a3], dict(quantiles=q, axis=axis))
+            s.add("nanquantile", [long], dict(quantiles=q, axis=-1))
+        for axis in (-1, 0, None):
+            s.add("nanmedian", [a2], dict(axis=axis))
+    special = np.array([[np.inf, 1, 2, nan], [np.inf, np.inf, -np.inf, 0], [nan] * 4, [3, 3, 3, 3.0], [-0.0, 0.0, -1, 1]])
+    for q in ([0, 0.5, 1], 0.3):
+        s.add("nanquantile", [special], dict(quantiles=q, axis=-1), "inf / all-NaN / constant rows")
+    ii = rs.randint(-50, 50, size=(6, 250))
+    s.add("nanquantile", [ii], dict(quantiles=[0.2, 0.8], axis=-1), "integers are cast to float64")
+    s.add("nanquantile", [np.arange(10.0)], dict(quantiles=0.45))
+    s.add("nanquantile", [np.array([5.0])], dict(quantiles=[0, 0.5, 1]))
+    s.save()
+
+
 if __name__ == "__main__":
+    gen_quantile()
     gen_reduce()
     gen_moving()
     gen_moving_exp()

@@ -411,3 +411,49 @@ def nanmin(a, *, axis=None):
 
 AGGREGATION_FUNCS = ["allnan", "anynan", "nancount", "nansum", "nanmean", "nanvar", "nanstd",
                      "nanargmax", "nanargmin", "nanmax", "nanmin"]
+
+
+# ----------------------------------------------------------- quantiles
+def nanquantile(a, quantiles, axis=None):
+    """numbagg.nanquantile (funcs.py:245-291 behind ndquantile, decorators.py:821-884):
+    float64 only; NaN = missing; linear interpolation between the two order statistics
+    around rank (valid - 1) * q, with the reference's own arithmetic (rank, proportion and
+    floor + proportion * (ceil - floor), each rounded separately).  The order statistics come
+    from a full sort here (np.partition in the reference: same values)."""
+    from collections.abc import Iterable
+
+    squeeze = not isinstance(quantiles, Iterable)
+    q = np.asarray([quantiles] if squeeze else quantiles, dtype=np.float64)
+    if np.any(q < 0) or np.any(q > 1):
+        raise ValueError(f"quantiles must be in the range [0, 1], inclusive. Got {q}.")
+    a = np.asarray(a)
+    if axis is None:
+        axis = tuple(range(a.ndim))
+    elif not isinstance(axis, tuple):
+        axis = (axis,)
+    moved, bshape, n = _reduce_rows(a, axis, by_stride=False)
+    rows = int(np.prod(bshape, dtype=np.int64))
+    flat = np.ascontiguousarray(moved, dtype=np.float64).reshape(rows, n)
+    out = np.empty((rows, len(q)), dtype=np.float64)
+    for r in range(rows):
+        x = flat[r]
+        valid = int(n - np.count_nonzero(np.isnan(x)))
+        if valid == 0:
+            out[r] = np.nan
+            continue
+        s = np.sort(x)  # NaN sorts last, like the reference's fill with the maximum
+        for i, qi in enumerate(q):
+            if np.isnan(qi):
+                out[r, i] = np.nan
+                continue
+            rank = np.float64(valid - 1) * qi
+            lo, hi = int(np.floor(rank)), int(np.ceil(rank))
+            proportion = rank - np.float64(lo)
+            with np.errstate(invalid="ignore"):
+                out[r, i] = s[lo] + proportion * (s[hi] - s[lo])
+    res = np.moveaxis(out.reshape(bshape + (len(q),)), -1, 0)
+    return res[0] if squeeze else res
+
+
+def nanmedian(a, axis=None):
+    return nanquantile(a, 0.5, axis=axis)
