@@ -94,6 +94,9 @@ WORKLOADS.update({
     "red_nanvar_f64_axis0": ("reduce", "nanvar", "f64", 1_000_000, 1000, dict(axis=0)),
     "red_nanmean_f32_short": ("reduce", "nanmean", "f32", 10_000_000, 100, dict(axis=-1)),
     "red_nansum_f64_all": ("reduce", "nansum", "f64", 1, 1_000_000_000, dict(axis=None)),
+    # selection (multi-pass by construction; roofline counts ONE read)
+    "quant_median_long": ("quantile", "nanquantile", "f64", 2000, 1_000_000, dict(quantiles=0.5, axis=-1)),
+    "quant_quartiles_short": ("quantile", "nanquantile", "f64", 1_000_000, 1000, dict(quantiles=[0.25, 0.5, 0.75], axis=-1)),
 })
 DEFAULT_WORKLOAD = "cfg2_group_nansum"
 TWO_INPUT = {"move_cov", "move_corr", "move_exp_nancov", "move_exp_nancorr"}
@@ -112,6 +115,8 @@ def alg_bytes(family, func, dt, rows, n, params):
     if family == "reduce":
         outs = {None: 1, -1: rows, 0: n}[params["axis"]]
         return rows * n * s + outs * 8
+    if family == "quantile":
+        return rows * n * s + rows * 8 * np.size(params["quantiles"])
     K = params["num_labels"]
     if family == "group":
         return rows * n * s + n * 8 + rows * K * s
@@ -152,8 +157,9 @@ def cpu_baseline(family, func, dt, rows, n, params, budget_s=12.0, reps=3):
         srows, used = 1, 1
     else:
         per_row = n
-        srows = max(1, min(rows, int(2.0e8 // per_row)))  # ~2e8 elements per call
-        sn, used = n, min(cores, srows)
+        # ~2e8 elements per call (the quantile port sorts row by row in NumPy: 2e7)
+        srows = max(1, min(rows, int((2.0e7 if family == "quantile" else 2.0e8) // per_row)))
+        sn, used = n, (1 if family == "quantile" else min(cores, srows))
     p = dict(params)
     if family == "group1d":
         p = dict(params)
@@ -273,6 +279,8 @@ def run_ours(args, wl):
     elif family == "group1d":
         labels = torch.randint(0, params["num_labels"], (rows * n,), generator=g, device=device, dtype=torch.int64)
 
+    qdev = torch.tensor(np.atleast_1d(params["quantiles"]), dtype=torch.float64, device=device) if family == "quantile" else None
+
     def step_device():
         if family == "move":
             return D.run_move(func, tensors, params["window"], params["min_count"], -1)
@@ -284,6 +292,8 @@ def run_ours(args, wl):
         if family == "reduce":
             axes = (0, 1) if params["axis"] is None else (params["axis"] % 2,)
             return D.run_reduce(func, a, axes)
+        if family == "quantile":
+            return D.run_quantile(a, qdev, (params["axis"] % 2,))
         v2 = a if family == "group" else a.view(1, -1)
         return D.run_group(func, v2, labels, params["num_labels"], 1)
 

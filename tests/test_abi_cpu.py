@@ -57,6 +57,7 @@ def test_product_never_imports_oracle():
 def test_function_census_and_metadata():
     assert len(nb.MOVE_FUNCS) == 6 and len(nb.MOVE_EXP_FUNCS) == 7
     assert len(nb.GROUPED_FUNCS) == 15 and len(nb.OTHER_FUNCS) == 2 and len(nb.AGGREGATION_FUNCS) == 11
+    assert len(nb.QUANTILE_FUNCS) == 2 and repr(nb.nanquantile) == "numbagg.nanquantile"
     assert repr(nb.nansum) == "numbagg.nansum" and nb.nanvar.supports_ddof and not nb.nansum.supports_ddof
     assert repr(nb.move_mean) == "numbagg.move_mean"  # numbagg/decorators.py:119-120
     assert nb.group_nanvar.supports_ddof and not nb.group_nanvar.supports_ints and not nb.group_nanvar.supports_bool
@@ -172,7 +173,13 @@ def test_c_abi_rejects_bad_arguments_without_a_device():
     assert need >= 3 * 8 * 2
     assert L.nbg_reduce(R["nansum"], _lib.NBG_F64, dummy, dummy, 1, 10_000_000, 1, 1, dummy, 8, None) == -6 and "workspace" in err()
     assert L.nbg_reduce_workspace_bytes(R["nansum"], _lib.NBG_F64, 100_000, 100, 1) == 0  # one CTA pass, no partials
+    # quantiles
+    assert L.nbg_quantile(dummy, dummy, dummy, 3, 10, 17, None, 0, None) == -3 and "16 quantiles" in err()
+    assert L.nbg_quantile(dummy, None, dummy, 3, 10, 2, None, 0, None) == -3
+    assert L.nbg_quantile(dummy, dummy, dummy, 3, 100_000, 2, None, 0, None) == -6 and "workspace" in err()
+    assert L.nbg_quantile_workspace_bytes(3, 4096, 2) == 0 and L.nbg_quantile_workspace_bytes(3, 4097, 2) > 3 * 4 * 1024
     before = L.nbg_launch_count()
+    assert L.nbg_quantile(None, None, None, 0, 10, 2, None, 0, None) == 0
     assert L.nbg_reduce(R["nansum"], _lib.NBG_F64, None, None, 0, 10, 1, 1, None, 0, None) == 0  # no outputs
     assert L.nbg_reduce_merge(R["nanvar"], _lib.NBG_F64, None, 0, 0, None, 0, 1, None) == 0
     assert L.nbg_launch_count() == before
