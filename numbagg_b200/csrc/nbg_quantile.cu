@@ -102,6 +102,7 @@ struct QuantWs {
     u64 *prefix;       // [rows][T2]
     i64 *remaining;    // [rows][T2]
     unsigned *hist;    // [rows][T2][256]
+    int *alias;        // [rows][T2]: first target with the same prefix (its histogram serves both)
 };
 
 // bin += 1 for every lane with `pred`, one shared-memory atomic per distinct digit in the warp
@@ -132,6 +133,19 @@ __global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__r
     }
     if (tid == 0) s_valid = 0;
     __syncthreads();
+    // targets that still share their prefix (floor and ceil rank of one quantile, usually up
+    // to the last bits) share one histogram: only the first of them is counted
+    int counted = 0;
+    if (pass > 0 && tid < T2) {
+        int first = tid;
+        for (int t = tid - 1; t >= 0; t--)
+            if (s_active[t] && s_prefix[t] == s_prefix[tid]) first = t;
+        counted = s_active[tid] && first == tid;
+        if (blockIdx.x == 0) ws.alias[row * T2 + tid] = first;
+    }
+    __syncthreads();  // every thread: all reads of s_active above precede the update below
+    if (pass > 0 && tid < T2) s_active[tid] = counted;
+    __syncthreads();
     const double *p = a + row * n;
     const int shift = 56 - 8 * pass;
     int local_valid = 0;
@@ -152,7 +166,9 @@ __global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__r
             const u64 head = key >> (shift + 8);
             for (int t = 0; t < T2; t++) {
                 if (!s_active[t]) continue;  // uniform across the CTA
-                warp_hist_add(h + t * 256, digit, in && head == s_prefix[t]);
+                // (pass 0 sees a handful of digits -- sign and top exponent bits -- and needs
+                // the warp-aggregated update; from here on the digits spread out)
+                if (in && head == s_prefix[t]) atomicAdd(&h[t * 256 + digit], 1u);
             }
         }
     }
@@ -174,7 +190,7 @@ __global__ void quant_select_kernel(QuantWs ws, const double *__restrict__ q, i6
     if (gid >= rows * T2) return;
     const i64 row = gid / T2;
     const int t = (int)(gid % T2);
-    unsigned *h = ws.hist + ((size_t)row * T2 + (pass == 0 ? 0 : t)) * 256;
+    unsigned *h = ws.hist + ((size_t)row * T2 + (pass == 0 ? 0 : ws.alias[gid])) * 256;
     i64 rem = ws.remaining[gid];
     u64 prefix = ws.prefix[gid];
     if (pass == 0) {
@@ -231,7 +247,7 @@ __global__ void quant_finish_kernel(QuantWs ws, const double *__restrict__ q, do
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct QuantLayout {
-    size_t valid, prefix, remaining, hist, total;
+    size_t valid, prefix, remaining, alias, hist, total;
 };
 QuantLayout quant_layout(i64 rows, i64 m) {
     QuantLayout l;
@@ -239,7 +255,8 @@ QuantLayout quant_layout(i64 rows, i64 m) {
     l.valid = 0;
     l.prefix = align256((size_t)rows * 8);
     l.remaining = l.prefix + align256((size_t)rows * T2 * 8);
-    l.hist = l.remaining + align256((size_t)rows * T2 * 8);
+    l.alias = l.remaining + align256((size_t)rows * T2 * 8);
+    l.hist = l.alias + align256((size_t)rows * T2 * 4);
     l.total = l.hist + align256((size_t)rows * T2 * 256 * 4);
     return l;
 }
@@ -276,7 +293,7 @@ extern "C" int nbg_quantile(const void *a, const void *q, void *out, int64_t row
         return fail(NBG_ERR_WORKSPACE, "nbg_quantile: workspace smaller than nbg_quantile_workspace_bytes()");
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     QuantWs ws{(i64 *)(base + l.valid), (u64 *)(base + l.prefix), (i64 *)(base + l.remaining),
-               (unsigned *)(base + l.hist)};
+               (unsigned *)(base + l.hist), (int *)(base + l.alias)};
     const int T2 = 2 * (int)m;
     int rc = check_cuda(cudaMemsetAsync(base, 0, l.total, stream), "nbg_quantile: workspace memset");
     if (rc) return rc;
