@@ -18,7 +18,9 @@ out = [f"# profiles — round {tag}", "",
        "like the reference's gufunc.  The `red_*` rows (plain NaN reductions, SURVEY 8(f) rank 1) only READ",
        "(8 bytes written per output), so they can exceed the measured COPY bandwidth used as `peak` (half",
        "reads, half writes): `roofline` above 1.0 means faster than a device-to-device copy moves the same",
-       "bytes; ncu shows ~90 % of the DRAM peak for `nansum` float32.", "",
+       "bytes; ncu shows ~90 % of the DRAM peak for `nansum` float32.  The `quant_*` rows (nanquantile,",
+       "SURVEY 8(f) rank 3) are selection: 8 reads of the data by construction, `roofline` counts one.",
+       "cfg1 is launch-bound: its K steps are replayed from one CUDA graph (`config.launch`).", "",
        "| workload | shape | Gel/s | ms/step | roofline (of measured) | e2e Gel/s | cpu Gel/s (cores) | kernels/step |",
        "|---|---|---:|---:|---:|---:|---:|---:|"]
 for d in rows:
