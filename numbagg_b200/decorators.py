@@ -811,20 +811,27 @@ def run_quantile(t: torch.Tensor, q: torch.Tensor, axes: tuple[int, ...]) -> tor
     rows = view.outer * view.inner
     L = _lib.lib()
     m_all = int(q.numel())
+    flat = cube.reshape(rows, view.n)
     out = torch.empty((rows, m_all), dtype=torch.float64, device=t.device)
-    for lo in range(0, m_all, _lib.NBG_QUANTILE_MAX_Q):
-        qc = q[lo:lo + _lib.NBG_QUANTILE_MAX_Q].contiguous()
-        m = int(qc.numel())
-        part = out if m == m_all else torch.empty((rows, m), dtype=torch.float64, device=t.device)
-        ws_bytes = L.nbg_quantile_workspace_bytes(rows, view.n, m)
-        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=t.device)
-        rc = L.nbg_quantile(dev.ptr(cube), dev.ptr(qc), dev.ptr(part), rows, view.n, m, ws.data_ptr(), ws_bytes,
-                            dev.stream_ptr())
-        _lib.check(rc, "nbg_quantile")
-        if part is not out:
-            out[:, lo:lo + m] = part
-    return torch.stack([view.restore(out[:, i].contiguous()) for i in range(m_all)]) if m_all else \
-        out.new_empty((0,) + tuple(view.restore(out.new_empty(rows)).shape))
+    # the C entry takes <= 16 quantiles and (on its long-row path) <= 65535 rows per call
+    row_step = rows if view.n <= 4096 else 32768
+    for r0 in range(0, rows, max(row_step, 1)):
+        block = flat[r0:r0 + row_step]
+        nrows = int(block.shape[0])
+        for lo in range(0, m_all, _lib.NBG_QUANTILE_MAX_Q):
+            qc = q[lo:lo + _lib.NBG_QUANTILE_MAX_Q].contiguous()
+            m = int(qc.numel())
+            part = torch.empty((nrows, m), dtype=torch.float64, device=t.device)
+            ws_bytes = L.nbg_quantile_workspace_bytes(nrows, view.n, m)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=t.device)
+            rc = L.nbg_quantile(dev.ptr(block), dev.ptr(qc), dev.ptr(part), nrows, view.n, m, ws.data_ptr(),
+                                ws_bytes, dev.stream_ptr())
+            _lib.check(rc, "nbg_quantile")
+            out[r0:r0 + nrows, lo:lo + m] = part
+    batch_shape = tuple(view.restore(out.new_empty(rows)).shape)
+    if m_all == 0:
+        return out.new_empty((0,) + batch_shape)
+    return torch.stack([view.restore(out[:, i].contiguous()) for i in range(m_all)])
 
 
 class ndquantile(NumbaBase):

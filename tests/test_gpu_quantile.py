@@ -106,3 +106,13 @@ def test_full_size_properties():
     below = int((t < r[3]).sum())
     assert abs(below - valid / 2) <= 1
     assert abs(float(r[3])) < 1e-3 and abs(float(r[2]) + 0.6745) < 1e-3
+
+
+def test_many_long_rows_are_batched():
+    """More long rows than one launch of the radix-select path takes (the host splits them)."""
+    import numbagg_b200 as nb
+
+    a = _data((70_000, 4100), seed=11, nan_frac=0.1)
+    got = nb.nanquantile(a, [0.5, 0.9], axis=-1)
+    sub = np.r_[0:50, 32760:32780, 69_990:70_000]
+    same(got[:, sub], oracle.nanquantile(a[sub], [0.5, 0.9], axis=-1))
