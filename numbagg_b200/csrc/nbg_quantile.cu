@@ -272,22 +272,31 @@ __global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__r
     const i64 per_cta = ((n + gridDim.x - 1) / gridDim.x + 31) & ~(i64)31;
     const i64 lo = (i64)blockIdx.x * per_cta;
     const i64 hi = lo + per_cta < n ? lo + per_cta : n;
-    for (i64 base = lo; base < hi; base += kQThreads) {
-        const i64 i = base + tid;
-        const bool in = i < hi;
-        const double x = in ? __ldcs(p + i) : 0.0;
-        const u64 key = quant_key(x);
-        const unsigned digit = (unsigned)(key >> shift) & 255u;
-        if (pass == 0) {
-            local_valid += (in && x == x) ? 1 : 0;
-            warp_hist_add(h, digit, in);
-        } else {
-            const u64 head = key >> (shift + 8);
-            for (int t = 0; t < T2; t++) {
-                if (!s_active[t]) continue;  // uniform across the CTA
-                // (pass 0 sees a handful of digits -- sign and top exponent bits -- and needs
-                // the warp-aggregated update; from here on the digits spread out)
-                if (in && head == s_prefix[t]) atomicAdd(&h[t * 256 + digit], 1u);
+    constexpr int U = 8;  // independent loads in flight per thread (64 bytes)
+    for (i64 base = lo; base < hi; base += (i64)U * kQThreads) {
+        double xs[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const i64 i = base + (i64)u * kQThreads + tid;
+            xs[u] = i < hi ? __ldcs(p + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool in = base + (i64)u * kQThreads + tid < hi;
+            const double x = xs[u];
+            const u64 key = quant_key(x);
+            const unsigned digit = (unsigned)(key >> shift) & 255u;
+            if (pass == 0) {
+                local_valid += (in && x == x) ? 1 : 0;
+                warp_hist_add(h, digit, in);
+            } else {
+                const u64 head = key >> (shift + 8);
+                for (int t = 0; t < T2; t++) {
+                    if (!s_active[t]) continue;  // uniform across the CTA
+                    // (pass 0 sees a handful of digits -- sign and top exponent bits -- and
+                    // needs the warp-aggregated update; from here on the digits spread out)
+                    if (in && head == s_prefix[t]) atomicAdd(&h[t * 256 + digit], 1u);
+                }
             }
         }
     }
