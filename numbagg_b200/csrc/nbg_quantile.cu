@@ -265,6 +265,25 @@ __global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__r
     __syncthreads();  // every thread: all reads of s_active above precede the update below
     if (pass > 0 && tid < T2) s_active[tid] = counted;
     __syncthreads();
+    // compact list of the histograms to fill: (prefix, table) pairs; one entry in the common
+    // case of a single quantile whose floor and ceil ranks still share their prefix
+    __shared__ int s_ncounted;
+    __shared__ int s_tab[2 * kQMaxQ];
+    __shared__ u64 s_pre[2 * kQMaxQ];
+    if (tid == 0) {
+        int c = 0;
+        for (int t = 0; t < T2 && pass > 0; t++)
+            if (s_active[t]) {
+                s_tab[c] = t;
+                s_pre[c] = s_prefix[t];
+                c++;
+            }
+        s_ncounted = c;
+    }
+    __syncthreads();
+    const int ncounted = s_ncounted;
+    const u64 pre0 = s_pre[0];
+    unsigned *h0 = h + (ncounted > 0 ? s_tab[0] : 0) * 256;
     const double *p = a + row * n;
     const int shift = 56 - 8 * pass;
     int local_valid = 0;
@@ -290,12 +309,14 @@ __global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__r
                 local_valid += (in && x == x) ? 1 : 0;
                 warp_hist_add(h, digit, in);
             } else {
+                // (pass 0 sees a handful of digits -- sign and top exponent bits -- and needs
+                // the warp-aggregated update; from here on the digits spread out)
                 const u64 head = key >> (shift + 8);
-                for (int t = 0; t < T2; t++) {
-                    if (!s_active[t]) continue;  // uniform across the CTA
-                    // (pass 0 sees a handful of digits -- sign and top exponent bits -- and
-                    // needs the warp-aggregated update; from here on the digits spread out)
-                    if (in && head == s_prefix[t]) atomicAdd(&h[t * 256 + digit], 1u);
+                if (ncounted == 1) {
+                    if (in && head == pre0) atomicAdd(&h0[digit], 1u);
+                } else {
+                    for (int c = 0; c < ncounted; c++)
+                        if (in && head == s_pre[c]) atomicAdd(&h[s_tab[c] * 256 + digit], 1u);
                 }
             }
         }
