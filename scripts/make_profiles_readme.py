@@ -31,7 +31,7 @@ out += ["", "Files:", "",
         "* `*_bench_all*.jsonl` — the raw bench.py JSON lines behind the table.",
         "* `*_launches_default_bench*.csv` — ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`) of the default bench command; the row-bins kernel is ~99 % of each step.",
         "* `*_ncu_*.txt` — per-kernel summaries of `ncu --set full` captures (scripts/ncu_summary.py): duration, DRAM bytes (= algorithmic bytes: no re-reads), pipe utilisation, stall reasons, top stalled SASS instructions.",
-        "* `*_launches_quant_median_long.csv` — ncu launch list of one `nanquantile` call on 2000 x 10^6 float64 (radix select: 8 x histogram + select + clear, then finish): every histogram pass takes about 6 ms.",
+        "* `*_launches_quant_median_long.csv` — ncu launch list of one `nanquantile` call on 2000 x 10^6 float64 (radix select: 8 x histogram + select + clear, then finish), captured before the compact target list: about 6 ms per histogram pass then, about 4 ms now.",
         ""]
 open("profiles/README.md", "w").write("\n".join(out))
 print("\n".join(out[:40]))
