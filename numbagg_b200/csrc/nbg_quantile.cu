@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(kQThreads) quant_smem_select_kernel(const doub
     __shared__ i64 s_rem[2 * kQMaxQ];
     __shared__ int s_alias[2 * kQMaxQ];
     __shared__ int s_counted[2 * kQMaxQ];
+    __shared__ int s_tab[2 * kQMaxQ];
+    __shared__ u64 s_pre[2 * kQMaxQ];
+    __shared__ int s_ncounted;
     __shared__ int s_valid;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = blockDim.x;  // 128 for rows up to 2048 elements (more resident CTAs, cheaper barriers), else 256
@@ -151,16 +154,27 @@ __global__ void __launch_bounds__(kQThreads) quant_smem_select_kernel(const doub
             s_counted[tid] = (s_rem[tid] >= 0 && first == tid) ? 1 : 0;
         }
         __syncthreads();
+        if (tid == 0) {  // compact (prefix, table) list of the histograms to fill
+            int c = 0;
+            for (int t = 0; t < T2; t++)
+                if (s_counted[t]) {
+                    s_tab[c] = t;
+                    s_pre[c] = s_prefix[t];
+                    c++;
+                }
+            s_ncounted = c;
+        }
         for (int t = 0; t < T2; t++)  // only the tables that will be counted into
             if (s_counted[t])
                 for (int i = tid; i < 256; i += T) h[t * 256 + i] = 0;
         __syncthreads();
+        const int ncounted = s_ncounted;
         for (int i = tid; i < n; i += T) {
             const u64 key = keys[i];
             const unsigned digit = (unsigned)(key >> shift) & 255u;
             const u64 head = pass == 0 ? 0 : key >> (shift + 8);
-            for (int t = 0; t < T2; t++)
-                if (s_counted[t] && head == s_prefix[t]) atomicAdd(&h[t * 256 + digit], 1u);
+            for (int c = 0; c < ncounted; c++)
+                if (head == s_pre[c]) atomicAdd(&h[s_tab[c] * 256 + digit], 1u);
         }
         __syncthreads();
         // a warp per target: lane l owns bins [8l, 8l + 8); find the bin holding the rank
