@@ -425,7 +425,44 @@ def gen_quantile():
     s.save()
 
 
+def gen_matrix():
+    """Matrix functions (funcs.py:338-532, moving_matrix.py:16-432): SURVEY 8(f) rank 2.
+    Oracle-only so far: these fixtures pin oracle/nbg_oracle.c ahead of the CUDA kernels."""
+    s = Suite("matrix")
+    rs = np.random.RandomState(13)
+    for dtype in (np.float64, np.float32):
+        for nan_frac in (0.0, 0.25, 0.7):
+            vo = fixture_array((5, 80), nan_frac=nan_frac, dtype=dtype, seed=41)      # (vars, obs)
+            vo[3] = vo[1] * 2 + 1            # a perfectly correlated pair
+            vo[4, :] = dtype(0.75)           # a constant variable: zero variance
+            b3 = fixture_array((2, 3, 4, 50), nan_frac=nan_frac, dtype=dtype, seed=42)  # batch dims
+            for f in ("nancorrmatrix", "nancovmatrix"):
+                s.add(f, [vo])
+                s.add(f, [b3])
+            ov = np.ascontiguousarray(vo.T)   # (obs, vars)
+            ob = np.ascontiguousarray(np.swapaxes(b3, -1, -2))
+            for f in ("move_corrmatrix", "move_covmatrix"):
+                for window, mc in ((10, None), (10, 3), (1, 1), (2, 1), (80, 5), (25, 1)):
+                    s.add(f, [ov], dict(window=window, min_count=mc))
+                s.add(f, [ob], dict(window=7, min_count=2))
+            al = (rs.rand(80) * 0.8 + 0.1).astype(dtype)
+            for f in ("move_exp_nancorrmatrix", "move_exp_nancovmatrix"):
+                for alpha in (0.1, 0.9, np.float32(0.25), al):
+                    for mw in (0, 0.3):
+                        s.add(f, [ov], dict(alpha=alpha, min_weight=mw))
+                s.add(f, [ob], dict(alpha=0.2))
+        one = fixture_array((1, 30), dtype=dtype, seed=43)
+        s.add("nancorrmatrix", [one])
+        s.add("nancovmatrix", [one])
+        s.add("move_covmatrix", [np.ascontiguousarray(one.T)], dict(window=5, min_count=1))
+    ii = rs.randint(-5, 6, size=(4, 40))
+    s.add("nancovmatrix", [ii], {}, "integers go through the float64 loop")
+    s.add("move_corrmatrix", [np.ascontiguousarray(ii.T)], dict(window=6, min_count=2))
+    s.save()
+
+
 if __name__ == "__main__":
+    gen_matrix()
     gen_quantile()
     gen_reduce()
     gen_moving()

@@ -457,3 +457,102 @@ def nanquantile(a, quantiles, axis=None):
 
 def nanmedian(a, axis=None):
     return nanquantile(a, 0.5, axis=axis)
+
+
+# -------------------------------------------- matrix functions (oracle only)
+def _matrix_input(a, what):
+    a = np.asarray(a)
+    dt = _float_loop_dtype(a)
+    return np.ascontiguousarray(a, dtype=dt), dt
+
+
+def _static_matrix(a, corr, name):
+    if np.asarray(a).ndim < 2:
+        raise ValueError(
+            f"{name} requires at least a 2D array with shape (..., vars, obs). "
+            "For 1D arrays, use nanvar for variance calculations."
+        )
+    a, dt = _matrix_input(a, name)
+    nv, no = a.shape[-2:]
+    batch = int(np.prod(a.shape[:-2], dtype=np.int64))
+    out = np.empty(a.shape[:-2] + (nv, nv), dtype=dt)
+    fn = getattr(lib(), f"orc_nanmatrix_{_SUFFIX[dt]}")
+    fn.restype = None
+    if batch > 0 and nv > 0:
+        fn(_ptr(a), _ptr(out), _i64(batch), _i64(nv), _i64(no), ctypes.c_int(corr))
+    return out
+
+
+def nancorrmatrix(a):
+    return _static_matrix(a, 1, "nancorrmatrix")
+
+
+def nancovmatrix(a):
+    return _static_matrix(a, 0, "nancovmatrix")
+
+
+def _move_matrix(a, window, min_count, corr, name):
+    a = np.asarray(a)
+    if a.ndim < 2:
+        raise ValueError(f"{name} requires at least a 2D array with shape (..., obs, vars).")
+    if min_count is None:
+        min_count = window
+    elif min_count < 0:
+        raise ValueError(f"min_count must be positive: {min_count}")
+    if not 0 < window <= a.shape[-2]:
+        raise ValueError(f"window not in valid range: {window}")
+    a, dt = _matrix_input(a, name)
+    no, nv = a.shape[-2:]
+    batch = int(np.prod(a.shape[:-2], dtype=np.int64))
+    out = np.empty(a.shape[:-2] + (no, nv, nv), dtype=dt)
+    fn = getattr(lib(), f"orc_move_matrix_{_SUFFIX[dt]}")
+    fn.restype = None
+    if batch > 0 and nv > 0:
+        fn(_ptr(a), _ptr(out), _i64(batch), _i64(no), _i64(nv), _i64(window), _i64(min_count), ctypes.c_int(corr))
+    return out
+
+
+def move_corrmatrix(a, window, min_count=None):
+    return _move_matrix(a, window, min_count, 1, "move_corrmatrix")
+
+
+def move_covmatrix(a, window, min_count=None):
+    return _move_matrix(a, window, min_count, 0, "move_covmatrix")
+
+
+def _move_exp_matrix(a, alpha, min_weight, corr, name):
+    a = np.asarray(a)
+    if a.ndim < 2:
+        raise ValueError(f"{name} requires at least a 2D array with shape (..., obs, vars).")
+    if not isinstance(alpha, np.ndarray):
+        alpha = np.broadcast_to(alpha, a.shape[-2])
+    # gufunc loop selection over (a, alpha); a Python-scalar min_weight is weakly typed
+    dt = _float_loop_dtype(a, alpha) if not isinstance(min_weight, np.generic) else _float_loop_dtype(a, alpha, np.asarray(min_weight))
+    a = np.ascontiguousarray(a, dtype=dt)
+    no, nv = a.shape[-2:]
+    bshape = a.shape[:-2]
+    batch = int(np.prod(bshape, dtype=np.int64))
+    alpha = np.asarray(alpha, dtype=dt)
+    if alpha.ndim == 1:
+        per_item, al = 0, np.ascontiguousarray(alpha)
+    else:
+        per_item, al = 1, np.ascontiguousarray(np.broadcast_to(alpha, bshape + (no,)))
+    out = np.empty(bshape + (no, nv, nv), dtype=dt)
+    fn = getattr(lib(), f"orc_move_exp_matrix_{_SUFFIX[dt]}")
+    fn.restype = None
+    if batch > 0 and nv > 0:
+        fn(_ptr(a), _ptr(al), ctypes.c_int(per_item), ctypes.c_double(float(min_weight)), _ptr(out),
+           _i64(batch), _i64(no), _i64(nv), ctypes.c_int(corr))
+    return out
+
+
+def move_exp_nancorrmatrix(a, alpha, min_weight=0):
+    return _move_exp_matrix(a, alpha, min_weight, 1, "move_exp_nancorrmatrix")
+
+
+def move_exp_nancovmatrix(a, alpha, min_weight=0):
+    return _move_exp_matrix(a, alpha, min_weight, 0, "move_exp_nancovmatrix")
+
+
+MATRIX_FUNCS = ["nancorrmatrix", "nancovmatrix", "move_corrmatrix", "move_covmatrix",
+                "move_exp_nancorrmatrix", "move_exp_nancovmatrix"]

@@ -9,7 +9,7 @@ import pytest
 from oracle import oracle
 from tests._golden import all_cases
 
-CASES = all_cases() + all_cases("reduce") + all_cases("quantile")
+CASES = all_cases() + all_cases("reduce") + all_cases("quantile") + all_cases("matrix")
 
 
 def _int_empty_mask(case, expected):
