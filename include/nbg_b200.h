@@ -243,6 +243,32 @@ size_t nbg_quantile_workspace_bytes(int64_t rows, int64_t n, int64_t m);
 int nbg_quantile(const void *a, const void *q, void *out, int64_t rows, int64_t n, int64_t m,
                  void *workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * Pairwise-complete covariance / correlation matrices: nancorrmatrix,
+ * nancovmatrix (numbagg/funcs.py:338-532 behind ndmatrix, decorators.py:677-740),
+ * move_corrmatrix, move_covmatrix (numbagg/moving_matrix.py:16-204 behind ndmovematrix,
+ * decorators.py:743-818) and move_exp_nancorrmatrix, move_exp_nancovmatrix
+ * (moving_matrix.py:207-432 behind ndmoveexpmatrix, decorators.py:1031-1100).
+ * Static ops: `a` is C-contiguous (batch, n_vars, n_obs), `out` (batch, n_vars, n_vars).
+ * Moving / exponential ops: `a` is (batch, n_obs, n_vars), `out` (batch, n_obs, n_vars,
+ * n_vars); `window`, `min_count` for the moving ops; for the exponential ops `alpha` holds one
+ * decay weight per observation in the dtype of `a` -- (n_obs) shared by all batch items
+ * (alpha_per_item = 0) or (batch, n_obs) -- and `min_weight` gates the output.
+ * dtype: NBG_F32 | NBG_F64.  Results are bit-identical to numbagg (same operations, same
+ * order, running sums in the input dtype).
+ */
+typedef enum {
+    NBG_MAT_NANCORR = 0,
+    NBG_MAT_NANCOV = 1,
+    NBG_MAT_MOVE_CORR = 2,
+    NBG_MAT_MOVE_COV = 3,
+    NBG_MAT_EXP_CORR = 4,
+    NBG_MAT_EXP_COV = 5
+} nbg_matrix_op;
+int nbg_matrix(int op, int dtype, const void *a, const void *alpha, int alpha_per_item,
+               double min_weight, void *out, int64_t batch, int64_t n_obs, int64_t n_vars,
+               int64_t window, int64_t min_count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

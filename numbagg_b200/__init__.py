@@ -44,6 +44,14 @@ from .grouped import (
     group_nanvar,
 )
 from .moving import move_corr, move_cov, move_mean, move_std, move_sum, move_var
+from .moving_matrix import (
+    move_corrmatrix,
+    move_covmatrix,
+    move_exp_nancorrmatrix,
+    move_exp_nancovmatrix,
+    nancorrmatrix,
+    nancovmatrix,
+)
 from .moving_exp import (
     move_exp_nancorr,
     move_exp_nancount,
@@ -69,11 +77,14 @@ AGGREGATION_FUNCS = [
     allnan, anynan, nancount, nansum, nanmean, nanvar, nanstd, nanargmax, nanargmin, nanmax, nanmin,
 ]
 QUANTILE_FUNCS = [nanquantile, nanmedian]
+MATRIX_FUNCS = [
+    nancorrmatrix, nancovmatrix, move_corrmatrix, move_covmatrix, move_exp_nancorrmatrix, move_exp_nancovmatrix,
+]
 
 __version__ = "0.1.0"
 
 __all__ = [
     *(f.__name__ for f in GROUPED_FUNCS + MOVE_EXP_FUNCS + MOVE_FUNCS + OTHER_FUNCS + AGGREGATION_FUNCS),
-    "nanquantile", "nanmedian", "AGGREGATION_FUNCS", "QUANTILE_FUNCS", "GROUPED_FUNCS", "MOVE_EXP_FUNCS", "MOVE_FUNCS", "OTHER_FUNCS",
+    "nanquantile", "nanmedian", *(f.__name__ for f in MATRIX_FUNCS), "MATRIX_FUNCS", "AGGREGATION_FUNCS", "QUANTILE_FUNCS", "GROUPED_FUNCS", "MOVE_EXP_FUNCS", "MOVE_FUNCS", "OTHER_FUNCS",
     "empty_pinned", "launch_count", "NbgError", "LIB_PATH",
 ]

@@ -27,6 +27,10 @@ REDUCE_OPS = dict(
     allnan=0, anynan=1, nancount=2, nansum=3, nanmean=4, nanvar=5, nanstd=6, nanargmax=7,
     nanargmin=8, nanmax=9, nanmin=10,
 )
+MATRIX_OPS = dict(
+    nancorrmatrix=0, nancovmatrix=1, move_corrmatrix=2, move_covmatrix=3, move_exp_nancorrmatrix=4,
+    move_exp_nancovmatrix=5,
+)
 NBG_REDUCE_STATE_WORDS = 3
 NBG_QUANTILE_MAX_Q = 16
 NBG_EXP_STATE = 11
@@ -64,6 +68,7 @@ _SIGNATURES = {
     "nbg_reduce_merge": (_int, [_int, _int, _vp, _i64, _i64, _vp, _i64, _i64, _vp]),
     "nbg_quantile_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "nbg_quantile": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "nbg_matrix": (_int, [_int, _int, _vp, _vp, _int, _dbl, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libnbg_b200.so")
-SOURCES = ["nbg_abi.cu", "nbg_move.cu", "nbg_move_exp.cu", "nbg_fill.cu", "nbg_group.cu", "nbg_reduce.cu", "nbg_quantile.cu"]
+SOURCES = ["nbg_abi.cu", "nbg_move.cu", "nbg_move_exp.cu", "nbg_fill.cu", "nbg_group.cu", "nbg_reduce.cu", "nbg_quantile.cu", "nbg_matrix.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "nbg_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -863,3 +863,104 @@ class ndquantile(NumbaBase):
         if squeeze:
             res = res[0]
         return _reduce_result(res, as_tensor)
+
+
+# ------------------------------------------------------------------- matrix functions
+def run_matrix(name: str, t: torch.Tensor, *, window: int = 0, min_count: int = 0, alpha: torch.Tensor | None = None,
+               min_weight: float = 0.0) -> torch.Tensor:
+    """Device-level entry for the six matrix functions.  Static ops take (..., vars, obs),
+    the moving / exponential ones (..., obs, vars); `alpha` is (obs,) or batch-shaped + (obs,)
+    in the dtype of `t`."""
+    static = name in ("nancorrmatrix", "nancovmatrix")
+    t = t if t.is_contiguous() else t.contiguous()
+    batch_shape = tuple(t.shape[:-2])
+    batch = math.prod(batch_shape)
+    if static:
+        nv, no = t.shape[-2:]
+        out = torch.empty(batch_shape + (nv, nv), dtype=t.dtype, device=t.device)
+    else:
+        no, nv = t.shape[-2:]
+        out = torch.empty(batch_shape + (no, nv, nv), dtype=t.dtype, device=t.device)
+    per_item = 0
+    if alpha is not None:
+        if alpha.dim() > 1:
+            alpha = alpha.expand(batch_shape + (no,))
+            per_item = 1
+        alpha = alpha.contiguous()
+    rc = _lib.lib().nbg_matrix(_lib.MATRIX_OPS[name], _NBG_DTYPE[dev._TORCH_TO_NP[t.dtype]], dev.ptr(t), dev.ptr(alpha),
+                               per_item, float(min_weight), dev.ptr(out), batch, no, nv, int(window), int(min_count),
+                               dev.stream_ptr())
+    _lib.check(rc, f"nbg_matrix({name})")
+    return out
+
+
+def _matrix_loop_dtype(*dtypes: np.dtype) -> np.dtype:
+    return _float_loop_dtype(*dtypes)
+
+
+class ndmatrix(NumbaBase):
+    """numbagg ``ndmatrix`` (decorators.py:677-740): ``(..., vars, obs) -> (..., vars, vars)``."""
+
+    def __call__(self, a, **kwargs):
+        if kwargs:
+            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        as_tensor = dev.is_tensor(a)
+        nd = a.dim() if as_tensor else np.ndim(a)
+        if nd < 2:
+            raise ValueError(
+                f"{self.__name__} requires at least a 2D array with shape (..., vars, obs). "
+                "For 1D arrays, use nanvar for variance calculations."
+            )
+        t = dev.to_device(a, _matrix_loop_dtype(dev.np_dtype_of(a)))
+        return _finish(run_matrix(self.__name__, t), as_tensor)
+
+
+class ndmovematrix(NumbaBase):
+    """numbagg ``ndmovematrix`` (decorators.py:743-818): ``(..., obs, vars) -> (..., obs, vars, vars)``."""
+
+    def __call__(self, a, window: int, min_count: int | None = None, **kwargs):
+        if kwargs:
+            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        as_tensor = dev.is_tensor(a)
+        if not as_tensor:
+            a = np.asarray(a)
+        nd = a.dim() if as_tensor else a.ndim
+        if nd < 2:
+            raise ValueError(f"{self.__name__} requires at least a 2D array with shape (..., obs, vars).")
+        if min_count is None:
+            min_count = window
+        elif min_count < 0:
+            raise ValueError(f"min_count must be positive: {min_count}")
+        if not 0 < window <= a.shape[-2]:
+            raise ValueError(f"window not in valid range: {window}")
+        t = dev.to_device(a, _matrix_loop_dtype(dev.np_dtype_of(a)))
+        return _finish(run_matrix(self.__name__, t, window=window, min_count=min_count), as_tensor)
+
+
+class ndmoveexpmatrix(NumbaBase):
+    """numbagg ``ndmoveexpmatrix`` (decorators.py:1031-1100): one `alpha` per observation
+    (a scalar is broadcast), loop dtype from (a, alpha) like NumPy picks it."""
+
+    def __call__(self, a, alpha, min_weight: float = 0, **kwargs):
+        if kwargs:
+            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        as_tensor = dev.is_tensor(a)
+        if not as_tensor:
+            a = np.asarray(a)
+        nd = a.dim() if as_tensor else a.ndim
+        if nd < 2:
+            raise ValueError(f"{self.__name__} requires at least a 2D array with shape (..., obs, vars).")
+        n_obs = a.shape[-2]
+        if dev.is_tensor(alpha):
+            alpha_dt = dev.np_dtype_of(alpha)
+        else:
+            if not isinstance(alpha, np.ndarray):
+                alpha = np.broadcast_to(alpha, n_obs)
+            alpha_dt = alpha.dtype
+        dts = [dev.np_dtype_of(a), alpha_dt]
+        if isinstance(min_weight, np.generic):  # NumPy scalars are strongly typed, Python numbers are not
+            dts.append(np.asarray(min_weight).dtype)
+        work = _matrix_loop_dtype(*dts)
+        t = dev.to_device(a, work)
+        al = dev.to_device(np.ascontiguousarray(alpha) if isinstance(alpha, np.ndarray) else alpha, work, t.device)
+        return _finish(run_matrix(self.__name__, t, alpha=al, min_weight=float(min_weight)), as_tensor)
