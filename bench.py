@@ -97,6 +97,8 @@ WORKLOADS.update({
     # selection (multi-pass by construction; roofline counts ONE read)
     "quant_median_long": ("quantile", "nanquantile", "f64", 2000, 1_000_000, dict(quantiles=0.5, axis=-1)),
     "quant_quartiles_short": ("quantile", "nanquantile", "f64", 1_000_000, 1000, dict(quantiles=[0.25, 0.5, 0.75], axis=-1)),
+    # matrix functions, (obs, vars) -> (obs, vars, vars); write-bound by construction
+    "mat_move_cov": ("matrix", "move_covmatrix", "f64", 200_000, 32, dict(window=100, min_count=10)),
 })
 DEFAULT_WORKLOAD = "cfg2_group_nansum"
 TWO_INPUT = {"move_cov", "move_corr", "move_exp_nancov", "move_exp_nancorr"}
@@ -117,6 +119,8 @@ def alg_bytes(family, func, dt, rows, n, params):
         return rows * n * s + outs * 8
     if family == "quantile":
         return rows * n * s + rows * 8 * np.size(params["quantiles"])
+    if family == "matrix":
+        return rows * n * s + rows * n * n * s
     K = params["num_labels"]
     if family == "group":
         return rows * n * s + n * 8 + rows * K * s
@@ -294,6 +298,8 @@ def run_ours(args, wl):
             return D.run_reduce(func, a, axes)
         if family == "quantile":
             return D.run_quantile(a, qdev, (params["axis"] % 2,))
+        if family == "matrix":
+            return D.run_matrix(func, a, window=params["window"], min_count=params["min_count"])
         v2 = a if family == "group" else a.view(1, -1)
         return D.run_group(func, v2, labels, params["num_labels"], 1)
 

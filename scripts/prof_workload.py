@@ -28,6 +28,8 @@ for _ in range(3):
         D.run_move_exp(func, tensors, params["alpha"], 0.0, -1)
     elif family == "fill":
         D.run_fill(func, a, n, -1)
+    elif family == "matrix":
+        D.run_matrix(func, a, window=params["window"], min_count=params["min_count"])
     elif family == "quantile":
         D.run_quantile(a, torch.tensor(np.atleast_1d(params["quantiles"]), dtype=torch.float64, device=dev), (params["axis"] % 2,))
     elif family == "reduce":

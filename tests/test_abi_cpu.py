@@ -57,6 +57,7 @@ def test_product_never_imports_oracle():
 def test_function_census_and_metadata():
     assert len(nb.MOVE_FUNCS) == 6 and len(nb.MOVE_EXP_FUNCS) == 7
     assert len(nb.GROUPED_FUNCS) == 15 and len(nb.OTHER_FUNCS) == 2 and len(nb.AGGREGATION_FUNCS) == 11
+    assert len(nb.MATRIX_FUNCS) == 6 and repr(nb.move_corrmatrix) == "numbagg.move_corrmatrix"
     assert len(nb.QUANTILE_FUNCS) == 2 and repr(nb.nanquantile) == "numbagg.nanquantile"
     assert repr(nb.nansum) == "numbagg.nansum" and nb.nanvar.supports_ddof and not nb.nansum.supports_ddof
     assert repr(nb.move_mean) == "numbagg.move_mean"  # numbagg/decorators.py:119-120
@@ -178,7 +179,15 @@ def test_c_abi_rejects_bad_arguments_without_a_device():
     assert L.nbg_quantile(dummy, None, dummy, 3, 10, 2, None, 0, None) == -3
     assert L.nbg_quantile(dummy, dummy, dummy, 3, 100_000, 2, None, 0, None) == -6 and "workspace" in err()
     assert L.nbg_quantile_workspace_bytes(3, 4096, 2) == 0 and L.nbg_quantile_workspace_bytes(3, 4097, 2) > 3 * 4 * 1024
+    # matrix functions
+    M = _lib.MATRIX_OPS
+    assert L.nbg_matrix(9, _lib.NBG_F64, dummy, None, 0, 0.0, dummy, 1, 10, 3, 2, 1, None) == -2
+    assert L.nbg_matrix(M["nancovmatrix"], _lib.NBG_I64, dummy, None, 0, 0.0, dummy, 1, 10, 3, 0, 0, None) == -1
+    assert L.nbg_matrix(M["move_covmatrix"], _lib.NBG_F64, dummy, None, 0, 0.0, dummy, 1, 10, 3, 0, 1, None) == -3 and "window" in err()
+    assert L.nbg_matrix(M["move_exp_nancovmatrix"], _lib.NBG_F64, dummy, None, 0, 0.0, dummy, 1, 10, 3, 0, 0, None) == -3 and "alpha" in err()
+    assert L.nbg_matrix(M["nancorrmatrix"], _lib.NBG_F32, dummy, None, 0, 0.0, None, 1, 10, 3, 0, 0, None) == -3
     before = L.nbg_launch_count()
+    assert L.nbg_matrix(M["nancorrmatrix"], _lib.NBG_F32, None, None, 0, 0.0, None, 0, 10, 3, 0, 0, None) == 0
     assert L.nbg_quantile(None, None, None, 0, 10, 2, None, 0, None) == 0
     assert L.nbg_reduce(R["nansum"], _lib.NBG_F64, None, None, 0, 10, 1, 1, None, 0, None) == 0  # no outputs
     assert L.nbg_reduce_merge(R["nanvar"], _lib.NBG_F64, None, 0, 0, None, 0, 1, None) == 0
@@ -193,8 +202,10 @@ def test_c_abi_header_constants_match_python_binding():
         m = re.search(rf"#define\s+{name}\s+(\d+)", text)
         assert m and int(m.group(1)) == value, name
     for table, prefix in ((_lib.MOVE_OPS, "NBG_"), (_lib.EXP_OPS, "NBG_"), (_lib.GROUP_OPS, "NBG_"),
-                          (_lib.REDUCE_OPS, "NBG_RED_")):
+                          (_lib.REDUCE_OPS, "NBG_RED_"), (_lib.MATRIX_OPS, "NBG_MAT_")):
         for fname, code in table.items():
             enum = prefix + fname.upper().replace("MOVE_EXP_", "EXP_")
+            if prefix == "NBG_MAT_":  # NBG_MAT_NANCORR, NBG_MAT_MOVE_COV, NBG_MAT_EXP_CORR ...
+                enum = prefix + fname.upper().replace("MATRIX", "").replace("MOVE_EXP_NAN", "EXP_")
             m = re.search(rf"\b{enum}\s*=\s*(\d+)", text)
             assert m and int(m.group(1)) == code, enum
