@@ -20,7 +20,8 @@ out = [f"# profiles — round {tag}", "",
        "reads, half writes): `roofline` above 1.0 means faster than a device-to-device copy moves the same",
        "bytes; ncu shows ~90 % of the DRAM peak for `nansum` float32.  The `quant_*` rows (nanquantile,",
        "SURVEY 8(f) rank 3) are selection: 8 reads of the data by construction, `roofline` counts one.",
-       "cfg1 is launch-bound: its K steps are replayed from one CUDA graph (`config.launch`).", "",
+       "cfg1 is launch-bound: its K steps are replayed from one CUDA graph (`config.launch`).  `mat_*` (matrix",
+       "functions, SURVEY 8(f) rank 2) is the first, bit-exact but sequential-per-pair kernel: 1024 threads.", "",
        "| workload | shape | Gel/s | ms/step | roofline (of measured) | e2e Gel/s | cpu Gel/s (cores) | kernels/step |",
        "|---|---|---:|---:|---:|---:|---:|---:|"]
 for d in rows:
