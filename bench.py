@@ -163,7 +163,8 @@ def cpu_baseline(family, func, dt, rows, n, params, budget_s=12.0, reps=3):
         per_row = n
         # ~2e8 elements per call (the quantile port sorts row by row in NumPy: 2e7)
         srows = max(1, min(rows, int((2.0e7 if family == "quantile" else 2.0e8) // per_row)))
-        sn, used = n, (1 if family == "quantile" else min(cores, srows))
+        # the quantile port is a NumPy loop; the matrix port parallelises over batch items (one here)
+        sn, used = n, (1 if family in ("quantile", "matrix") else min(cores, srows))
     p = dict(params)
     if family == "group1d":
         p = dict(params)
