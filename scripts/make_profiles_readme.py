@@ -2,6 +2,12 @@
 import json, sys
 path, tag = sys.argv[1], sys.argv[2]
 rows = []
+
+
+def fmt(x):
+    return f"{x:.1f}" if x >= 10 else f"{x:.3g}"
+
+
 for line in open(path):
     try:
         d = json.loads(line)
@@ -26,8 +32,8 @@ out = [f"# profiles — round {tag}", "",
        "|---|---|---:|---:|---:|---:|---:|---:|"]
 for d in rows:
     c = d["config"]
-    out.append(f"| {c['workload']} ({c['func']}, {d['dtype']}) | {c['shape'][0]}x{c['shape'][1]}{' axis=' + str(c['axis']) if 'axis' in c else ''} | {d['value']/1e9:.3g} | {d['ms_per_step']:.3f} | "
-               f"{d['roofline']['frac']:.3g} | {d['e2e']['value']/1e9:.3g} | {d['cpu_baseline']['value']/1e9:.2g} ({d['cpu_baseline']['cores']}) | {d['gpu_launches']/d['steps']:.0f} |")
+    out.append(f"| {c['workload']} ({c['func']}, {d['dtype']}) | {c['shape'][0]}x{c['shape'][1]}{' axis=' + str(c['axis']) if 'axis' in c else ''} | {fmt(d['value']/1e9)} | {d['ms_per_step']:.3f} | "
+               f"{d['roofline']['frac']:.3g} | {fmt(d['e2e']['value']/1e9)} | {fmt(d['cpu_baseline']['value']/1e9)} ({d['cpu_baseline']['cores']}) | {d['gpu_launches']/d['steps']:.0f} |")
 out += ["", "Files:", "",
         "* `*_bench_all*.jsonl` — the raw bench.py JSON lines behind the table.",
         "* `*_launches_default_bench*.csv` — ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`) of the default bench command; the row-bins kernel is ~99 % of each step.",
