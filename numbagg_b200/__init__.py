@@ -13,6 +13,7 @@ from .funcs import (
     allnan,
     anynan,
     bfill,
+    count,
     ffill,
     nanargmax,
     nanargmin,
@@ -85,6 +86,6 @@ __version__ = "0.1.0"
 
 __all__ = [
     *(f.__name__ for f in GROUPED_FUNCS + MOVE_EXP_FUNCS + MOVE_FUNCS + OTHER_FUNCS + AGGREGATION_FUNCS),
-    "nanquantile", "nanmedian", *(f.__name__ for f in MATRIX_FUNCS), "MATRIX_FUNCS", "AGGREGATION_FUNCS", "QUANTILE_FUNCS", "GROUPED_FUNCS", "MOVE_EXP_FUNCS", "MOVE_FUNCS", "OTHER_FUNCS",
+    "count", "nanquantile", "nanmedian", *(f.__name__ for f in MATRIX_FUNCS), "MATRIX_FUNCS", "AGGREGATION_FUNCS", "QUANTILE_FUNCS", "GROUPED_FUNCS", "MOVE_EXP_FUNCS", "MOVE_FUNCS", "OTHER_FUNCS",
     "empty_pinned", "launch_count", "NbgError", "LIB_PATH",
 ]

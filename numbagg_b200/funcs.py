@@ -14,6 +14,7 @@ nansum = ndaggregate("nansum", doc="Sum of the non-NaN elements along `axis`.")
 nanmean = ndaggregate("nanmean", doc="Mean of the non-NaN elements along `axis`.")
 nanvar = ndaggregate("nanvar", supports_ddof=True, doc="Variance of the non-NaN elements along `axis`.")
 nanstd = ndaggregate("nanstd", supports_ddof=True, doc="Standard deviation of the non-NaN elements along `axis`.")
+count = nancount  # numbagg/funcs.py:329
 nanargmax = ndreduce("nanargmax", doc="Flat index of the first maximum, ignoring NaN.")
 nanargmin = ndreduce("nanargmin", doc="Flat index of the first minimum, ignoring NaN.")
 nanmax = ndreduce("nanmax", doc="Maximum, ignoring NaN.")
@@ -28,6 +29,6 @@ def nanmedian(a, *, axis=None, **kwargs):
 
 
 __all__ = [
-    "ffill", "bfill", "allnan", "anynan", "nancount", "nansum", "nanmean", "nanvar", "nanstd",
+    "ffill", "bfill", "allnan", "anynan", "nancount", "count", "nansum", "nanmean", "nanvar", "nanstd",
     "nanargmax", "nanargmin", "nanmax", "nanmin", "nanquantile", "nanmedian",
 ]

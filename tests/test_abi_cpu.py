@@ -74,6 +74,20 @@ def test_function_census_and_metadata():
     assert sig.parameters["ddof"].default == 1 and sig.parameters["num_labels"].default is None
 
 
+def test_every_public_function_of_the_reference_exists():
+    """numbagg.__all__ (numbagg/__init__.py:3-62), frozen here because the reference cannot be
+    imported on the GPU box."""
+    reference_all = """allnan anynan bfill count ffill group_nanall group_nanany group_nanargmax group_nanargmin
+    group_nancount group_nanfirst group_nanlast group_nanmax group_nanmean group_nanmin group_nanprod group_nanstd
+    group_nansum group_nansum_of_squares group_nanvar move_corr move_corrmatrix move_cov move_covmatrix
+    move_exp_nancorr move_exp_nancorrmatrix move_exp_nancount move_exp_nancov move_exp_nancovmatrix move_exp_nanmean
+    move_exp_nanstd move_exp_nansum move_exp_nanvar move_mean move_std move_sum move_var nanargmax nanargmin
+    nancorrmatrix nancount nancovmatrix nanmax nanmean nanmedian nanmin nanquantile nanstd nansum nanvar""".split()
+    missing = [name for name in reference_all if not callable(getattr(nb, name, None))]
+    assert not missing, missing
+    assert nb.count is nb.nancount
+
+
 A = np.arange(10.0)
 
 
