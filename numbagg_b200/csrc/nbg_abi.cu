@@ -1,6 +1,8 @@
 // nbg_abi.cu -- process-wide state of the C ABI (error string, launch counter, version).
 #include "nbg_common.cuh"
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_set>
 
@@ -16,10 +18,14 @@ int allow_big_smem_impl(const void *kern, const char *what) {
     const uint64_t key = (uint64_t)(uintptr_t)kern ^ ((uint64_t)(dev + 1) << 56);
     std::lock_guard<std::mutex> lock(mu);
     if (done.count(key)) return NBG_OK;
-    int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), what);
+    int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemOptIn), what);
     if (rc) return rc;
     done.insert(key);
     return NBG_OK;
+}
+int prefetch_distance(int resident_ctas_per_sm) {
+    if (const char *e = getenv("NBG_PREFETCH_TILES")) return atoi(e);
+    return kNumSMs * resident_ctas_per_sm;
 }
 }  // namespace nbg
 

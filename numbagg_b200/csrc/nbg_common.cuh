@@ -43,7 +43,8 @@ inline int check_cuda(cudaError_t e, const char *what) {
 }
 
 constexpr int kNumSMs = 148;  // B200
-constexpr size_t kMaxSmem = 200 * 1024;  // dynamic shared memory we opt kernels into
+constexpr size_t kMaxSmem = 200 * 1024;  // dynamic shared memory the tile kernels size themselves for
+constexpr size_t kMaxSmemOptIn = 226 * 1024;  // what kernels are opted into (227 KB per CTA minus room for static smem)
 
 // Opt a kernel into kMaxSmem bytes of dynamic shared memory, once per (kernel, device).
 int allow_big_smem_impl(const void *kern, const char *what);
@@ -114,6 +115,15 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+// plain arrival (release.cta): a consumer warp hands a ring stage back to the producer
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// L2 prefetch of a global range (no shared-memory destination): keeps DRAM reads in flight for
+// tiles that the NEXT wave of CTAs will stage, independent of CTA occupancy
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done;
@@ -210,6 +220,21 @@ __device__ __forceinline__ void span_fill_edges(T *s, const T *row, int64_t p0, 
     for (int j = blk_hi + tid; j < pl.hi; j += THREADS) s[j] = row[p0 + j];
     for (int j = pl.hi + tid; j < len; j += THREADS) s[j] = fill;
 }
+
+// L2 prefetch of the in-range, 16-byte aligned interior of a span (what a later CTA will stage).
+template <typename T>
+__device__ __forceinline__ void span_prefetch_l2(const T *row, int64_t p0, int len, int64_t n) {
+    const int64_t lo = p0 < 0 ? 0 : p0;
+    const int64_t hi = (p0 + len > n) ? n : (p0 + len);
+    if (hi <= lo) return;
+    const uintptr_t a = ((uintptr_t)(row + lo) + 15) & ~(uintptr_t)15;
+    const uintptr_t b = (uintptr_t)(row + hi) & ~(uintptr_t)15;
+    if (b > a) bulk_prefetch_l2(reinterpret_cast<const void *>(a), (uint32_t)(b - a));
+}
+
+// Tiles ahead of the running one that a CTA prefetches into L2 (0 = off).  Default: one full
+// wave of resident CTAs; NBG_PREFETCH_TILES overrides (tuning / A-B measurement).
+int prefetch_distance(int resident_ctas_per_sm);
 
 // Bulk-store s[0, cnt) to g[0, cnt): when s and g share their 16-byte phase thread 0 issues
 // the aligned middle as one bulk store and all threads store the unaligned edges; otherwise

@@ -35,6 +35,7 @@
 //                            order, i.e. the reference's own summation order.
 #include "nbg_common.cuh"
 #include "nbg_group_rowbins.cuh"
+#include "nbg_group_rowbins2.cuh"
 
 namespace nbg {
 
@@ -412,6 +413,53 @@ __global__ void group_finalize_kernel(GroupWs ws, V *__restrict__ out, int op, i
     out[s] = r;
 }
 
+// ------------------------------------------------------------------------- L2 residency
+// The per-element-label path resolves one atomic per element in L2; the accumulator table must
+// stay there while tens of GB of inputs stream past it.  The table is marked PERSISTING (it may
+// use the L2 set-aside) and everything else the kernel touches STREAMING, through the stream's
+// access-policy window; the window is cleared again after the launch (stream-ordered).
+struct L2Window {
+    cudaStream_t st;
+    bool on;
+};
+static L2Window l2_window_begin(cudaStream_t st, void *base, size_t bytes) {
+    L2Window w{st, false};
+    const char *e = getenv("NBG_L2_PERSIST");
+    if (!e || atoi(e) == 0) return w;  // off unless asked for (see DESIGN.md 4.3 for the measurement)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return w;
+    int dev = 0, max_persist = 0, max_window = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (max_persist <= 0 || max_window <= 0 || bytes < ((size_t)1 << 20)) return w;
+    static std::atomic<unsigned> limit_set{0};
+    if (!(limit_set.load() & (1u << dev))) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+        limit_set.fetch_or(1u << dev);
+    }
+    cudaStreamAttrValue attr = {};
+    const size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+    attr.accessPolicyWindow.base_ptr = base;
+    attr.accessPolicyWindow.num_bytes = win;
+    double ratio = (double)max_persist / (double)win;
+    attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) {
+        cudaGetLastError();
+        return w;
+    }
+    w.on = true;
+    return w;
+}
+static void l2_window_end(const L2Window &w) {
+    if (!w.on) return;
+    cudaStreamAttrValue attr = {};
+    attr.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(w.st, cudaStreamAttributeAccessPolicyWindow, &attr);
+}
+
 // ---------------------------------------------------------------------------------- launch
 static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
@@ -420,6 +468,13 @@ static int launch_atomic(const V *values, const L *labels, int labels_per_row, G
                          int64_t K, int64_t index_offset, cudaStream_t stream) {
     const int64_t bpr = (n + 2047) / 2048;
     if (bpr * rows > INT32_MAX) return fail(NBG_ERR_UNSUPPORTED, "nbg_group: grid too large");
+    // table bytes actually hammered by the atomics: the record planes this op uses
+    const L2Window l2 = l2_window_begin(stream, ws.ch[0] < ws.ch[2] ? ws.ch[0] : ws.ch[2],
+                                        (size_t)ws_layout(OP).words * (size_t)rows * (size_t)K * 8);
+    struct L2Guard {
+        const L2Window &w;
+        ~L2Guard() { l2_window_end(w); }
+    } l2_guard{l2};
     group_atomic_kernel<V, L, OP, 0><<<(unsigned)(bpr * rows), 256, 0, stream>>>(values, labels, labels_per_row, ws,
                                                                                   rows, n, K, index_offset, bpr);
     int rc = check_launch("nbg_group(atomic)");
@@ -441,6 +496,26 @@ template <typename V, typename L>
 static int try_rowbins(int op, const V *values, const L *labels, GroupWs ws, void *scratch, size_t scratch_bytes,
                        int64_t rows, int64_t n, int64_t K, int64_t index_offset, cudaStream_t stream, bool *handled) {
     *handled = false;
+    // conflict-free class-private bins first (one- to three-channel additive ops, prod, any/all)
+#define NBG_RB2_CASE(CLS)                                                                                              \
+    case CLS: {                                                                                                        \
+        int rc2 = rb2_launch<V, L, CLS>(values, labels, ws.ch, ws.stride, scratch, scratch_bytes, rows, n, K, index_offset, stream, handled); \
+        if (rc2 || *handled) return rc2;                                                                               \
+        break;                                                                                                         \
+    }
+    switch (rb_class_of(op)) {
+        NBG_RB2_CASE(RB_SUM)
+        NBG_RB2_CASE(RB_COUNT)
+        NBG_RB2_CASE(RB_MEAN)
+        NBG_RB2_CASE(RB_SUMSQ)
+        NBG_RB2_CASE(RB_VAR)
+        NBG_RB2_CASE(RB_PROD)
+        NBG_RB2_CASE(RB_ANY)
+        NBG_RB2_CASE(RB_ALL)
+        default:
+            break;
+    }
+#undef NBG_RB2_CASE
 #define NBG_RB_CASE(CLS) \
     case CLS:            \
         return rb_launch<V, L, CLS>(values, labels, ws.ch, ws.stride, scratch, scratch_bytes, rows, n, K, index_offset, stream, handled)
@@ -526,7 +601,9 @@ extern "C" int nbg_group_record_words(int op) { return nbg::ws_layout(op).words;
 static size_t group_scratch_bytes(int64_t n, int64_t rows) {
     // widest tile is 1536 columns (a short row still needs one whole tile), narrowest 128;
     // plus one lock word per group of 8 rows
-    return (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * nbg::kRbHdr * 4 + (size_t)(rows / 8 + 2) * 4 + 2048;
+    const size_t v1 = (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * nbg::kRbHdr * 4 + (size_t)(rows / 8 + 2) * 4 + 2048;
+    const size_t v2 = nbg::rb2_scratch_bytes(n);
+    return v1 > v2 ? v1 : v2;
 }
 
 extern "C" size_t nbg_group_workspace_bytes(int op, int, int64_t rows, int64_t n, int64_t num_labels) {

@@ -357,6 +357,7 @@ struct RbBin<V, RB_ANY> {  // grouped.py:247-257
     __device__ __forceinline__ void zero() { flag = 0; }
     template <typename I>
     __device__ __forceinline__ void add(V v, bool ok, I) { flag |= (ok && v != (V)0) ? 1 : 0; }
+    __device__ __forceinline__ void merge(const RbBin &o) { flag |= o.flag; }
 };
 template <typename V>
 struct RbBin<V, RB_ALL> {  // grouped.py:260-270
@@ -364,6 +365,7 @@ struct RbBin<V, RB_ALL> {  // grouped.py:260-270
     __device__ __forceinline__ void zero() { flag = 1; }
     template <typename I>
     __device__ __forceinline__ void add(V v, bool ok, I) { flag &= (ok && v == (V)0) ? 0 : 1; }
+    __device__ __forceinline__ void merge(const RbBin &o) { flag &= o.flag; }
 };
 
 template <typename V, int CLS>

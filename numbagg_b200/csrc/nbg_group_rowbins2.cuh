@@ -1,0 +1,610 @@
+// nbg_group_rowbins2.cuh -- shared-label grouped reductions, bank-conflict-free edition
+// (groupndreduce with axis=int, numbagg/decorators.py:633-645; loop bodies grouped.py:7-270).
+//
+// Round 1's row-bins kernel (nbg_group_rowbins.cuh) was bound by shared-memory WAVEFRONTS, not by
+// HBM: ncu on BASELINE config 2 counted 1.29 G bank conflicts on 1.25 G shared-memory
+// instructions -- 9.1 wavefronts per 32 elements against a floor of ~4.5 -- and the kernel time
+// equalled wavefronts / 148 SMs to within 1 %.  The conflicts are structural there: TMA places
+// every row of a tile on a 16-byte boundary, so element (row, col) can only live in banks
+// = col (mod 4) [4-byte data]; four sub-warps reading four unrelated columns collide whenever two
+// columns agree mod 4, and their bins collide whenever two labels agree mod 4.
+//
+// This kernel removes both by construction:
+//   * a warp is 4 sub-warps x 8 lanes (lane = row of an 8-row group); sub-warp q only ever
+//     processes columns with  col % NCLS == q  (NCLS = 16 / sizeof(V) column classes), and rows
+//     are pitched 16 bytes apart in banks, so the 32 lanes of every value load hit 32 distinct
+//     banks;
+//   * bins are PRIVATE PER COLUMN CLASS: bins[channel][label][class q][row] -- 128 bytes per
+//     (channel, label), one bank per lane, any labels -- and the NCLS partial results of a
+//     (row, label) are merged when the CTA flushes.  (The summation order therefore differs
+//     from the reference's; float sums are compared at rtol 1e-5 / 1e-12 like every other
+//     kernel, see DESIGN.md.)
+//   * the column plan (built once per call from the labels, shared by all rows) lists, per tile
+//     and class, the valid columns stably sorted by label, cut into 64/NCLS label-aligned
+//     balanced ranges, each padded to a multiple of 4 entries so that a sub-warp fetches four
+//     entries with one 16-byte load.  No atomics anywhere: a label range belongs to one sub-warp
+//     per tile and its bins to one lane.
+// Row tiles and plan blocks stream through an S-stage TMA ring (cp.async.bulk + mbarrier) filled by
+// a dedicated producer warp; consumer warps hand stages back through `empty` mbarriers, so there
+// is no CTA-wide barrier per tile and warps drift apart by up to S-1 tiles.
+// With few labels (runs of equal labels inside a range) the sub-warp accumulates a run in
+// registers and touches the bin once per run (RUNS).
+//
+// Shared-memory wavefronts per 32 elements: TMA fill 1 + entries 0.25 + values 1 + bins 2 per
+// channel = 4.25 (one channel) -- below the 5.6 that HBM allows at 6.45 TB/s and 1.9 GHz, so the
+// kernel is HBM-bound for one-channel ops.
+#pragma once
+
+#include "nbg_group_rowbins.cuh"
+
+namespace nbg {
+
+constexpr int kRb2Consumers = kRbThreads;        // 512 consumer threads = 64 sub-warps of 8 rows
+constexpr int kRb2Threads = kRb2Consumers + 32;  // + one producer warp
+constexpr int kRb2Pad = 64 * 3;                  // worst-case padding entries per tile
+constexpr int kRb2MaxStages = 4;
+
+// ---------------------------------------------------------------------------------- channel ops
+// Words have the size of V (float/int32 -> 4 bytes, double/int64 -> 8 bytes); counters are the
+// integer of that size (n < 2^31 on this path).
+template <typename V>
+struct Rb2Word {
+    using I = typename RbCounter<V>::type;
+};
+
+template <typename V, int CLS>
+struct Rb2Op;
+
+#define NBG_RB2_ONE(CLS_, ZERO_, STEP_, MERGE_)                                                        \
+    template <typename V>                                                                              \
+    struct Rb2Op<V, CLS_> {                                                                            \
+        using I = typename Rb2Word<V>::I;                                                              \
+        static constexpr int NCH = 1;                                                                  \
+        struct W {                                                                                     \
+            V a;                                                                                       \
+        };                                                                                             \
+        __device__ static __forceinline__ W zero() {                                                   \
+            W w;                                                                                       \
+            ZERO_;                                                                                     \
+            return w;                                                                                  \
+        }                                                                                              \
+        __device__ static __forceinline__ void step(W &w, V v, bool ok) { STEP_; }                     \
+        __device__ static __forceinline__ void merge(W &w, const W &o) { MERGE_; }                     \
+    }
+
+template <typename V>
+__device__ __forceinline__ V rb2_from_int(typename Rb2Word<V>::I i) {
+    V v;
+    memcpy(&v, &i, sizeof(V));
+    return v;
+}
+template <typename V>
+__device__ __forceinline__ typename Rb2Word<V>::I rb2_to_int(V v) {
+    typename Rb2Word<V>::I i;
+    memcpy(&i, &v, sizeof(V));
+    return i;
+}
+
+NBG_RB2_ONE(RB_SUM, w.a = (V)0, w.a = v_add(w.a, ok ? v : (V)0), w.a = v_add(w.a, o.a));
+NBG_RB2_ONE(RB_SUMSQ, w.a = (V)0, w.a = v_add(w.a, v_sq(ok ? v : (V)0)), w.a = v_add(w.a, o.a));
+NBG_RB2_ONE(RB_PROD, w.a = (V)1, w.a = v_mul(w.a, ok ? v : (V)1), w.a = v_mul(w.a, o.a));
+// integer-valued words live in the V-sized slot as raw bits
+NBG_RB2_ONE(RB_COUNT, w.a = rb2_from_int<V>(0), w.a = rb2_from_int<V>(rb2_to_int<V>(w.a) + (ok ? 1 : 0)),
+            w.a = rb2_from_int<V>(rb2_to_int<V>(w.a) + rb2_to_int<V>(o.a)));
+NBG_RB2_ONE(RB_ANY, w.a = rb2_from_int<V>(0), w.a = rb2_from_int<V>(rb2_to_int<V>(w.a) | ((ok && v != (V)0) ? 1 : 0)),
+            w.a = rb2_from_int<V>(rb2_to_int<V>(w.a) | rb2_to_int<V>(o.a)));
+NBG_RB2_ONE(RB_ALL, w.a = rb2_from_int<V>(1), w.a = rb2_from_int<V>(rb2_to_int<V>(w.a) & ((ok && v == (V)0) ? 0 : 1)),
+            w.a = rb2_from_int<V>(rb2_to_int<V>(w.a) & rb2_to_int<V>(o.a)));
+#undef NBG_RB2_ONE
+
+template <typename V>
+struct Rb2Op<V, RB_MEAN> {  // grouped.py:7-27
+    using I = typename Rb2Word<V>::I;
+    static constexpr int NCH = 2;
+    struct W {
+        V a;
+        V b;  // count bits
+    };
+    __device__ static __forceinline__ W zero() { return W{(V)0, rb2_from_int<V>(0)}; }
+    __device__ static __forceinline__ void step(W &w, V v, bool ok) {
+        w.a = v_add(w.a, ok ? v : (V)0);
+        w.b = rb2_from_int<V>(rb2_to_int<V>(w.b) + (ok ? 1 : 0));
+    }
+    __device__ static __forceinline__ void merge(W &w, const W &o) {
+        w.a = v_add(w.a, o.a);
+        w.b = rb2_from_int<V>(rb2_to_int<V>(w.b) + rb2_to_int<V>(o.b));
+    }
+};
+template <typename V>
+struct Rb2Op<V, RB_VAR> {  // grouped.py:148-208
+    using I = typename Rb2Word<V>::I;
+    static constexpr int NCH = 3;
+    struct W {
+        V a, b;
+        V c;  // count bits
+    };
+    __device__ static __forceinline__ W zero() { return W{(V)0, (V)0, rb2_from_int<V>(0)}; }
+    __device__ static __forceinline__ void step(W &w, V v, bool ok) {
+        const V m = ok ? v : (V)0;
+        w.a = v_add(w.a, m);
+        w.b = v_add(w.b, v_sq(m));
+        w.c = rb2_from_int<V>(rb2_to_int<V>(w.c) + (ok ? 1 : 0));
+    }
+    __device__ static __forceinline__ void merge(W &w, const W &o) {
+        w.a = v_add(w.a, o.a);
+        w.b = v_add(w.b, o.b);
+        w.c = rb2_from_int<V>(rb2_to_int<V>(w.c) + rb2_to_int<V>(o.c));
+    }
+};
+
+// merged words -> the round-1 bin type, so that its workspace flush (RbFlush) is reused as is
+template <typename V, int CLS>
+__device__ __forceinline__ RbBin<V, CLS> rb2_to_bin(const typename Rb2Op<V, CLS>::W &w) {
+    RbBin<V, CLS> b;
+    if constexpr (CLS == RB_SUM || CLS == RB_SUMSQ) {
+        b.s = w.a;
+    } else if constexpr (CLS == RB_PROD) {
+        b.pr = w.a;
+    } else if constexpr (CLS == RB_COUNT) {
+        b.c = rb2_to_int<V>(w.a);
+    } else if constexpr (CLS == RB_ANY || CLS == RB_ALL) {
+        b.flag = rb2_to_int<V>(w.a);
+    } else if constexpr (CLS == RB_MEAN) {
+        b.s = w.a;
+        b.c = rb2_to_int<V>(w.b);
+    } else {
+        b.s = w.a;
+        b.ss = w.b;
+        b.c = rb2_to_int<V>(w.c);
+        b.pad = 0;
+    }
+    return b;
+}
+
+// ----------------------------------------------------------------------------------- plan
+// Per tile: header hdr[q * (SUBS + 1) + j] = first entry of range j of class q (the next range
+// starts where this one ends; every range is a multiple of 4 entries long), then the entries
+// (byte offset of the column inside a tile row << 16 | slot) -- both fields pre-scaled so that the
+// kernel forms each shared-memory address with one or two integer instructions.  Padding entries
+// point at the dummy slot `nslots` and at column q (same class, always inside the tile).  A CTA of a cluster of `nc` owns the labels with
+// label % nc == rank and addresses them as slot = label / nc; its plan lists only those.
+template <typename L, int NCLS>
+__global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ labels, int64_t n, int K, int C,
+                                                          int ent_cap, int nc, int vsize, uint32_t *__restrict__ plan) {
+    constexpr int SUBS = 64 / NCLS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int NK = NCLS * K;
+    int *offs = reinterpret_cast<int *>(smem_raw);               // [NK + 1] histogram -> exclusive offsets
+    int *cursor = offs + (NK + 1);                               // [NK]
+    uint32_t *skey = reinterpret_cast<uint32_t *>(cursor + NK);  // [C] class * K + label, or ~0
+    uint32_t *sent = skey + C;                                   // [C] entries in (class, label, column) order
+    __shared__ int warp_tot[8];
+    __shared__ int ub[65];   // unpadded range bounds over `sent`, flattened (class, range)
+    __shared__ int pst[65];  // padded start of every range
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tile = blockIdx.x / nc, rank = blockIdx.x % nc;
+    const int64_t c0 = (int64_t)tile * C;
+    uint32_t *out = plan + (size_t)blockIdx.x * (kRbHdr + ent_cap);
+    const int nslots = (K + nc - 1) / nc;
+
+    for (int k = tid; k <= NK; k += 256) offs[k] = 0;
+    __syncthreads();
+    for (int j = tid; j < C; j += 256) {
+        const int64_t col = c0 + j;
+        long long lab = -1;
+        if (col < n) lab = (long long)labels[col];
+        const bool valid = lab >= 0 && lab < K && (nc == 1 || (int)(lab % nc) == rank);
+        const uint32_t key = (uint32_t)((j % NCLS) * K + (int)lab);
+        skey[j] = valid ? key : 0xffffffffu;
+        if (valid) atomicAdd(&offs[key], 1);
+    }
+    __syncthreads();
+    {  // exclusive scan of offs[0..NK)
+        const int per = (NK + 255) / 256;
+        const int beg = min(tid * per, NK), end = min(beg + per, NK);
+        int local = 0;
+        for (int k = beg; k < end; k++) local += offs[k];
+        int inc = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        int base = 0;
+        for (int w2 = 0; w2 < wid; w2++) base += warp_tot[w2];
+        int run = base + inc - local;
+        for (int k = beg; k < end; k++) {
+            const int c = offs[k];
+            offs[k] = run;
+            cursor[k] = run;
+            run += c;
+        }
+        if (tid == 255) {
+            int tot = 0;
+            for (int w2 = 0; w2 < 8; w2++) tot += warp_tot[w2];
+            offs[NK] = tot;
+        }
+    }
+    __syncthreads();
+    // stable placement by one warp: columns in ascending order, 32 at a time
+    if (wid == 0) {
+        for (int j0 = 0; j0 < C; j0 += 32) {
+            const int j = j0 + lane;
+            const uint32_t key = j < C ? skey[j] : 0xffffffffu;
+            const bool valid = key != 0xffffffffu;
+            const unsigned m = __match_any_sync(0xffffffffu, key);
+            if (valid) {
+                const int rk = __popc(m & ((1u << lane) - 1u));
+                const int lab = (int)(key % (uint32_t)K);
+                sent[cursor[key] + rk] = ((uint32_t)(j * vsize) << 16) | (uint32_t)(lab / nc);
+            }
+            __syncwarp();
+            if (valid && (m & ((1u << lane) - 1u)) == 0) cursor[key] += __popc(m);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // label-aligned balanced ranges per class (unpadded positions)
+    if (tid <= 64) {
+        int b;
+        if (tid == 64) {
+            b = offs[NK];
+        } else {
+            const int q = tid / SUBS, j = tid % SUBS;
+            const int cs = offs[q * K], ce = offs[(q + 1) * K];
+            if (j == 0 || ce == cs) {
+                b = cs;
+            } else {
+                const int e = cs + (int)(((long long)j * (ce - cs)) / SUBS);
+                const uint32_t ent = sent[e];
+                const int lab = (int)(ent & 0xffffu) * nc + rank;
+                b = offs[q * K + lab];  // start of the label run containing e
+            }
+        }
+        ub[tid] = b;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int p = 0;
+        for (int g = 0; g < 64; g++) {
+            pst[g] = p;
+            p += (ub[g + 1] - ub[g] + 3) & ~3;
+        }
+        pst[64] = p;
+    }
+    __syncthreads();
+    // header: hdr[q * (SUBS + 1) + j], j = 0..SUBS  (entry SUBS of class q = start of class q + 1)
+    if (tid < NCLS * (SUBS + 1)) {
+        const int q = tid / (SUBS + 1), j = tid % (SUBS + 1);
+        out[tid] = (uint32_t)pst[q * SUBS + j];
+    }
+    for (int t2 = NCLS * (SUBS + 1) + tid; t2 < kRbHdr; t2 += 256) out[t2] = 0;
+    // entries into their padded places
+    const int total = offs[NK];
+    for (int pos = tid; pos < total; pos += 256) {
+        int lo = 0, hi = 63;  // last range g with ub[g] <= pos
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (ub[mid] <= pos) lo = mid;
+            else hi = mid - 1;
+        }
+        out[kRbHdr + pst[lo] + (pos - ub[lo])] = sent[pos];
+    }
+    if (tid < 64) {
+        const int cnt = ub[tid + 1] - ub[tid];
+        const int q = tid / SUBS;
+        const uint32_t dummy = ((uint32_t)(q * vsize) << 16) | (uint32_t)nslots;
+        for (int i = cnt; i < ((cnt + 3) & ~3); i++) out[kRbHdr + pst[tid] + i] = dummy;
+    }
+}
+
+// ----------------------------------------------------------------------------------- kernel
+struct Rb2Params {
+    const void *values;
+    const uint32_t *plan;
+    void *ws_ch[3];
+    int64_t ws_stride;
+    int64_t rows, n;
+    int K, C, S, ent_cap;
+    int ntiles, tiles_per_seg, nseg;
+    int64_t index_offset;
+};
+
+template <typename V>
+__host__ __device__ inline size_t rb2_stage_bytes(int C, int ent_cap) {
+    return ((size_t)(kRbHdr + ent_cap) * 4 + (size_t)kRbRows * rb_row_stride<V>(C) * sizeof(V) + 15) & ~(size_t)15;
+}
+template <typename V, int CLS>
+__host__ __device__ inline size_t rb2_bins_bytes(int nslots) {
+    return (size_t)Rb2Op<V, CLS>::NCH * (size_t)(nslots + 1) * 128;
+}
+template <typename V, int CLS>
+__host__ __device__ inline size_t rb2_smem_bytes(int nslots, int C, int ent_cap, int S) {
+    return 128 + rb2_bins_bytes<V, CLS>(nslots) + (size_t)S * rb2_stage_bytes<V>(C, ent_cap);
+}
+
+template <typename V, int CLS, bool RUNS>
+__global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Params p) {
+    using Op = Rb2Op<V, CLS>;
+    using W = typename Op::W;
+    using Acc = typename std::conditional<std::is_floating_point<V>::value, double, long long>::type;
+    constexpr int NCH = Op::NCH;
+    constexpr int NCLS = 16 / (int)sizeof(V);
+    constexpr int SUBS = 64 / NCLS;
+    static_assert(sizeof(W) == NCH * sizeof(V), "channel words are V-sized");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);       // [S]
+    uint64_t *empty = full + kRb2MaxStages;                        // [S]
+    unsigned char *bins = smem_raw + 128;
+    const int C = p.C, K = p.K, S = p.S;
+    const int nslots = K;  // single-CTA ownership: slot == label
+    const size_t bins_bytes = rb2_bins_bytes<V, CLS>(nslots);
+    const size_t ch_bytes = (size_t)(nslots + 1) * 128;
+    unsigned char *stage0 = bins + bins_bytes;
+    const size_t stage_bytes = rb2_stage_bytes<V>(C, p.ent_cap);
+    const int stride = rb_row_stride<V>(C);
+
+    const int tid = threadIdx.x;
+    const int64_t g = blockIdx.x / p.nseg;
+    const int seg = blockIdx.x % p.nseg;
+    const int64_t r0 = g * kRbRows;
+    const int nrows = (int)min((int64_t)kRbRows, p.rows - r0);
+    const int t_beg = seg * p.tiles_per_seg;
+    const int t_end = min(t_beg + p.tiles_per_seg, p.ntiles);
+    const int ntl = t_end - t_beg;
+    const V *vbase = reinterpret_cast<const V *>(p.values) + r0 * p.n;
+
+    // bins start at the identity of every channel (word images are channel-uniform)
+    {
+        const W z = Op::zero();
+        const V *zw = reinterpret_cast<const V *>(&z);
+        constexpr int WPS = 128 / (int)sizeof(V);  // words per (channel, slot)
+        V *bw = reinterpret_cast<V *>(bins);
+        for (int ch = 0; ch < NCH; ch++)
+            for (int i = tid; i < (nslots + 1) * WPS; i += kRb2Threads) bw[(size_t)ch * (nslots + 1) * WPS + i] = zw[ch];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kRb2Consumers / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (tid >= kRb2Consumers) {
+        // ---------------------------------------------------------------- producer warp
+        if (tid == kRb2Consumers) {
+            const uint32_t plan_bytes = (uint32_t)(kRbHdr + p.ent_cap) * 4u;
+            for (int it = 0; it < ntl; it++) {
+                const int st = it % S;
+                mbar_wait(&empty[st], (uint32_t)(((it / S) & 1) ^ 1));  // fresh barrier: passes at once
+                const int t = t_beg + it;
+                unsigned char *sb = stage0 + (size_t)st * stage_bytes;
+                const int64_t c0 = (int64_t)t * C;
+                const int cols = (int)min((int64_t)C, p.n - c0);
+                const uint32_t row_bytes = (uint32_t)cols * (uint32_t)sizeof(V);
+                mbar_arrive_expect_tx(&full[st], plan_bytes + (uint32_t)nrows * row_bytes);
+                bulk_g2s(sb, p.plan + (size_t)t * (kRbHdr + p.ent_cap), plan_bytes, &full[st]);
+                V *tile = reinterpret_cast<V *>(sb + (size_t)(kRbHdr + p.ent_cap) * 4);
+                for (int rr = 0; rr < nrows; rr++)
+                    bulk_g2s(tile + (size_t)rr * stride, vbase + (int64_t)rr * p.n + c0, row_bytes, &full[st]);
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- consumer warps
+        const int r = tid & (kRbRows - 1);
+        const int sub = tid >> 3;
+        const int q = sub % NCLS;   // column class of this sub-warp
+        const int j = sub / NCLS;   // its label range within the class
+        const uint32_t bins_s = smem_u32(bins) + (uint32_t)(q * kRbRows + r) * (uint32_t)sizeof(V);
+        const bool active = r < nrows;
+        for (int it = 0; it < ntl; it++) {
+            const int st = it % S;
+            mbar_wait(&full[st], (uint32_t)((it / S) & 1));
+            const uint32_t sb = smem_u32(stage0 + (size_t)st * stage_bytes);
+            const uint32_t *hdr = reinterpret_cast<const uint32_t *>(__cvta_shared_to_generic(sb));
+            const uint32_t ent_s = sb + kRbHdr * 4;
+            const uint32_t tile_s = sb + (uint32_t)(kRbHdr + p.ent_cap) * 4 + (uint32_t)r * (uint32_t)stride * (uint32_t)sizeof(V);
+            const int b0 = (int)hdr[q * (SUBS + 1) + j], b1 = (int)hdr[q * (SUBS + 1) + j + 1];
+            auto val_at = [&](uint32_t e) -> V {
+                return *reinterpret_cast<const V *>(__cvta_shared_to_generic(tile_s + (e >> 16)));
+            };
+            auto bin_ptr = [&](uint32_t slot, int ch) -> V * {
+                return reinterpret_cast<V *>(__cvta_shared_to_generic(bins_s + (uint32_t)ch * (uint32_t)ch_bytes + slot * 128u));
+            };
+            auto rmw = [&](uint32_t slot, V v) {
+                W w;
+                V *ww = reinterpret_cast<V *>(&w);
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) ww[ch] = *bin_ptr(slot, ch);
+                Op::step(w, v, !is_nan(v));
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) *bin_ptr(slot, ch) = ww[ch];
+            };
+            if (active) {
+                if constexpr (!RUNS) {
+                    for (int i = b0; i < b1; i += 4) {
+                        const uint4 e = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ent_s + (uint32_t)i * 4u));
+                        const V v0 = val_at(e.x), v1 = val_at(e.y), v2 = val_at(e.z), v3 = val_at(e.w);
+                        // read-modify-write in entry order: consecutive entries may share a label
+                        rmw(e.x & 0xffffu, v0);
+                        rmw(e.y & 0xffffu, v1);
+                        rmw(e.z & 0xffffu, v2);
+                        rmw(e.w & 0xffffu, v3);
+                    }
+                } else {
+                    uint32_t cur = 0xffffffffu;
+                    W acc = Op::zero();
+                    auto flush_run = [&]() {
+                        W w;
+                        V *ww = reinterpret_cast<V *>(&w);
+#pragma unroll
+                        for (int ch = 0; ch < NCH; ch++) ww[ch] = *bin_ptr(cur, ch);
+                        Op::merge(w, acc);
+#pragma unroll
+                        for (int ch = 0; ch < NCH; ch++) *bin_ptr(cur, ch) = ww[ch];
+                    };
+                    auto one = [&](uint32_t e, V v) {
+                        const uint32_t slot = e & 0xffffu;
+                        if (slot != cur) {
+                            if (cur != 0xffffffffu) flush_run();
+                            cur = slot;
+                            acc = Op::zero();
+                        }
+                        Op::step(acc, v, !is_nan(v));
+                    };
+                    for (int i = b0; i < b1; i += 4) {
+                        const uint4 e = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ent_s + (uint32_t)i * 4u));
+                        const V v0 = val_at(e.x), v1 = val_at(e.y), v2 = val_at(e.z), v3 = val_at(e.w);
+                        one(e.x, v0);
+                        one(e.y, v1);
+                        one(e.z, v2);
+                        one(e.w, v3);
+                    }
+                    if (cur != 0xffffffffu) flush_run();
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[st]);  // this warp is done with stage st
+        }
+    }
+    __syncthreads();
+
+    // ---- flush: merge the NCLS class-private partials of every (row, label), then into the workspace
+    Acc *c0p = reinterpret_cast<Acc *>(p.ws_ch[0]);
+    Acc *c1p = reinterpret_cast<Acc *>(p.ws_ch[1]);
+    long long *c2p = reinterpret_cast<long long *>(p.ws_ch[2]);
+    const bool atomic = p.nseg > 1;
+    constexpr int WPS = 128 / (int)sizeof(V);
+    const V *bw = reinterpret_cast<const V *>(bins);
+    for (int idx = tid; idx < K * kRbRows; idx += kRb2Threads) {
+        const int rr = idx & (kRbRows - 1), k = idx >> 3;  // row fastest: 8 lanes read 8 neighbouring banks
+        if (rr >= nrows) continue;
+        W tot;
+        V *tw = reinterpret_cast<V *>(&tot);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) tw[ch] = bw[((size_t)ch * (nslots + 1) + k) * WPS + rr];
+#pragma unroll
+        for (int qq = 1; qq < NCLS; qq++) {
+            W o;
+            V *ow = reinterpret_cast<V *>(&o);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) ow[ch] = bw[((size_t)ch * (nslots + 1) + k) * WPS + qq * kRbRows + rr];
+            Op::merge(tot, o);
+        }
+        const RbBin<V, CLS> b = rb2_to_bin<V, CLS>(tot);
+        const size_t o = ((size_t)(r0 + rr) * K + k) * (size_t)p.ws_stride;  // record offset (words)
+        if constexpr (CLS <= RB_VAR) {
+            RbFlush<V, CLS>::flush(b, c0p + o, c1p + o, c2p + o, atomic);
+        } else {
+            RbFlush<V, CLS>::flush(b, c0p + o, c1p + o, p.index_offset, atomic);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ host
+struct Rb2Geometry {
+    bool ok;
+    int C, S, ent_cap, ntiles, nseg, tiles_per_seg, runs;
+    size_t smem, plan_bytes, plan_smem;
+};
+
+template <typename V, int CLS>
+static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
+    Rb2Geometry g = {};
+    constexpr int PER16 = 16 / (int)sizeof(V);
+    constexpr int NCLS = PER16;
+    if (K <= 0 || K > 65534 || n <= 0 || n >= ((int64_t)1 << 31) || (n % PER16) != 0 || rows < 1) return g;
+    if (getenv("NBG_RB2_OFF")) return g;
+    const size_t bins = rb2_bins_bytes<V, CLS>((int)K);
+    if (bins + 128 > kMaxSmemOptIn) return g;
+    const size_t avail = kMaxSmemOptIn - 128 - bins;
+    int S = 3, C = 0;
+    if (const char *e = getenv("NBG_RB2_S")) S = atoi(e);
+    if (S < 2) S = 2;
+    if (S > kRb2MaxStages) S = kRb2MaxStages;
+    auto fit = [&](int s) {
+        int c = 2048;
+        while (c >= 64 && (size_t)s * rb2_stage_bytes<V>(c, c + kRb2Pad) > avail) c -= 64;
+        return c >= 64 ? c : 0;
+    };
+    C = fit(S);
+    if (C < 256 && S > 2) {
+        S = 2;
+        C = fit(S);
+    }
+    if (const char *e = getenv("NBG_RB2_C")) C = atoi(e);
+    if (C < 128 || (C % PER16) != 0) return g;
+    // tiles never wider than the row (short rows: one tile)
+    const int64_t n_up = (n + 63) / 64 * 64;
+    if (C > n_up) C = (int)n_up;
+    g.C = C, g.S = S, g.ent_cap = C + kRb2Pad;
+    g.smem = rb2_smem_bytes<V, CLS>((int)K, C, g.ent_cap, S);
+    if (g.smem > kMaxSmemOptIn) return g;
+    g.plan_smem = (size_t)(2 * NCLS * K + 1) * 4 + (size_t)2 * C * 4 + 16;
+    if (g.plan_smem > kMaxSmem) return g;
+    g.ntiles = (int)((n + C - 1) / C);
+    const int64_t groups = (rows + kRbRows - 1) / kRbRows;
+    // one CTA per SM: whole rows per CTA once there are >= 4 waves of row groups, otherwise column
+    // segments (~8 waves) merged into the workspace with atomics
+    const int64_t slots = kNumSMs;
+    int64_t nseg = groups >= 4 * slots ? 1 : (8 * slots + groups - 1) / groups;
+    if (const char *e = getenv("NBG_RB2_NSEG")) nseg = atoi(e);
+    if (nseg > g.ntiles) nseg = g.ntiles;
+    if (nseg < 1) nseg = 1;
+    g.tiles_per_seg = (int)((g.ntiles + nseg - 1) / nseg);
+    g.nseg = (g.ntiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
+    g.plan_bytes = (size_t)g.ntiles * (kRbHdr + g.ent_cap) * 4 + 256;
+    // average run of equal labels inside a class range >= 2: accumulate runs in registers
+    g.runs = ((int64_t)C / NCLS >= 2 * K) ? 1 : 0;
+    if (const char *e = getenv("NBG_RB2_RUNS")) g.runs = atoi(e);
+    g.ok = true;
+    return g;
+}
+
+inline size_t rb2_scratch_bytes(int64_t n) {
+    // narrowest tile is 128 columns: header + padding per tile, 4 bytes per column
+    return (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * (kRbHdr + kRb2Pad) * 4 + 4096;
+}
+
+template <typename V, typename L, int CLS>
+static int rb2_launch(const V *values, const L *labels, void *ws_ch[3], int64_t ws_stride, void *scratch, size_t scratch_bytes,
+                      int64_t rows, int64_t n, int64_t K, int64_t index_offset, cudaStream_t stream, bool *handled) {
+    *handled = false;
+    constexpr int NCLS = 16 / (int)sizeof(V);
+    const Rb2Geometry g = rb2_geometry<V, CLS>(rows, n, K);
+    if (!g.ok || scratch == nullptr || scratch_bytes < g.plan_bytes + 256) return NBG_OK;
+    if (((uintptr_t)values & 15) != 0) return NBG_OK;
+    uint32_t *plan = reinterpret_cast<uint32_t *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    auto pk = group_plan2_kernel<L, NCLS>;
+    int rc = allow_big_smem(pk, "nbg_group(plan2): cudaFuncSetAttribute");
+    if (rc) return rc;
+    pk<<<(unsigned)g.ntiles, 256, g.plan_smem, stream>>>(labels, n, (int)K, g.C, g.ent_cap, 1, (int)sizeof(V), plan);
+    rc = check_launch("nbg_group(plan2)");
+    if (rc) return rc;
+    Rb2Params p;
+    p.values = values;
+    p.plan = plan;
+    p.ws_ch[0] = ws_ch[0], p.ws_ch[1] = ws_ch[1], p.ws_ch[2] = ws_ch[2];
+    p.ws_stride = ws_stride;
+    p.index_offset = index_offset;
+    p.rows = rows, p.n = n, p.K = (int)K, p.C = g.C, p.S = g.S, p.ent_cap = g.ent_cap;
+    p.ntiles = g.ntiles, p.tiles_per_seg = g.tiles_per_seg, p.nseg = g.nseg;
+    const int64_t groups = (rows + kRbRows - 1) / kRbRows;
+    if (groups * g.nseg > INT32_MAX) return NBG_OK;
+    auto launch = [&](auto kern) -> int {
+        int r2 = allow_big_smem(kern, "nbg_group(rowbins2): cudaFuncSetAttribute");
+        if (r2) return r2;
+        kern<<<(unsigned)(groups * g.nseg), kRb2Threads, g.smem, stream>>>(p);
+        return check_launch("nbg_group(rowbins2)");
+    };
+    rc = g.runs ? launch(group_rowbins2_kernel<V, CLS, true>) : launch(group_rowbins2_kernel<V, CLS, false>);
+    if (rc) return rc;
+    *handled = true;
+    return NBG_OK;
+}
+
+}  // namespace nbg

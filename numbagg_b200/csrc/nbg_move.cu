@@ -201,6 +201,8 @@ struct MoveParams {
     int window;     // halo must fit in shared memory on this path
     int min_count;  // already clamped per op, saturated to int
     int tiles_per_row;
+    int prefetch_dist;  // tiles ahead whose spans this CTA prefetches into L2 (0: off)
+    int64_t ntiles;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -311,6 +313,16 @@ __global__ void __launch_bounds__(THREADS) move_rowtile_kernel(MoveParams p) {
         mbar_arrive_expect_tx(bar, tx);
         if (pla.blk_bytes) bulk_g2s(sa + pla.blk_lo, row_a + p0 + pla.blk_lo, pla.blk_bytes, bar);
         if (NIN == 2 && plb.blk_bytes) bulk_g2s(sb + plb.blk_lo, row_b + p0 + plb.blk_lo, plb.blk_bytes, bar);
+    }
+    if (tid == 0 && p.prefetch_dist > 0) {
+        const int64_t tl = (int64_t)blockIdx.x + p.prefetch_dist;
+        if (tl < p.ntiles) {
+            const int64_t row2 = tl / p.tiles_per_row;
+            const int64_t c2 = (tl % p.tiles_per_row) * (int64_t)TILE;
+            // the tile proper; its halo is the tail of the preceding tile (fetched by that one)
+            span_prefetch_l2(reinterpret_cast<const T *>(p.a) + row2 * p.n, c2, TILE, p.n);
+            if (NIN == 2) span_prefetch_l2(reinterpret_cast<const T *>(p.b) + row2 * p.n, c2, TILE, p.n);
+        }
     }
     span_fill_edges<T, THREADS>(sa, row_a, p0, len, pla, quiet_nan<T>(), halo_a, p.halo_len);
     if (NIN == 2) span_fill_edges<T, THREADS>(sb, row_b, p0, len, plb, quiet_nan<T>(), halo_b, p.halo_len);
@@ -483,6 +495,8 @@ static int launch_rowtile(MoveParams p, int64_t outer, int64_t n, cudaStream_t s
     const int64_t tpr = (n + SM::TILE - 1) / SM::TILE;
     if (tpr * outer > INT32_MAX) return fail(NBG_ERR_UNSUPPORTED, "nbg_move: more than 2^31 tiles");
     p.tiles_per_row = (int)tpr;
+    p.ntiles = tpr * outer;
+    p.prefetch_dist = prefetch_distance(2);
     auto kern = move_rowtile_kernel<T, Op, THREADS, E, RCP>;
     int rc = allow_big_smem(kern, "nbg_move: cudaFuncSetAttribute");
     if (rc) return rc;

@@ -217,6 +217,7 @@ struct ScanParams {
     double min_weight;
     int64_t limit;
     int alpha_nd;  // alpha stream: 0 = 1-D shared by rows, 1 = per row
+    int prefetch_dist;  // tiles ahead whose input spans this CTA prefetches into L2 (0: off)
 };
 
 template <class P, int THREADS, int E>
@@ -279,6 +280,17 @@ __global__ void __launch_bounds__(THREADS, P::MIN_CTAS) scan_rowtile_kernel(Scan
 #pragma unroll
         for (int s = 0; s < NS; s++)
             if (pl[s].blk_bytes) bulk_g2s(s_[s] + pl[s].blk_lo, rows_[s] + p0 + pl[s].blk_lo, pl[s].blk_bytes, bar);
+    }
+    if (tid == 0 && p.prefetch_dist > 0) {
+        // keep HBM busy for the wave of CTAs that replaces this one: its TMA loads then hit L2
+        const int64_t tl = tile_lin + p.prefetch_dist;
+        if (tl < p.ntiles) {
+            const int64_t row2 = tl / p.tiles_per_row;
+            const int64_t c2 = (tl % p.tiles_per_row) * (int64_t)TILE;
+            const int64_t q0 = P::REV ? (p.n - c2 - TILE) : c2;
+#pragma unroll
+            for (int s = 0; s < NS; s++) span_prefetch_l2(P::stream_row(p, s, row2), q0, TILE, p.n);
+        }
     }
 #pragma unroll
     for (int s = 0; s < NS; s++)
@@ -370,6 +382,7 @@ static int launch_scan_rowtile(ScanParams p, int64_t rows, int64_t n, void *work
     p.tiles_per_row = (int)tpr;
     p.rows = rows;
     p.n = n;
+    p.prefetch_dist = prefetch_distance(P::MIN_CTAS);
     int rc = check_cuda(cudaMemsetAsync(p.ws_base, 0, (size_t)ntiles * sizeof(TileDesc<Agg>), stream), what);
     if (rc) return rc;
     auto kern = scan_rowtile_kernel<P, THREADS, E>;

@@ -27,3 +27,21 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Observed worst errors of every tolerance-class comparison (tests/_parity.py) -> a JSON file
+    next to the other GPU-run artefacts; profiles/ keeps the copy that is judged."""
+    try:
+        import json
+
+        from tests import _parity
+
+        if not _parity.OBSERVED:
+            return
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "parity_observed.json"), "w") as f:
+            json.dump(dict(sorted(_parity.OBSERVED.items())), f, indent=1)
+    except Exception:
+        pass

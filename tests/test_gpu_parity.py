@@ -272,9 +272,11 @@ def test_group_value_index_ops_across_column_segments(nb, dtype, rows, n, K):
         _group_check(nb, f, v, labels, num_labels=K, axis=-1)
 
 
-def test_group_rowbins_is_bit_exact_with_whole_rows(nb):
-    # >= 4 waves of 8-row groups => one CTA per row group walks whole rows in column order:
-    # float32 sums must then be IDENTICAL to the sequential reference, not just close
+def test_group_rowbins_legacy_is_bit_exact_with_whole_rows(nb, monkeypatch):
+    # The round-1 row-bins kernel (still the path of arg*/first/last/min/max and of bins that do
+    # not fit the class-private layout): >= 4 waves of 8-row groups => one CTA per row group walks
+    # whole rows in column order, so float32 sums are IDENTICAL to the sequential reference.
+    monkeypatch.setenv("NBG_RB2_OFF", "1")
     rows, n, K = 9600, 256, 37
     v = fixture_array((rows, n), dtype=np.float32, seed=21)
     labels = np.random.RandomState(21).randint(0, K, size=n)
@@ -282,6 +284,29 @@ def test_group_rowbins_is_bit_exact_with_whole_rows(nb):
         got = getattr(nb, f)(v, labels, num_labels=K, axis=-1)
         exp = getattr(oracle, f)(v, labels, num_labels=K, axis=-1)
         np.testing.assert_array_equal(got, exp, err_msg=f)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+@pytest.mark.parametrize("rows,n,K", [(9600, 256, 37), (64, 40_000, 1000), (17, 100_000, 1400), (3, 300_000, 5),
+                                      (1, 200_004, 600), (40, 4096, 1)])
+def test_group_rowbins2_class_private_bins(nb, dtype, rows, n, K):
+    # conflict-free class-private bins (nbg_group_rowbins2.cuh): whole rows per CTA, column
+    # segments merged with atomics (few rows), register runs (few labels), the dummy-padded
+    # plan (ragged last tile, labels outside [0, K)), every value dtype.  Counts / any / all and
+    # integer sums are exact; float sums differ from the reference only by summation order.
+    rs = np.random.RandomState(rows + K)
+    if np.dtype(dtype).kind == "f":
+        v = np.round((fixture_array((rows, n), dtype=dtype, seed=K) - 0.3) * 8, 3).astype(dtype)
+    else:
+        v = rs.randint(-50, 50, size=(rows, n)).astype(dtype)
+    labels = rs.randint(-1, K + 1, size=n)
+    fs = ["group_nansum", "group_nancount", "group_nansum_of_squares", "group_nanany", "group_nanall"]
+    if np.dtype(dtype).kind == "f":
+        fs += ["group_nanmean", "group_nanvar", "group_nanstd"]
+    for f in fs:
+        _group_check(nb, f, v, labels, num_labels=K, axis=-1)
+    vv = (1.0 + v / 64).astype(dtype) if np.dtype(dtype).kind == "f" else np.where(v % 7 == 0, 2, 1).astype(dtype)
+    _group_check(nb, "group_nanprod", vv, labels, num_labels=K, axis=-1)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32, np.int64])
