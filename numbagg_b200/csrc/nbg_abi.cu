@@ -18,7 +18,13 @@ int allow_big_smem_impl(const void *kern, const char *what) {
     const uint64_t key = (uint64_t)(uintptr_t)kern ^ ((uint64_t)(dev + 1) << 56);
     std::lock_guard<std::mutex> lock(mu);
     if (done.count(key)) return NBG_OK;
-    int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemOptIn), what);
+    // static + dynamic shared memory of a CTA may not exceed 227 KB
+    cudaFuncAttributes fa;
+    int rc = check_cuda(cudaFuncGetAttributes(&fa, kern), what);
+    if (rc) return rc;
+    size_t dyn = (size_t)227 * 1024 - fa.sharedSizeBytes;
+    if (dyn > kMaxSmemOptIn) dyn = kMaxSmemOptIn;
+    rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), what);
     if (rc) return rc;
     done.insert(key);
     return NBG_OK;

@@ -76,6 +76,46 @@ __device__ __forceinline__ long long sq_as_input(int64_t v) {
     return (long long)((unsigned long long)v * (unsigned long long)v);
 }
 
+// ---- L2 cache-policy hints -------------------------------------------------------------------
+// The accumulator table is the only data of the per-element-label path that is touched more than
+// once; its reductions carry an L2::evict_last policy (createpolicy) while the inputs stream
+// through with evict-first loads (__ldcs), so the table survives in L2 next to a 32 GB stream.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+struct L2Hint {
+    uint64_t pol;
+    bool on;
+};
+__device__ __forceinline__ void red_add(double *p, double v, const L2Hint &h) {
+    if (h.on) asm volatile("red.global.add.f64.L2::cache_hint [%0], %1, %2;" ::"l"(p), "d"(v), "l"(h.pol) : "memory");
+    else atomicAdd(p, v);
+}
+__device__ __forceinline__ void red_add(long long *p, long long v, const L2Hint &h) {
+    if (h.on) asm volatile("red.global.add.u64.L2::cache_hint [%0], %1, %2;" ::"l"(p), "l"(v), "l"(h.pol) : "memory");
+    else atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+}
+__device__ __forceinline__ void red_max(unsigned long long *p, unsigned long long v, const L2Hint &h) {
+    if (h.on) asm volatile("red.global.max.u64.L2::cache_hint [%0], %1, %2;" ::"l"(p), "l"(v), "l"(h.pol) : "memory");
+    else atomicMax(p, v);
+}
+__device__ __forceinline__ void red_max(long long *p, long long v, const L2Hint &h) {
+    if (h.on) asm volatile("red.global.max.s64.L2::cache_hint [%0], %1, %2;" ::"l"(p), "l"(v), "l"(h.pol) : "memory");
+    else atomicMax(p, v);
+}
+__device__ __forceinline__ void red_min(long long *p, long long v, const L2Hint &h) {
+    if (h.on) asm volatile("red.global.min.s64.L2::cache_hint [%0], %1, %2;" ::"l"(p), "l"(v), "l"(h.pol) : "memory");
+    else atomicMin(p, v);
+}
+__device__ __forceinline__ unsigned long long ld_hint(const unsigned long long *p, const L2Hint &h) {
+    if (!h.on) return *p;
+    unsigned long long v;
+    asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(h.pol) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void atomic_add_acc(double *p, double v) { atomicAdd(p, v); }
 __device__ __forceinline__ void atomic_add_acc(long long *p, long long v) {
     atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
@@ -111,7 +151,16 @@ struct WsLayout {
     int planar;   // 1: channels are separate (rows*K)-word planes
     int words;    // total 8-byte words per (row, label)
 };
-__host__ __device__ inline WsLayout ws_layout(int op) {
+// Tables larger than this cannot stay in L2 next to the input stream: multi-channel additive ops
+// then switch to one plane per channel and the per-element-label path makes one pass per plane
+// with that plane pinned in L2 (measured on config 5, 10 M labels: nanvar 97.8 ms interleaved ->
+// see DESIGN.md 4.3).
+constexpr size_t kL2TableBytes = (size_t)96 << 20;
+__host__ __device__ inline WsLayout ws_layout(int op, int64_t slots = 0) {
+    if ((op == NBG_GROUP_NANMEAN || op == NBG_GROUP_NANVAR || op == NBG_GROUP_NANSTD) &&
+        (size_t)slots * (op == NBG_GROUP_NANMEAN ? 16 : 32) > kL2TableBytes) {
+        return WsLayout{1, {0, 1, op == NBG_GROUP_NANMEAN ? 1 : 2}, 1, op == NBG_GROUP_NANMEAN ? 2 : 4};
+    }
     switch (op) {
         case NBG_GROUP_NANCOUNT:
             return WsLayout{1, {0, 0, 0}, 0, 1};  // count only (ch2)
@@ -136,7 +185,7 @@ struct GroupWs {
     int64_t stride;
     __host__ __device__ static GroupWs carve(void *base, int op, int64_t rows, int64_t K) {
         GroupWs w;
-        const WsLayout l = ws_layout(op);
+        const WsLayout l = ws_layout(op, rows * K);
         const size_t plane = l.planar ? (size_t)rows * (size_t)K : 1;
         for (int c = 0; c < 3; c++) w.ch[c] = static_cast<unsigned char *>(base) + (size_t)l.slot[c] * plane * 8;
         w.stride = l.stride;
@@ -148,12 +197,13 @@ struct GroupWs {
 __global__ void group_init_kernel(GroupWs ws, int op, int is_float, int64_t slots) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= slots) return;
-    const WsLayout l = ws_layout(op);
+    const WsLayout l = ws_layout(op, slots);
     unsigned long long *w0 = reinterpret_cast<unsigned long long *>(ws.ch[0]) + i * ws.stride;
     unsigned long long *w1 = reinterpret_cast<unsigned long long *>(ws.ch[1]) + i * ws.stride;
     if (l.planar) {
         *w0 = 0;
         *w1 = 0;
+        reinterpret_cast<unsigned long long *>(ws.ch[2])[i * ws.stride] = 0;  // third plane (var) or an alias
     } else {
         unsigned long long *rec = w0 - l.slot[0];
         for (int w = 0; w < l.stride; w++) rec[w] = 0;
@@ -181,11 +231,15 @@ __global__ void group_init_kernel(GroupWs ws, int op, int is_float, int64_t slot
 // --------------------------------------------------------------------- generic atomic kernel
 // PHASE 1 of arg* re-reads the data and records the smallest index whose key equals the
 // group's extreme; every other op has PHASE 0 only.
-template <typename V, typename L, int OP, int PHASE>
+// CHM: bit c set = this pass updates channel c (planar multi-pass of mean / var / std; 7 = all).
+template <typename V, typename L, int OP, int PHASE, int CHM = 7>
 __global__ void __launch_bounds__(256) group_atomic_kernel(const V *__restrict__ values, const L *__restrict__ labels,
                                                            int labels_per_row, GroupWs ws, int64_t rows, int64_t n,
-                                                           int64_t K, int64_t index_offset, int64_t blocks_per_row) {
+                                                           int64_t K, int64_t index_offset, int64_t blocks_per_row,
+                                                           int l2_hint) {
     using Acc = typename VTraits<V>::Acc;
+    L2Hint hint{0, l2_hint != 0};
+    if (hint.on) hint.pol = l2_policy_evict_last();
     const int64_t row = blockIdx.x / blocks_per_row;
     const int64_t blk = blockIdx.x % blocks_per_row;
     const V *vrow = values + row * n;
@@ -210,38 +264,38 @@ __global__ void __launch_bounds__(256) group_atomic_kernel(const V *__restrict__
         if (is_nan(v)) continue;
         const int64_t gi = index_offset + i;
         if (OP == NBG_GROUP_NANSUM) {
-            atomic_add_acc(c0 + label, (Acc)v);
+            red_add(c0 + label, (Acc)v, hint);
         } else if (OP == NBG_GROUP_NANMEAN) {
-            atomic_add_acc(c0 + label, (Acc)v);
-            atomic_add_acc(cnt + label, 1ll);
+            if (CHM & 1) red_add(c0 + label, (Acc)v, hint);
+            if (CHM & 4) red_add(cnt + label, 1ll, hint);
         } else if (OP == NBG_GROUP_NANCOUNT) {
-            atomic_add_acc(cnt + label, 1ll);
+            red_add(cnt + label, 1ll, hint);
         } else if (OP == NBG_GROUP_NANSUM_OF_SQUARES) {
-            atomic_add_acc(c0 + label, (Acc)sq_as_input(v));
+            red_add(c0 + label, (Acc)sq_as_input(v), hint);
         } else if (OP == NBG_GROUP_NANVAR || OP == NBG_GROUP_NANSTD) {
-            atomic_add_acc(c0 + label, (Acc)v);
-            atomic_add_acc(c1 + label, (Acc)sq_as_input(v));
-            atomic_add_acc(cnt + label, 1ll);
+            if (CHM & 1) red_add(c0 + label, (Acc)v, hint);
+            if (CHM & 2) red_add(c1 + label, (Acc)sq_as_input(v), hint);
+            if (CHM & 4) red_add(cnt + label, 1ll, hint);
         } else if (OP == NBG_GROUP_NANPROD) {
             atomic_mul_acc<V>(c0 + label, v);
         } else if (OP == NBG_GROUP_NANMAX) {
-            atomicMax(key0 + label, order_key((double)v));
+            red_max(key0 + label, order_key((double)v), hint);
         } else if (OP == NBG_GROUP_NANMIN) {
-            atomicMax(key0 + label, ~order_key((double)v));
+            red_max(key0 + label, ~order_key((double)v), hint);
         } else if (OP == NBG_GROUP_NANANY) {
             if (v != (V)0) reinterpret_cast<volatile long long *>(c0)[label] = 1;
         } else if (OP == NBG_GROUP_NANALL) {
             if (v == (V)0) reinterpret_cast<volatile long long *>(c0)[label] = 0;
         } else if (OP == NBG_GROUP_NANFIRST) {
-            atomicMin(idx1 + label, (long long)gi);
+            red_min(idx1 + label, (long long)gi, hint);
         } else if (OP == NBG_GROUP_NANLAST) {
-            atomicMax(idx1 + label, (long long)gi);
+            red_max(idx1 + label, (long long)gi, hint);
         } else if (OP == NBG_GROUP_NANARGMAX || OP == NBG_GROUP_NANARGMIN) {
             const unsigned long long k = OP == NBG_GROUP_NANARGMAX ? order_key((double)v) : ~order_key((double)v);
             if (PHASE == 0) {
-                atomicMax(key0 + label, k);
+                red_max(key0 + label, k, hint);
             } else {
-                if (k == key0[label]) atomicMin(idx1 + label, (long long)gi);
+                if (k == ld_hint(key0 + label, hint)) atomicMin(idx1 + label, (long long)gi);
             }
         }
     }
@@ -425,7 +479,7 @@ struct L2Window {
 static L2Window l2_window_begin(cudaStream_t st, void *base, size_t bytes) {
     L2Window w{st, false};
     const char *e = getenv("NBG_L2_PERSIST");
-    if (!e || atoi(e) == 0) return w;  // off unless asked for (see DESIGN.md 4.3 for the measurement)
+    if (!e || atoi(e) == 0) return w;  // opt-in: the set-aside it needs halves the scan kernels' throughput
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return w;
     int dev = 0, max_persist = 0, max_window = 0;
@@ -468,24 +522,46 @@ static int launch_atomic(const V *values, const L *labels, int labels_per_row, G
                          int64_t K, int64_t index_offset, cudaStream_t stream) {
     const int64_t bpr = (n + 2047) / 2048;
     if (bpr * rows > INT32_MAX) return fail(NBG_ERR_UNSUPPORTED, "nbg_group: grid too large");
-    // table bytes actually hammered by the atomics: the record planes this op uses
-    const L2Window l2 = l2_window_begin(stream, ws.ch[0] < ws.ch[2] ? ws.ch[0] : ws.ch[2],
-                                        (size_t)ws_layout(OP).words * (size_t)rows * (size_t)K * 8);
-    struct L2Guard {
-        const L2Window &w;
-        ~L2Guard() { l2_window_end(w); }
-    } l2_guard{l2};
-    group_atomic_kernel<V, L, OP, 0><<<(unsigned)(bpr * rows), 256, 0, stream>>>(values, labels, labels_per_row, ws,
-                                                                                  rows, n, K, index_offset, bpr);
-    int rc = check_launch("nbg_group(atomic)");
+    const unsigned grid = (unsigned)(bpr * rows);
+    const size_t plane_bytes = (size_t)rows * (size_t)K * 8;
+    const WsLayout lay = ws_layout(OP, rows * K);
+    // evict_last hints on the table reductions: config 5 nansum 22.9 -> 12.6 ms, nanfirst 49.7 -> 11.6 ms,
+    // no device-wide state (NBG_L2_HINT=0 switches them off for A/B runs)
+    int l2_hint = 1;
+    if (const char *e = getenv("NBG_L2_HINT")) l2_hint = atoi(e);
+    // one pass with the L2 window `win` over the table bytes that pass hammers with atomics
+    auto pass = [&](auto kern, void *win, size_t win_bytes, const char *what) -> int {
+        const L2Window l2 = l2_window_begin(stream, win, win_bytes);
+        kern<<<grid, 256, 0, stream>>>(values, labels, labels_per_row, ws, rows, n, K, index_offset, bpr, l2_hint);
+        const int rc = check_launch(what);
+        l2_window_end(l2);
+        return rc;
+    };
+    int rc;
+    constexpr bool kMean = OP == NBG_GROUP_NANMEAN, kVar = OP == NBG_GROUP_NANVAR || OP == NBG_GROUP_NANSTD;
+    if ((kMean || kVar) && lay.planar) {
+        // table too large for L2: one pass per channel plane, that plane pinned
+        rc = pass(group_atomic_kernel<V, L, OP, 0, 1>, ws.ch[0], plane_bytes, "nbg_group(atomic, sum plane)");
+        if (rc) return rc;
+        if (kVar) {
+            rc = pass(group_atomic_kernel<V, L, OP, 0, 2>, ws.ch[1], plane_bytes, "nbg_group(atomic, sum-of-squares plane)");
+            if (rc) return rc;
+        }
+        return pass(group_atomic_kernel<V, L, OP, 0, 4>, ws.ch[2], plane_bytes, "nbg_group(atomic, count plane)");
+    }
+    constexpr bool kArg = OP == NBG_GROUP_NANARGMAX || OP == NBG_GROUP_NANARGMIN;
+    constexpr bool kEdge = OP == NBG_GROUP_NANFIRST || OP == NBG_GROUP_NANLAST;
+    // arg*: both phases hammer / probe the key plane; first / last: the index plane; others: the table
+    void *win = kEdge ? ws.ch[1] : ws.ch[0];
+    if (OP == NBG_GROUP_NANCOUNT) win = ws.ch[2];
+    const size_t win_bytes = (kArg || kEdge) ? plane_bytes : (size_t)lay.words * plane_bytes;
+    rc = pass(group_atomic_kernel<V, L, OP, 0>, win, win_bytes, "nbg_group(atomic)");
     if (rc) return rc;
-    if (OP == NBG_GROUP_NANARGMAX || OP == NBG_GROUP_NANARGMIN) {
-        group_atomic_kernel<V, L, OP, 1><<<(unsigned)(bpr * rows), 256, 0, stream>>>(values, labels, labels_per_row,
-                                                                                      ws, rows, n, K, index_offset, bpr);
-        rc = check_launch("nbg_group(atomic, index phase)");
+    if (kArg) {
+        rc = pass(group_atomic_kernel<V, L, OP, 1>, win, win_bytes, "nbg_group(atomic, index phase)");
         if (rc) return rc;
     }
-    if (OP == NBG_GROUP_NANFIRST || OP == NBG_GROUP_NANLAST) {
+    if (kEdge) {
         group_gather_kernel<V><<<blocks_for(rows * K, 256), 256, 0, stream>>>(values, ws, rows, n, K, index_offset);
         rc = check_launch("nbg_group(gather)");
     }
@@ -594,7 +670,7 @@ static bool float_only(int op) {
 }  // namespace nbg
 
 static size_t group_state_bytes(int op, int64_t rows, int64_t num_labels) {
-    return (size_t)nbg::ws_layout(op).words * (size_t)rows * (size_t)num_labels * 8 + 256;
+    return (size_t)nbg::ws_layout(op, rows * num_labels).words * (size_t)rows * (size_t)num_labels * 8 + 256;
 }
 extern "C" int nbg_group_record_words(int op) { return nbg::ws_layout(op).words; }
 // scratch for the shared-label plan: 4 bytes per column + one header per (smallest) tile

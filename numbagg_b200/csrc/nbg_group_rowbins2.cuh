@@ -21,12 +21,25 @@
 //     kernel, see DESIGN.md.)
 //   * the column plan (built once per call from the labels, shared by all rows) lists, per tile
 //     and class, the valid columns stably sorted by label, cut into 64/NCLS label-aligned
-//     balanced ranges, each padded to a multiple of 4 entries so that a sub-warp fetches four
-//     entries with one 16-byte load.  No atomics anywhere: a label range belongs to one sub-warp
-//     per tile and its bins to one lane.
+//     ranges, each padded to a multiple of 4 entries so that a sub-warp fetches four entries
+//     with one 16-byte load.  No atomics anywhere: a label range belongs to one sub-warp per
+//     tile and its bins to one lane.
+//   * RANGES MOVE ONLY BETWEEN NEIGHBOURS: the ranges of a tile are balanced per tile (every
+//     sub-warp gets the same number of entries, so the 4 sub-warps of a warp -- which execute in
+//     lock step -- waste no lanes), but boundary j is clamped into a fixed window around its
+//     NOMINAL position (cut so that the ranges' shares of all n columns are equal: one global
+//     histogram pass over the labels), and the windows of adjacent boundaries do not overlap.
+//     A label can therefore only ever belong to range j-1 or j (or j and j+1) -- two sub-warps
+//     that live in ADJACENT warps.  A warp starts tile t+1 only after both neighbour warps have
+//     finished tile t (two mbarriers per warp, used alternately: arrive = release, try_wait =
+//     acquire, hardware sleep instead of polling the shared-memory pipe this kernel is bound
+//     by); there is no CTA-wide barrier per tile, and non-adjacent warps drift apart by up to
+//     S-1 tiles.
 // Row tiles and plan blocks stream through an S-stage TMA ring (cp.async.bulk + mbarrier) filled by
-// a dedicated producer warp; consumer warps hand stages back through `empty` mbarriers, so there
-// is no CTA-wide barrier per tile and warps drift apart by up to S-1 tiles.
+// a dedicated producer warp, which also prefetches the tiles a few stages further ahead into L2
+// (cp.async.bulk.prefetch.L2): the bins leave room for only ~90 KB of staging, less than the
+// bytes-in-flight HBM latency needs, so DRAM reads are decoupled from the ring.  Consumer warps
+// hand stages back through `empty` mbarriers; there is no CTA-wide barrier per tile.
 // With few labels (runs of equal labels inside a range) the sub-warp accumulates a run in
 // registers and touches the bin once per run (RUNS).
 //
@@ -43,6 +56,7 @@ constexpr int kRb2Consumers = kRbThreads;        // 512 consumer threads = 64 su
 constexpr int kRb2Threads = kRb2Consumers + 32;  // + one producer warp
 constexpr int kRb2Pad = 64 * 3;                  // worst-case padding entries per tile
 constexpr int kRb2MaxStages = 4;
+constexpr int kRb2Header = 384;  // mbarriers: full[4], empty[4], done[16][2]
 
 // ---------------------------------------------------------------------------------- channel ops
 // Words have the size of V (float/int32 -> 4 bytes, double/int64 -> 8 bytes); counters are the
@@ -168,9 +182,70 @@ __device__ __forceinline__ RbBin<V, CLS> rb2_to_bin(const typename Rb2Op<V, CLS>
 // kernel forms each shared-memory address with one or two integer instructions.  Padding entries
 // point at the dummy slot `nslots` and at column q (same class, always inside the tile).  A CTA of a cluster of `nc` owns the labels with
 // label % nc == rank and addresses them as slot = label / nc; its plan lists only those.
+// Global label histogram per column class (hist[class * K + label], zeroed by the caller).
+template <typename L, int NCLS>
+__global__ void __launch_bounds__(256) group_hist2_kernel(const L *__restrict__ labels, int64_t n, int K,
+                                                          int *__restrict__ hist) {
+    const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t i = i0 + k;
+        if (i >= n) break;
+        const long long lab = (long long)labels[i];
+        if (lab >= 0 && lab < K) atomicAdd(&hist[(int)(i % NCLS) * K + (int)lab], 1);
+    }
+}
+// cuts[q * (G + 1) + g] = first label of group g's interval in class q (g = 0..G; [G] = K): the
+// smallest label whose exclusive prefix count reaches g/G of the class total.
+__global__ void __launch_bounds__(256) group_cuts2_kernel(const int *__restrict__ hist, int K, int ncls, int G,
+                                                          int *__restrict__ cuts) {
+    extern __shared__ int pre[];  // [K + 1] exclusive prefix of one class
+    __shared__ int wtot[8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int q = 0; q < ncls; q++) {
+        const int per = (K + 255) / 256;
+        const int beg = min(tid * per, K), end = min(beg + per, K);
+        int local = 0;
+        for (int k = beg; k < end; k++) local += hist[q * K + k];
+        int inc = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) wtot[wid] = inc;
+        __syncthreads();
+        int base = 0;
+        for (int w2 = 0; w2 < wid; w2++) base += wtot[w2];
+        int run = base + inc - local;
+        for (int k = beg; k < end; k++) {
+            pre[k] = run;
+            run += hist[q * K + k];
+        }
+        if (tid == 255) pre[K] = run;
+        __syncthreads();
+        if (tid <= G) {
+            int cut = K;
+            if (tid < G) {
+                const long long target = ((long long)tid * pre[K]) / G;
+                int lo = 0, hi = K;  // first label with pre[label] >= target
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (pre[mid] >= target) hi = mid;
+                    else lo = mid + 1;
+                }
+                cut = tid == 0 ? 0 : lo;
+            }
+            cuts[q * (G + 1) + tid] = cut;
+        }
+        __syncthreads();
+    }
+}
+
 template <typename L, int NCLS>
 __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ labels, int64_t n, int K, int C,
-                                                          int ent_cap, int nc, int vsize, uint32_t *__restrict__ plan) {
+                                                          int ent_cap, int nc, int vsize, const int *__restrict__ cuts,
+                                                          uint32_t *__restrict__ plan) {
     constexpr int SUBS = 64 / NCLS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int NK = NCLS * K;
@@ -246,7 +321,8 @@ __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ 
         }
     }
     __syncthreads();
-    // label-aligned balanced ranges per class (unpadded positions)
+    // ranges (unpadded positions), balanced per tile; the first label of range j is clamped into
+    // [M(j-1), M(j)], M(j) = midpoint of the nominal cuts j and j+1 (cuts[q][0] = 0, cuts[q][SUBS] = K)
     if (tid <= 64) {
         int b;
         if (tid == 64) {
@@ -254,13 +330,18 @@ __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ 
         } else {
             const int q = tid / SUBS, j = tid % SUBS;
             const int cs = offs[q * K], ce = offs[(q + 1) * K];
-            if (j == 0 || ce == cs) {
+            if (j == 0) {
                 b = cs;
             } else {
-                const int e = cs + (int)(((long long)j * (ce - cs)) / SUBS);
-                const uint32_t ent = sent[e];
-                const int lab = (int)(ent & 0xffffu) * nc + rank;
-                b = offs[q * K + lab];  // start of the label run containing e
+                const int *cq = cuts + q * (SUBS + 1);
+                const int m_lo = (cq[j - 1] + cq[j]) >> 1, m_hi = (cq[j] + cq[j + 1]) >> 1;
+                int lab = cq[j];
+                if (ce > cs) {
+                    const int e = cs + (int)(((long long)j * (ce - cs)) / SUBS);
+                    lab = (int)(sent[e] & 0xffffu) * nc + rank;  // label of the entry at the even split
+                }
+                lab = max(m_lo, min(lab, m_hi));
+                b = offs[q * K + lab];  // first entry of that label in this tile (lab == K: end of class)
             }
         }
         ub[tid] = b;
@@ -309,6 +390,7 @@ struct Rb2Params {
     int64_t rows, n;
     int K, C, S, ent_cap;
     int ntiles, tiles_per_seg, nseg;
+    int PD;  // tiles beyond the ring that the producer prefetches into L2 (0: off)
     int64_t index_offset;
 };
 
@@ -322,7 +404,7 @@ __host__ __device__ inline size_t rb2_bins_bytes(int nslots) {
 }
 template <typename V, int CLS>
 __host__ __device__ inline size_t rb2_smem_bytes(int nslots, int C, int ent_cap, int S) {
-    return 128 + rb2_bins_bytes<V, CLS>(nslots) + (size_t)S * rb2_stage_bytes<V>(C, ent_cap);
+    return kRb2Header + rb2_bins_bytes<V, CLS>(nslots) + (size_t)S * rb2_stage_bytes<V>(C, ent_cap);
 }
 
 template <typename V, int CLS, bool RUNS>
@@ -337,7 +419,8 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);       // [S]
     uint64_t *empty = full + kRb2MaxStages;                        // [S]
-    unsigned char *bins = smem_raw + 128;
+    uint64_t *done = empty + kRb2MaxStages;                        // [16][2]: warp w finished a tile of parity b
+    unsigned char *bins = smem_raw + kRb2Header;
     const int C = p.C, K = p.K, S = p.S;
     const int nslots = K;  // single-CTA ownership: slot == label
     const size_t bins_bytes = rb2_bins_bytes<V, CLS>(nslots);
@@ -366,6 +449,7 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
             for (int i = tid; i < (nslots + 1) * WPS; i += kRb2Threads) bw[(size_t)ch * (nslots + 1) * WPS + i] = zw[ch];
     }
     if (tid == 0) {
+        for (int w2 = 0; w2 < 2 * (kRb2Consumers / 32); w2++) mbar_init(&done[w2], 1);
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kRb2Consumers / 32);
@@ -391,6 +475,14 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
                 V *tile = reinterpret_cast<V *>(sb + (size_t)(kRbHdr + p.ent_cap) * 4);
                 for (int rr = 0; rr < nrows; rr++)
                     bulk_g2s(tile + (size_t)rr * stride, vbase + (int64_t)rr * p.n + c0, row_bytes, &full[st]);
+                // L2 prefetch of the tile PD steps ahead (first step: everything up to it)
+                if (p.PD > 0) {
+                    for (int t2 = (it == 0 ? t + 1 : t + p.PD); t2 <= t + p.PD && t2 < t_end; t2++) {
+                        const int64_t d0 = (int64_t)t2 * C;
+                        const uint32_t db = (uint32_t)min((int64_t)C, p.n - d0) * (uint32_t)sizeof(V);
+                        for (int rr = 0; rr < nrows; rr++) bulk_prefetch_l2(vbase + (int64_t)rr * p.n + d0, db);
+                    }
+                }
             }
         }
     } else {
@@ -401,8 +493,19 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
         const int j = sub / NCLS;   // its label range within the class
         const uint32_t bins_s = smem_u32(bins) + (uint32_t)(q * kRbRows + r) * (uint32_t)sizeof(V);
         const bool active = r < nrows;
+        const int wrp = tid >> 5;
         for (int it = 0; it < ntl; it++) {
             const int st = it % S;
+            if (it > 0) {
+                // labels move only between ADJACENT ranges from one tile to the next: both neighbour
+                // warps must have finished the previous tile before this one touches its bins
+                // (a neighbour is never more than one tile ahead of this wait, so the two barriers of a
+                // warp cannot alias phases)
+                const int tp = it - 1;
+                const uint32_t par = (uint32_t)((tp >> 1) & 1);
+                if (wrp > 0) mbar_wait(&done[2 * (wrp - 1) + (tp & 1)], par);
+                if (wrp < kRb2Consumers / 32 - 1) mbar_wait(&done[2 * (wrp + 1) + (tp & 1)], par);
+            }
             mbar_wait(&full[st], (uint32_t)((it / S) & 1));
             const uint32_t sb = smem_u32(stage0 + (size_t)st * stage_bytes);
             const uint32_t *hdr = reinterpret_cast<const uint32_t *>(__cvta_shared_to_generic(sb));
@@ -468,7 +571,10 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
                 }
             }
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty[st]);  // this warp is done with stage st
+            if ((tid & 31) == 0) {
+                mbar_arrive(&done[2 * wrp + (it & 1)]);  // release: this warp's bin updates of tile `it`
+                mbar_arrive(&empty[st]);                 // and it is done with stage st
+            }
         }
     }
     __syncthreads();
@@ -508,8 +614,8 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
 // ------------------------------------------------------------------------------------ host
 struct Rb2Geometry {
     bool ok;
-    int C, S, ent_cap, ntiles, nseg, tiles_per_seg, runs;
-    size_t smem, plan_bytes, plan_smem;
+    int C, S, ent_cap, ntiles, nseg, tiles_per_seg, runs, PD;
+    size_t smem, plan_bytes, plan_smem, aux_bytes;
 };
 
 template <typename V, int CLS>
@@ -520,8 +626,8 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
     if (K <= 0 || K > 65534 || n <= 0 || n >= ((int64_t)1 << 31) || (n % PER16) != 0 || rows < 1) return g;
     if (getenv("NBG_RB2_OFF")) return g;
     const size_t bins = rb2_bins_bytes<V, CLS>((int)K);
-    if (bins + 128 > kMaxSmemOptIn) return g;
-    const size_t avail = kMaxSmemOptIn - 128 - bins;
+    if (bins + kRb2Header > kMaxSmemOptIn) return g;
+    const size_t avail = kMaxSmemOptIn - kRb2Header - bins;
     int S = 3, C = 0;
     if (const char *e = getenv("NBG_RB2_S")) S = atoi(e);
     if (S < 2) S = 2;
@@ -561,13 +667,17 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
     // average run of equal labels inside a class range >= 2: accumulate runs in registers
     g.runs = ((int64_t)C / NCLS >= 2 * K) ? 1 : 0;
     if (const char *e = getenv("NBG_RB2_RUNS")) g.runs = atoi(e);
+    g.PD = 0;  // measured: no gain on config 2 (the ring already covers the latency at this rate)
+    if (const char *e = getenv("NBG_RB2_PD")) g.PD = atoi(e);
+    // global histogram per class + group cuts (ints)
+    g.aux_bytes = ((size_t)NCLS * K + (size_t)NCLS * 33 + 64) * 4;
     g.ok = true;
     return g;
 }
 
 inline size_t rb2_scratch_bytes(int64_t n) {
     // narrowest tile is 128 columns: header + padding per tile, 4 bytes per column
-    return (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * (kRbHdr + kRb2Pad) * 4 + 4096;
+    return (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * (kRbHdr + kRb2Pad) * 4 + 4096 + ((size_t)4 * 65536 + 256) * 4;
 }
 
 template <typename V, typename L, int CLS>
@@ -576,13 +686,25 @@ static int rb2_launch(const V *values, const L *labels, void *ws_ch[3], int64_t 
     *handled = false;
     constexpr int NCLS = 16 / (int)sizeof(V);
     const Rb2Geometry g = rb2_geometry<V, CLS>(rows, n, K);
-    if (!g.ok || scratch == nullptr || scratch_bytes < g.plan_bytes + 256) return NBG_OK;
+    if (!g.ok || scratch == nullptr || scratch_bytes < g.plan_bytes + g.aux_bytes + 512) return NBG_OK;
     if (((uintptr_t)values & 15) != 0) return NBG_OK;
     uint32_t *plan = reinterpret_cast<uint32_t *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
-    auto pk = group_plan2_kernel<L, NCLS>;
-    int rc = allow_big_smem(pk, "nbg_group(plan2): cudaFuncSetAttribute");
+    int *hist = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(plan) + ((g.plan_bytes + 255) & ~(size_t)255));
+    int *cuts = hist + (size_t)NCLS * K;
+    constexpr int SUBS = 64 / NCLS;  // ranges per class
+    // labels only: global per-class histogram -> group cuts -> per-tile plan
+    int rc = check_cuda(cudaMemsetAsync(hist, 0, (size_t)NCLS * K * sizeof(int), stream), "nbg_group(hist2): memset");
     if (rc) return rc;
-    pk<<<(unsigned)g.ntiles, 256, g.plan_smem, stream>>>(labels, n, (int)K, g.C, g.ent_cap, 1, (int)sizeof(V), plan);
+    group_hist2_kernel<L, NCLS><<<(unsigned)((n + 1023) / 1024), 256, 0, stream>>>(labels, n, (int)K, hist);
+    rc = check_launch("nbg_group(hist2)");
+    if (rc) return rc;
+    group_cuts2_kernel<<<1, 256, (size_t)(K + 1) * sizeof(int), stream>>>(hist, (int)K, NCLS, SUBS, cuts);
+    rc = check_launch("nbg_group(cuts2)");
+    if (rc) return rc;
+    auto pk = group_plan2_kernel<L, NCLS>;
+    rc = allow_big_smem(pk, "nbg_group(plan2): cudaFuncSetAttribute");
+    if (rc) return rc;
+    pk<<<(unsigned)g.ntiles, 256, g.plan_smem, stream>>>(labels, n, (int)K, g.C, g.ent_cap, 1, (int)sizeof(V), cuts, plan);
     rc = check_launch("nbg_group(plan2)");
     if (rc) return rc;
     Rb2Params p;
@@ -593,6 +715,7 @@ static int rb2_launch(const V *values, const L *labels, void *ws_ch[3], int64_t 
     p.index_offset = index_offset;
     p.rows = rows, p.n = n, p.K = (int)K, p.C = g.C, p.S = g.S, p.ent_cap = g.ent_cap;
     p.ntiles = g.ntiles, p.tiles_per_seg = g.tiles_per_seg, p.nseg = g.nseg;
+    p.PD = g.PD;
     const int64_t groups = (rows + kRbRows - 1) / kRbRows;
     if (groups * g.nseg > INT32_MAX) return NBG_OK;
     auto launch = [&](auto kern) -> int {

@@ -71,14 +71,27 @@ def main():
     steps = 10
     if "--steps" in sys.argv:
         steps = int(sys.argv[sys.argv.index("--steps") + 1])
+    if "persist" in args:
+        # trigger the persisting-L2 set-aside (per-element-label path) BEFORE timing unrelated kernels
+        v = gen((1, 50_000_000), torch.float64, 0.1)
+        lab = torch.randint(0, 1_000_000, (50_000_000,), device=dev, dtype=torch.int64)
+        D.run_group("group_nansum", v, lab, 1_000_000, 1)
+        torch.cuda.synchronize()
+        del v, lab
     if "cfg2" in args:
         rows, n, K = 10_000, 1_000_000, 1000
         a = gen((rows, n), torch.float32, 0.1)
         labels = torch.from_numpy(np.random.RandomState(0).randint(0, K, size=n)).to(dev)
         ab = rows * n * 4 + n * 8 + rows * K * 4
-        rb2 = [dict(NBG_RB2_OFF=1), dict(NBG_RB2_S=2), dict(NBG_RB2_S=3), dict(NBG_RB2_S=4),
-               dict(NBG_RB2_S=3, NBG_RB2_C=512), dict(NBG_RB2_S=2, NBG_RB2_C=1024), dict(NBG_RB2_S=3, NBG_RB2_NSEG=2)]
-        for f, sets in (("group_nansum", rb2), ("group_nancount", [rb2[0], rb2[2]]), ("group_nansum_of_squares", [rb2[0], rb2[2]]),
+        rb2 = [dict(NBG_RB2_OFF=1), dict(NBG_RB2_S=3)]
+        if "sweep" in args:
+            for S in (2, 3):
+                for NSEG in (1, 2, 3, 4):
+                    rb2.append(dict(NBG_RB2_S=S, NBG_RB2_NSEG=NSEG))
+            rb2.append(dict(NBG_RB2_S=2, NBG_RB2_PD=4))
+            rb2.append(dict(NBG_RB2_S=2, NBG_RB2_C=1536))
+            rb2.append(dict(NBG_RB2_S=2, NBG_RB2_C=1280))
+        for f, sets in (("group_nansum", rb2), ("group_nancount", rb2[:2]), ("group_nansum_of_squares", rb2[:2]),
                         ("group_nanmean", [{}]), ("group_nanstd", [{}]), ("group_nanmax", [{}]), ("group_nanargmax", [{}])):
             run("cfg2_" + f, lambda: D.run_group(f, a, labels, K, 1), ab, sets, steps)
         # 1/8 of the rows: the per-GPU share of the strong-scaled config at N=8
@@ -126,13 +139,14 @@ def main():
         ab = n * 16 + K * 8
         v2 = a.view(1, -1)
         for f in ("group_nansum", "group_nanvar", "group_nanargmax", "group_nanfirst"):
-            run("cfg5_" + f, lambda: D.run_group(f, v2, labels, K, 1), ab, [dict(NBG_L2_PERSIST=0), dict(NBG_L2_PERSIST=1)], max(3, steps // 3))
+            run("cfg5_" + f, lambda: D.run_group(f, v2, labels, K, 1), ab, [dict(NBG_L2_PERSIST=0, NBG_L2_HINT=0), dict(NBG_L2_PERSIST=0, NBG_L2_HINT=1), dict(NBG_L2_PERSIST=1, NBG_L2_HINT=0)], max(3, steps // 3))
+        run("cfg5_group_nanmean", lambda: D.run_group("group_nanmean", v2, labels, K, 1), ab, [dict(NBG_L2_HINT=1)], 3)
         lab32 = labels.to(torch.int32)
-        run("cfg5_group_nansum_i32labels", lambda: D.run_group("group_nansum", v2, lab32, K, 1), n * 12 + K * 8, [dict(NBG_L2_PERSIST=1)], 3)
+        run("cfg5_group_nansum_i32labels", lambda: D.run_group("group_nansum", v2, lab32, K, 1), n * 12 + K * 8, [dict(NBG_L2_HINT=1)], 3)
         del lab32
         torch.cuda.empty_cache()
         slab = labels.sort().values
-        run("cfg5_group_nansum_sorted", lambda: D.run_group("group_nansum", v2, slab, K, 1), ab, [dict(NBG_L2_PERSIST=1)], 3)
+        run("cfg5_group_nansum_sorted", lambda: D.run_group("group_nansum", v2, slab, K, 1), ab, [dict(NBG_L2_HINT=1)], 3)
 
 
 if __name__ == "__main__":
