@@ -147,6 +147,20 @@ int nbg_fill(int dir, int itemsize, const void *a, void *out, int64_t outer, int
              int64_t inner, int64_t limit, const int64_t *carry_in, int64_t *agg_out,
              void *workspace, size_t workspace_bytes, void *stream);
 size_t nbg_fill_workspace_bytes(int itemsize, int64_t outer, int64_t n, int64_t inner);
+/*
+ * Single-pass core-axis sharding of ffill / bfill (one read + one write per element instead of
+ * an aggregate pass followed by a scan pass).  Step 1: nbg_fill() with carry_in = the SENTINEL
+ * carry {1, nbg_fill_sentinel_bits(itemsize), 0}: the result is final everywhere except in the
+ * leading (bfill: trailing) NaN run of the shard, which now holds the sentinel -- a NaN payload
+ * that no output can otherwise contain, because inputs that are NaN are never copied.  Step 2,
+ * after the shards' aggregates have been exchanged and folded into `carry` ((outer, 3) int64,
+ * same words as carry_in): nbg_fill_patch() rewrites the sentinel run in place -- the carried
+ * value while `dist + position + 1 <= limit`, NaN afterwards.  It reads one element per 4096
+ * outside that run.  inner must be 1.
+ */
+uint64_t nbg_fill_sentinel_bits(int itemsize);
+int nbg_fill_patch(int dir, int itemsize, void *out, int64_t outer, int64_t n, int64_t inner,
+                   int64_t limit, const int64_t *carry, void *stream);
 
 /*
  * Grouped reductions.  Replaces the loops "(a..),(a..),(z)" / "(a..),(a..),(),(z)" built by
@@ -170,6 +184,12 @@ size_t nbg_fill_workspace_bytes(int itemsize, int64_t outer, int64_t n, int64_t 
  */
 #define NBG_GROUP_WS_CHANNELS 4 /* upper bound of nbg_group_record_words() */
 int nbg_group_record_words(int op); /* 8-byte slots per (row, label) record: 1, 2 or 4 */
+/* Where the channels of an op's record live for a (rows, num_labels) table, so that a caller can
+ * run collectives on single channels: layout[0] = stride between records in 8-byte words,
+ * layout[1..3] = offset of channel 0..2 in 8-byte words from the (256-byte aligned) state base,
+ * layout[4] = 1 when channels are separate planes (offsets are multiples of rows*num_labels).
+ * Channels per op: DESIGN.md "group workspace". */
+int nbg_group_record_layout(int op, int64_t rows, int64_t num_labels, int64_t layout[5]);
 size_t nbg_group_workspace_bytes(int op, int vdtype, int64_t rows, int64_t n, int64_t num_labels);
 int nbg_group_init(int op, int vdtype, void *workspace, int64_t rows, int64_t num_labels,
                    void *stream);

@@ -55,7 +55,10 @@ _SIGNATURES = {
     "nbg_move_exp_workspace_bytes": (_sz, [_int, _int, _i64, _i64, _i64]),
     "nbg_fill": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "nbg_fill_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
+    "nbg_fill_sentinel_bits": (ctypes.c_uint64, [_int]),
+    "nbg_fill_patch": (_int, [_int, _int, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "nbg_group_record_words": (_int, [_int]),
+    "nbg_group_record_layout": (_int, [_int, _i64, _i64, ctypes.POINTER(_i64)]),
     "nbg_group_workspace_bytes": (_sz, [_int, _int, _i64, _i64, _i64]),
     "nbg_group_init": (_int, [_int, _int, _vp, _i64, _i64, _vp]),
     "nbg_group_accumulate": (_int, [_int, _int, _int, _vp, _vp, _int, _vp, _sz, _i64, _i64, _i64, _i64, _vp]),

@@ -152,6 +152,38 @@ __global__ void __launch_bounds__(256) fill_colwalk_kernel(FillColParams p) {
     }
 }
 
+// ---------------------------------------------------------------- sentinel patch (sharding)
+// See include/nbg_b200.h: after a shard has been filled with the sentinel carry, only its leading
+// (scan-order) run of sentinel values depends on the predecessors.  One CTA per 4096 scan
+// positions; a CTA whose first position is not the sentinel lies beyond the run and leaves.
+constexpr unsigned long long kFillSentinel64 = 0x7ff8dead5e171e1dull;
+constexpr unsigned long long kFillSentinel32 = 0x7fc5e171ull;
+template <typename T>
+__device__ __forceinline__ unsigned long long fill_sentinel() {
+    return sizeof(T) == 8 ? kFillSentinel64 : kFillSentinel32;
+}
+constexpr int kPatchTile = 4096;
+
+template <typename T, bool REV>
+__global__ void __launch_bounds__(256) fill_patch_kernel(T *__restrict__ out, int64_t n, int64_t tiles_per_row, int64_t limit,
+                                                         const int64_t *__restrict__ carry) {
+    const int64_t row = blockIdx.x / tiles_per_row;
+    const int64_t c0 = (blockIdx.x % tiles_per_row) * (int64_t)kPatchTile;  // scan-order start
+    T *o = out + row * n;
+    auto at = [&](int64_t k) -> T * { return o + (REV ? (n - 1 - k) : k); };
+    if (to_bits(*at(c0)) != fill_sentinel<T>()) return;  // the sentinel run is a prefix in scan order
+    const int64_t has = carry[row * NBG_FILL_STATE + 0];
+    const unsigned long long bits = (unsigned long long)carry[row * NBG_FILL_STATE + 1];
+    const int64_t dist = carry[row * NBG_FILL_STATE + 2];
+    for (int j = threadIdx.x; j < kPatchTile; j += 256) {
+        const int64_t k = c0 + j;
+        if (k >= n) break;
+        T *p = at(k);
+        if (to_bits(*p) != fill_sentinel<T>()) continue;
+        *p = (has && dist + k + 1 <= limit) ? from_bits<T>(bits) : quiet_nan<T>();
+    }
+}
+
 template <typename T>
 struct FillTile;
 template <>
@@ -213,4 +245,32 @@ extern "C" int nbg_fill(int dir, int itemsize, const void *a, void *out, int64_t
     if (itemsize == 8)
         return launch_fill<double>(dir, a, out, outer, n, inner, limit, carry_in, agg_out, workspace, workspace_bytes, st);
     return fail(NBG_ERR_BAD_DTYPE, "nbg_fill: itemsize must be 4 (float32) or 8 (float64)");
+}
+
+extern "C" uint64_t nbg_fill_sentinel_bits(int itemsize) {
+    return itemsize == 8 ? nbg::kFillSentinel64 : nbg::kFillSentinel32;
+}
+
+extern "C" int nbg_fill_patch(int dir, int itemsize, void *out, int64_t outer, int64_t n, int64_t inner, int64_t limit,
+                              const int64_t *carry, void *stream) {
+    using namespace nbg;
+    if (dir != NBG_FFILL && dir != NBG_BFILL) return fail(NBG_ERR_BAD_OP, "nbg_fill_patch: dir must be NBG_FFILL or NBG_BFILL");
+    if (outer < 0 || n < 0 || inner < 0 || limit < 0) return fail(NBG_ERR_BAD_ARG, "nbg_fill_patch: negative argument");
+    if (outer * n * inner == 0) return NBG_OK;
+    if (inner != 1) return fail(NBG_ERR_UNSUPPORTED, "nbg_fill_patch: inner must be 1 (use the two-pass form otherwise)");
+    if (!out || !carry) return fail(NBG_ERR_BAD_ARG, "nbg_fill_patch: null pointer");
+    const int64_t tpr = (n + kPatchTile - 1) / kPatchTile;
+    if (tpr * outer > INT32_MAX) return fail(NBG_ERR_UNSUPPORTED, "nbg_fill_patch: grid too large");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)(tpr * outer);
+    if (itemsize == 4) {
+        if (dir == NBG_FFILL) fill_patch_kernel<float, false><<<grid, 256, 0, st>>>(static_cast<float *>(out), n, tpr, limit, carry);
+        else fill_patch_kernel<float, true><<<grid, 256, 0, st>>>(static_cast<float *>(out), n, tpr, limit, carry);
+    } else if (itemsize == 8) {
+        if (dir == NBG_FFILL) fill_patch_kernel<double, false><<<grid, 256, 0, st>>>(static_cast<double *>(out), n, tpr, limit, carry);
+        else fill_patch_kernel<double, true><<<grid, 256, 0, st>>>(static_cast<double *>(out), n, tpr, limit, carry);
+    } else {
+        return fail(NBG_ERR_BAD_DTYPE, "nbg_fill_patch: itemsize must be 4 or 8");
+    }
+    return check_launch("nbg_fill_patch");
 }

@@ -673,6 +673,17 @@ static size_t group_state_bytes(int op, int64_t rows, int64_t num_labels) {
     return (size_t)nbg::ws_layout(op, rows * num_labels).words * (size_t)rows * (size_t)num_labels * 8 + 256;
 }
 extern "C" int nbg_group_record_words(int op) { return nbg::ws_layout(op).words; }
+extern "C" int nbg_group_record_layout(int op, int64_t rows, int64_t num_labels, int64_t layout[5]) {
+    using namespace nbg;
+    if (op < 0 || op > NBG_GROUP_NANALL) return fail(NBG_ERR_BAD_OP, "nbg_group_record_layout: unknown op");
+    if (!layout) return fail(NBG_ERR_BAD_ARG, "nbg_group_record_layout: null output");
+    const WsLayout l = ws_layout(op, rows * num_labels);
+    const int64_t plane = l.planar ? rows * num_labels : 1;
+    layout[0] = l.stride;
+    for (int c = 0; c < 3; c++) layout[1 + c] = (int64_t)l.slot[c] * plane;
+    layout[4] = l.planar;
+    return NBG_OK;
+}
 // scratch for the shared-label plan: 4 bytes per column + one header per (smallest) tile
 static size_t group_scratch_bytes(int64_t n, int64_t rows) {
     // widest tile is 1536 columns (a short row still needs one whole tile), narrowest 128;

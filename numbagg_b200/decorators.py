@@ -35,9 +35,101 @@ _NBG_DTYPE = {
 
 def _float_loop_dtype(*dtypes: np.dtype) -> np.dtype:
     """Loop selection NumPy performs over the (float32, float64) gufunc loops the reference
-    registers: float32/float16 -> float32 loop, anything else -> float64."""
+    registers: the FIRST loop every operand casts to safely -- float16, bool and
+    8/16-bit integers reach float32, everything else float64 (probed against the reference:
+    move_mean(int8) is float32, move_mean(int32) float64)."""
     dt = np.result_type(*dtypes)
-    return _F32 if dt in (_F32, np.dtype(np.float16)) else _F64
+    return _F32 if np.can_cast(dt, _F32, "safe") else _F64
+
+
+_GUFUNC_IGNORED_KWARGS = ("order", "subok")  # accepted by NumPy gufuncs, no effect on values
+
+
+class _GufuncKwargs:
+    """The keyword arguments the reference forwards to its gufunc (`**kwargs` at
+    numbagg/decorators.py:311-341, 380-414, 471-487, 712-731, 783-807, 836-876, 1069-1089):
+    `out=`, `dtype=`, `casting=` (plus `order=` / `subok=`, which do not change values).
+    Anything else raises the TypeError NumPy raises."""
+
+    def __init__(self, name: str, kwargs: dict):
+        self.name = name
+        out = kwargs.pop("out", None)
+        if isinstance(out, tuple):
+            if len(out) != 1:
+                raise ValueError("The 'out' tuple must have exactly one entry per ufunc output")
+            out = out[0]
+        self.out = out
+        self.dtype = kwargs.pop("dtype", None)
+        if self.dtype is not None:
+            self.dtype = np.dtype(self.dtype)
+        self.casting = kwargs.pop("casting", "same_kind")
+        if self.casting not in ("no", "equiv", "safe", "same_kind", "unsafe"):
+            raise ValueError("casting must be one of 'no', 'equiv', 'safe', 'same_kind', or 'unsafe'")
+        for k in _GUFUNC_IGNORED_KWARGS:
+            kwargs.pop(k, None)
+        if kwargs:
+            raise TypeError(f"{name}() got an unexpected keyword argument '{sorted(kwargs)[0]}'")
+
+    def loop_dtype(self, natural: np.dtype, loops=(_F32, _F64), dtype_ok=None) -> np.dtype:
+        """`natural`: the loop NumPy would pick from the inputs.  `dtype=` selects a loop by its
+        output dtype; `dtype_ok` restricts which (the move / fill gufuncs also have int64 scalar
+        operands, so only their float64 loop is reachable through `dtype=`)."""
+        if self.dtype is None:
+            return natural
+        ok = loops if dtype_ok is None else dtype_ok
+        if self.dtype not in ok:
+            raise TypeError(f"No loop matching the specified signature and casting was found for ufunc {self.name}")
+        return self.dtype
+
+    def check_inputs(self, loop: np.dtype, *in_dtypes: np.dtype) -> None:
+        for i, dt in enumerate(in_dtypes):
+            if not np.can_cast(dt, loop, self.casting):
+                raise TypeError(f"Cannot cast ufunc '{self.name}' input {i} from {dt!r} to {loop!r} "
+                                f"with casting rule '{self.casting}'")
+
+    def check_out(self, loop: np.dtype, shape: tuple) -> None:
+        if self.out is None:
+            return
+        odt = dev.np_dtype_of(self.out)
+        if not np.can_cast(loop, odt, self.casting):
+            raise TypeError(f"Cannot cast ufunc '{self.name}' output from {loop!r} to {odt!r} "
+                            f"with casting rule '{self.casting}'")
+        if tuple(self.out.shape) != tuple(shape):
+            raise ValueError(f"operands could not be broadcast together: output of shape {tuple(shape)} "
+                             f"does not fit `out` of shape {tuple(self.out.shape)}")
+
+
+def _on_tensor_device(fn):
+    """Run a device-level entry on the device its tensors live on (not the caller's current
+    device): pointers, workspaces and the stream handed to the C ABI must belong to one device.
+    Tensors on different devices are an error."""
+    import functools
+
+    def _tensors(x, acc):
+        if isinstance(x, torch.Tensor):
+            if x.is_cuda:
+                acc.append(x)
+        elif isinstance(x, (list, tuple)):
+            for y in x:
+                _tensors(y, acc)
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        ts: list[torch.Tensor] = []
+        _tensors(args, ts)
+        _tensors(tuple(kwargs.values()), ts)
+        if not ts:
+            return fn(*args, **kwargs)
+        d = ts[0].device
+        for t in ts[1:]:
+            if t.device != d:
+                raise ValueError(f"{fn.__name__}: operands live on different devices ({d} and {t.device})")
+        if torch.cuda.current_device() == d.index:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(d):
+            return fn(*args, **kwargs)
+
+    return wrapper
 
 
 def _is_int(x) -> bool:
@@ -192,6 +284,7 @@ class NumbaBase:
 
 
 # ------------------------------------------------------------------------------- moving
+@_on_tensor_device
 def run_move(name: str, arrs: list[torch.Tensor], window: int, min_count: int, axis: int,
              halos: list[torch.Tensor] | None = None) -> torch.Tensor:
     """Device-level entry (CUDA tensors of one float dtype, same shape) -> CUDA tensor."""
@@ -223,9 +316,8 @@ class ndmove(NumbaBase):
 
     def __call__(self, *arr, window: int, min_count: int | None = None,
                  axis: int | tuple[int, ...] = -1, **kwargs):
-        out = kwargs.pop("out", None)
-        if kwargs:
-            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        kw = _GufuncKwargs(self.__name__, kwargs)
+        out = kw.out
         if len(arr) != self.n_inputs:
             raise TypeError(f"{self.__name__}() takes {self.n_inputs} array argument(s), got {len(arr)}")
         if min_count is None:
@@ -249,7 +341,11 @@ class ndmove(NumbaBase):
         if not _is_int(window) or not _is_int(min_count):
             # NumPy refuses to cast a float window/min_count to the int64 loop operand
             raise TypeError(f"window and min_count must be integers: {window!r}, {min_count!r}")
-        dt = _float_loop_dtype(*[dev.np_dtype_of(a) for a in arr])
+        in_dts = [dev.np_dtype_of(a) for a in arr]
+        # `dtype=` also constrains the int64 window / min_count operands: only float64 resolves
+        dt = kw.loop_dtype(_float_loop_dtype(*in_dts), dtype_ok=(_F64,))
+        kw.check_inputs(dt, *in_dts)
+        kw.check_out(dt, np.broadcast_shapes(*[tuple(a.shape) for a in arr]))
         if not as_tensor and out is None:
             piped = _rows_pipelined(list(arr), dt, axis,
                                     lambda ts: run_move(self.__name__, ts, window, min_count, axis))
@@ -272,6 +368,7 @@ class ndmove(NumbaBase):
 
 
 # --------------------------------------------------------------------------- exp moving
+@_on_tensor_device
 def run_move_exp(name: str, arrs: list[torch.Tensor], alpha, min_weight: float, axis: int,
                  carry_in: torch.Tensor | None = None, want_agg: bool = False,
                  want_out: bool = True):
@@ -290,6 +387,12 @@ def run_move_exp(name: str, arrs: list[torch.Tensor], alpha, min_weight: float, 
     L = _lib.lib()
     code = _lib.EXP_OPS[name]
     dcode = _NBG_DTYPE[dev.np_dtype_of(view.t)]
+    if view.t.numel() == 0:  # empty input: empty result, identity aggregate (D = D2 = 1)
+        agg0 = None
+        if want_agg:
+            agg0 = torch.zeros((view.outer * view.inner, _lib.NBG_EXP_STATE), dtype=torch.float64, device=view.t.device)
+            agg0[:, :2] = 1.0
+        return (view.restore(torch.empty_like(view.t)) if want_out else None), agg0
     out = torch.empty_like(view.t) if want_out else None
     slices = view.outer * view.inner
     agg = torch.empty((slices, _lib.NBG_EXP_STATE), dtype=torch.float64, device=view.t.device) if want_agg else None
@@ -315,9 +418,8 @@ class ndmoveexp(NumbaBase):
 
     def __call__(self, *arr, alpha, min_weight: float = 0,
                  axis: int | tuple[int, ...] = -1, **kwargs):
-        out = kwargs.pop("out", None)
-        if kwargs:
-            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        kw = _GufuncKwargs(self.__name__, kwargs)
+        out = kw.out
         if len(arr) != self.n_inputs:
             raise TypeError(f"{self.__name__}() takes {self.n_inputs} array argument(s), got {len(arr)}")
         if isinstance(axis, tuple):
@@ -343,7 +445,10 @@ class ndmoveexp(NumbaBase):
             # np.broadcast_to(alpha, n) in the reference: the scalar's own dtype takes part in
             # loop selection (python float -> float64, np.float32 -> float32)
             alpha_dtype = np.asarray(alpha).dtype
-        dt = _float_loop_dtype(*[dev.np_dtype_of(a) for a in arr], alpha_dtype)
+        in_dts = [dev.np_dtype_of(a) for a in arr]
+        dt = kw.loop_dtype(_float_loop_dtype(*in_dts, alpha_dtype))
+        kw.check_inputs(dt, *in_dts)
+        kw.check_out(dt, np.broadcast_shapes(*[tuple(a.shape) for a in arr]))
         if not as_tensor and out is None and not alpha_is_array:
             a_s = float(np.float32(alpha)) if dt == _F32 else float(alpha)
             m_s = float(np.float32(min_weight)) if dt == _F32 else float(min_weight)
@@ -377,12 +482,16 @@ class ndmoveexp(NumbaBase):
 
 
 # -------------------------------------------------------------------------------- fills
+@_on_tensor_device
 def run_fill(name: str, t: torch.Tensor, limit: int, axis: int,
              carry_in: torch.Tensor | None = None, want_agg: bool = False, want_out: bool = True):
     """Device-level entry for ffill/bfill on a float32/float64 CUDA tensor."""
     view = dev.CoreView(t, axis)
     L = _lib.lib()
     itemsize = view.t.element_size()
+    if view.t.numel() == 0:  # nothing to scan: empty result, identity aggregate
+        agg0 = torch.zeros((view.outer * view.inner, _lib.NBG_FILL_STATE), dtype=torch.int64, device=t.device) if want_agg else None
+        return (view.restore(torch.empty_like(view.t)) if want_out else None), agg0
     out = torch.empty_like(view.t) if want_out else None
     slices = view.outer * view.inner
     agg = torch.empty((slices, _lib.NBG_FILL_STATE), dtype=torch.int64, device=t.device) if want_agg else None
@@ -397,13 +506,31 @@ def run_fill(name: str, t: torch.Tensor, limit: int, axis: int,
     return (view.restore(out) if out is not None else None), agg
 
 
+def fill_sentinel_bits(itemsize: int) -> int:
+    """NaN payload that marks "depends on the predecessors' carry" in a sharded fill."""
+    return int(_lib.lib().nbg_fill_sentinel_bits(int(itemsize)))
+
+
+@_on_tensor_device
+def run_fill_patch(name: str, out: torch.Tensor, limit: int, axis: int, carry: torch.Tensor) -> None:
+    """Second step of the single-pass sharded fill: rewrite the sentinel run of `out` in place from
+    the folded carry ((slices, NBG_FILL_STATE) int64).  The core axis must be the last one."""
+    nd = out.dim()
+    if axis % nd != nd - 1 or not out.is_contiguous():
+        raise ValueError("run_fill_patch needs a C-contiguous tensor with the core axis last")
+    n = out.shape[-1]
+    outer = out.numel() // max(n, 1)
+    rc = _lib.lib().nbg_fill_patch(_lib.FILL_DIRS[name], out.element_size(), dev.ptr(out), outer, n, 1, int(limit),
+                                   dev.ptr(carry), dev.stream_ptr())
+    _lib.check(rc, f"nbg_fill_patch({name})")
+
+
 class ndfill(NumbaBase):
     """Forward/backward fill along one axis (numbagg ``ndfill``)."""
 
     def __call__(self, arr, *, limit: None | int = None, axis: int = -1, **kwargs):
-        out = kwargs.pop("out", None)
-        if kwargs:
-            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        kw = _GufuncKwargs(self.__name__, kwargs)
+        out = kw.out
         as_tensor = dev.is_tensor(arr)
         if not as_tensor:
             arr = np.asarray(arr)
@@ -414,6 +541,9 @@ class ndfill(NumbaBase):
         dt = dev.np_dtype_of(arr)
         if not np.issubdtype(dt, np.number):
             raise TypeError(f"Unsupported dtype for fill operation: {dt}")
+        # the fill gufunc is compiled per dtype (decorators.py:427-463): the only loop is the input's own
+        kw.loop_dtype(dt, dtype_ok=(dt,) if dt == _F64 else ())
+        kw.check_out(dt, tuple(arr.shape))
         if dt.kind in "iu":
             # np.isnan is constant-false for integers (funcs.py:303,319): the loop is a copy
             res = arr.clone() if as_tensor else arr.copy()
@@ -441,6 +571,7 @@ class ndfill(NumbaBase):
 
 
 # ------------------------------------------------------------------------------ grouped
+@_on_tensor_device
 def run_group(name: str, values: torch.Tensor, labels: torch.Tensor, num_labels: int, ddof: int,
               labels_per_row: bool = False) -> torch.Tensor:
     """Device-level entry: values (rows, n) contiguous, labels (n,) or (rows, n), both CUDA;
@@ -559,6 +690,7 @@ def group_record_words(name: str) -> int:
     return int(_lib.lib().nbg_group_record_words(_lib.GROUP_OPS[name]))
 
 
+@_on_tensor_device
 def run_group_partial(name: str, values: torch.Tensor, labels: torch.Tensor, num_labels: int,
                       index_offset: int = 0, labels_per_row: bool = False) -> torch.Tensor:
     """init + accumulate for one element shard.  Returns the accumulator state as an int64
@@ -581,6 +713,20 @@ def run_group_partial(name: str, values: torch.Tensor, labels: torch.Tensor, num
     return ws[: words * rows * num_labels * 8].view(torch.int64).view(rows, num_labels, words)
 
 
+def group_state_channels(name: str, state: torch.Tensor, rows: int, num_labels: int) -> list[torch.Tensor]:
+    """Writable 1-D views (rows * num_labels int64 words each) of channels 0..2 of a group state
+    returned by run_group_partial -- what the multi-GPU combine all-reduces.  Channel meanings per
+    op: DESIGN.md "group workspace"; channels an op does not use alias another one."""
+    import ctypes
+
+    lay = (ctypes.c_int64 * 5)()
+    _lib.check(_lib.lib().nbg_group_record_layout(_lib.GROUP_OPS[name], rows, num_labels, lay), "nbg_group_record_layout")
+    flat = state.reshape(-1)
+    slots = rows * num_labels
+    return [torch.as_strided(flat, (slots,), (int(lay[0]),), int(lay[1 + c])) for c in range(3)]
+
+
+@_on_tensor_device
 def run_group_combine(name: str, vdtype: np.dtype, acc: torch.Tensor, other: torch.Tensor) -> None:
     """acc <- merge(acc, other) where `other` covers LATER elements (nbg_group_combine)."""
     rows, K, _ = acc.shape
@@ -589,6 +735,7 @@ def run_group_combine(name: str, vdtype: np.dtype, acc: torch.Tensor, other: tor
     _lib.check(rc, f"nbg_group_combine({name})")
 
 
+@_on_tensor_device
 def run_group_finalize(name: str, vdtype: np.dtype, state: torch.Tensor, ddof: int) -> torch.Tensor:
     rows, K, _ = state.shape
     out = torch.empty((rows, K), dtype=dev._NP_TO_TORCH[np.dtype(vdtype)], device=state.device)
@@ -614,6 +761,12 @@ def _reduce_loop_dtype(name: str, dt: np.dtype) -> np.dtype:
     if dt.kind == "f":
         return _F32 if dt.itemsize <= 4 else _F64
     if name in _REDUCE_FLOAT_ONLY:
+        # first loop the input casts to safely: 8/16-bit integers reach float32.  bool does so for
+        # nanmean only -- with the integer `ddof` operand of nanvar / nanstd NumPy resolves bool to
+        # the float64 loop (probed against the reference)
+        small = dt.kind in "iu" and dt.itemsize <= 2
+        if small or (dt.kind == "b" and name == "nanmean"):
+            return _F32
         return _F64
     if dt.kind == "b" or (dt.kind in "iu" and dt.itemsize < 4) or dt == np.dtype(np.int32):
         return np.dtype(np.int32)
@@ -674,6 +827,7 @@ class ReduceView:
         return out.permute(self._back) if self._back else out
 
 
+@_on_tensor_device
 def run_reduce(name: str, t: torch.Tensor, axes: tuple[int, ...], ddof: int = 1) -> torch.Tensor:
     """Device-level entry: reduce `axes` (in that order) of a CUDA tensor whose dtype is one
     of the loop dtypes; returns a CUDA tensor of the batch shape."""
@@ -693,6 +847,7 @@ def run_reduce(name: str, t: torch.Tensor, axes: tuple[int, ...], ddof: int = 1)
     return view.restore(out)
 
 
+@_on_tensor_device
 def run_reduce_partial(name: str, t: torch.Tensor, axes: tuple[int, ...], index_offset: int = 0):
     """Element shard -> (3, outs) int64 state records (include/nbg_b200.h) + the view."""
     work = dev._TORCH_TO_NP[t.dtype]
@@ -709,6 +864,7 @@ def run_reduce_partial(name: str, t: torch.Tensor, axes: tuple[int, ...], index_
     return states, view
 
 
+@_on_tensor_device
 def run_reduce_merge(name: str, work: np.dtype, states: torch.Tensor, n_total: int, ddof: int = 1) -> torch.Tensor:
     """Fold (parts, 3, outs) gathered state records and finalize -> flat (outs,) result."""
     parts, _, outs = states.shape
@@ -801,6 +957,7 @@ class ndreduce(NumbaBase):
 
 
 # ------------------------------------------------------------------------- quantiles
+@_on_tensor_device
 def run_quantile(t: torch.Tensor, q: torch.Tensor, axes: tuple[int, ...]) -> torch.Tensor:
     """Device-level entry: float64 CUDA tensor `t`, float64 CUDA vector `q` (quantiles in
     [0, 1] or NaN); returns (len(q),) + batch shape."""
@@ -813,8 +970,13 @@ def run_quantile(t: torch.Tensor, q: torch.Tensor, axes: tuple[int, ...]) -> tor
     m_all = int(q.numel())
     flat = cube.reshape(rows, view.n)
     out = torch.empty((rows, m_all), dtype=torch.float64, device=t.device)
-    # the C entry takes <= 16 quantiles and (on its long-row path) <= 65535 rows per call
-    row_step = rows if view.n <= 4096 else 32768
+    # the C entry takes <= 16 quantiles and (on its long-row path) <= 65535 rows per call; the long-row
+    # workspace holds rows * 2m * 256 histogram words, so the row block shrinks with the number of
+    # quantiles to keep it at <= ~128 MB, and it is allocated once
+    m_max = min(m_all, _lib.NBG_QUANTILE_MAX_Q)
+    row_step = rows if view.n <= 4096 else max(256, min(32768, (128 << 20) // max(1, 2 * m_max * 256 * 4)))
+    ws_cap = int(L.nbg_quantile_workspace_bytes(min(rows, row_step), view.n, max(m_max, 1))) if rows and m_all else 0
+    ws_all = torch.empty(max(ws_cap, 1), dtype=torch.uint8, device=t.device)
     for r0 in range(0, rows, max(row_step, 1)):
         block = flat[r0:r0 + row_step]
         nrows = int(block.shape[0])
@@ -823,7 +985,7 @@ def run_quantile(t: torch.Tensor, q: torch.Tensor, axes: tuple[int, ...]) -> tor
             m = int(qc.numel())
             part = torch.empty((nrows, m), dtype=torch.float64, device=t.device)
             ws_bytes = L.nbg_quantile_workspace_bytes(nrows, view.n, m)
-            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=t.device)
+            ws = ws_all if ws_bytes <= ws_all.numel() else torch.empty(ws_bytes, dtype=torch.uint8, device=t.device)
             rc = L.nbg_quantile(dev.ptr(block), dev.ptr(qc), dev.ptr(part), nrows, view.n, m, ws.data_ptr(),
                                 ws_bytes, dev.stream_ptr())
             _lib.check(rc, "nbg_quantile")
@@ -841,8 +1003,7 @@ class ndquantile(NumbaBase):
     def __call__(self, a, quantiles, axis: int | tuple[int, ...] | None = None, **kwargs):
         from collections.abc import Iterable
 
-        if kwargs:
-            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        kw = _GufuncKwargs(self.__name__, kwargs)
         squeeze = not isinstance(quantiles, Iterable)
         qs = np.asarray([quantiles] if squeeze else quantiles, dtype=np.float64)
         if qs.ndim != 1:
@@ -857,15 +1018,24 @@ class ndquantile(NumbaBase):
         dt = dev.np_dtype_of(a)
         if dt.kind not in "fiub":
             raise TypeError(f"Unsupported dtype for {self.__name__}: {dt}")
+        kw.loop_dtype(_F64, dtype_ok=(_F64,))
+        kw.check_inputs(_F64, dt)
         t = dev.to_device(a, _F64)  # the reference has a float64 loop only
         q = torch.from_numpy(qs).to(t.device)
         res = run_quantile(t, q, axes)
+        if kw.out is not None:
+            # the gufunc's output is (..., m) BEFORE the quantile axis is moved first and squeezed
+            # (decorators.py:876-884); `out` has that layout
+            raw = torch.movedim(res, 0, -1)
+            kw.check_out(_F64, tuple(raw.shape))
+            _finish(raw, as_tensor, kw.out)
         if squeeze:
             res = res[0]
         return _reduce_result(res, as_tensor)
 
 
 # ------------------------------------------------------------------- matrix functions
+@_on_tensor_device
 def run_matrix(name: str, t: torch.Tensor, *, window: int = 0, min_count: int = 0, alpha: torch.Tensor | None = None,
                min_weight: float = 0.0) -> torch.Tensor:
     """Device-level entry for the six matrix functions.  Static ops take (..., vars, obs),
@@ -902,8 +1072,7 @@ class ndmatrix(NumbaBase):
     """numbagg ``ndmatrix`` (decorators.py:677-740): ``(..., vars, obs) -> (..., vars, vars)``."""
 
     def __call__(self, a, **kwargs):
-        if kwargs:
-            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        kw = _GufuncKwargs(self.__name__, kwargs)
         as_tensor = dev.is_tensor(a)
         nd = a.dim() if as_tensor else np.ndim(a)
         if nd < 2:
@@ -911,16 +1080,20 @@ class ndmatrix(NumbaBase):
                 f"{self.__name__} requires at least a 2D array with shape (..., vars, obs). "
                 "For 1D arrays, use nanvar for variance calculations."
             )
-        t = dev.to_device(a, _matrix_loop_dtype(dev.np_dtype_of(a)))
-        return _finish(run_matrix(self.__name__, t), as_tensor)
+        in_dt = dev.np_dtype_of(a)
+        work = kw.loop_dtype(_matrix_loop_dtype(in_dt))
+        kw.check_inputs(work, in_dt)
+        t = dev.to_device(a, work)
+        res = run_matrix(self.__name__, t)
+        kw.check_out(work, tuple(res.shape))
+        return _finish(res, as_tensor, kw.out)
 
 
 class ndmovematrix(NumbaBase):
     """numbagg ``ndmovematrix`` (decorators.py:743-818): ``(..., obs, vars) -> (..., obs, vars, vars)``."""
 
     def __call__(self, a, window: int, min_count: int | None = None, **kwargs):
-        if kwargs:
-            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        kw = _GufuncKwargs(self.__name__, kwargs)
         as_tensor = dev.is_tensor(a)
         if not as_tensor:
             a = np.asarray(a)
@@ -933,8 +1106,13 @@ class ndmovematrix(NumbaBase):
             raise ValueError(f"min_count must be positive: {min_count}")
         if not 0 < window <= a.shape[-2]:
             raise ValueError(f"window not in valid range: {window}")
-        t = dev.to_device(a, _matrix_loop_dtype(dev.np_dtype_of(a)))
-        return _finish(run_matrix(self.__name__, t, window=window, min_count=min_count), as_tensor)
+        in_dt = dev.np_dtype_of(a)
+        work = kw.loop_dtype(_matrix_loop_dtype(in_dt), dtype_ok=(_F64,))  # int64 window / min_count operands
+        kw.check_inputs(work, in_dt)
+        t = dev.to_device(a, work)
+        res = run_matrix(self.__name__, t, window=window, min_count=min_count)
+        kw.check_out(work, tuple(res.shape))
+        return _finish(res, as_tensor, kw.out)
 
 
 class ndmoveexpmatrix(NumbaBase):
@@ -942,8 +1120,7 @@ class ndmoveexpmatrix(NumbaBase):
     (a scalar is broadcast), loop dtype from (a, alpha) like NumPy picks it."""
 
     def __call__(self, a, alpha, min_weight: float = 0, **kwargs):
-        if kwargs:
-            raise TypeError(f"{self.__name__}() got unexpected keyword arguments {sorted(kwargs)}")
+        kw = _GufuncKwargs(self.__name__, kwargs)
         as_tensor = dev.is_tensor(a)
         if not as_tensor:
             a = np.asarray(a)
@@ -960,7 +1137,10 @@ class ndmoveexpmatrix(NumbaBase):
         dts = [dev.np_dtype_of(a), alpha_dt]
         if isinstance(min_weight, np.generic):  # NumPy scalars are strongly typed, Python numbers are not
             dts.append(np.asarray(min_weight).dtype)
-        work = _matrix_loop_dtype(*dts)
+        work = kw.loop_dtype(_matrix_loop_dtype(*dts))
+        kw.check_inputs(work, dts[0])
         t = dev.to_device(a, work)
         al = dev.to_device(np.ascontiguousarray(alpha) if isinstance(alpha, np.ndarray) else alpha, work, t.device)
-        return _finish(run_matrix(self.__name__, t, alpha=al, min_weight=float(min_weight)), as_tensor)
+        res = run_matrix(self.__name__, t, alpha=al, min_weight=float(min_weight))
+        kw.check_out(work, tuple(res.shape))
+        return _finish(res, as_tensor, kw.out)

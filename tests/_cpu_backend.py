@@ -144,6 +144,36 @@ class OracleBackend:
         o = torch.from_numpy(np.ascontiguousarray(np.moveaxis(out.reshape(shape), -1, axis))) if want_out else None
         return o, (torch.from_numpy(agg) if want_agg else None)
 
+    SENTINEL = 0x7FF8DEAD5E171E1D  # any NaN payload no output can otherwise hold
+
+    @staticmethod
+    def fill_sentinel(itemsize):
+        return OracleBackend.SENTINEL
+
+    @staticmethod
+    def fill_patch(name, out, limit, axis, carry):
+        """In-place rewrite of the leading (scan-order) sentinel run from the folded carry."""
+        a = out.numpy()
+        nd = a.ndim
+        assert axis % nd == nd - 1
+        flat = a.reshape(-1, a.shape[-1])
+        bits = flat.view(np.int64)
+        rev = name == "bfill"
+        for r in range(flat.shape[0]):
+            has, cb, dist = [int(v) for v in carry[r]]
+            n = flat.shape[1]
+            for q in range(n):
+                i = n - 1 - q if rev else q
+                if bits[r, i] != OracleBackend.SENTINEL:
+                    break
+                bits[r, i] = cb if (has and dist + q + 1 <= limit) else np.array([np.nan]).view(np.int64)[0]
+
+    @staticmethod
+    def group_channels(name, state, rows, K):
+        words, slots = _layout(name)
+        flat = state.reshape(-1)
+        return [torch.as_strided(flat, (rows * K,), (words,), slots[c]) for c in range(3)]
+
     # ---- group workspace protocol (numbagg_b200/csrc/nbg_group.cu header), float64 values
     @staticmethod
     def _key(v):

@@ -47,16 +47,17 @@ def _worker(rank, world, port, case, uneven, results):
         b = a**2 + 1
         cuts = _split(60, world, uneven)
         lo, hi = cuts[rank], cuts[rank + 1]
+        lens = [cuts[r + 1] - cuts[r] for r in range(world)]
         ta, tb = torch.from_numpy(a[:, lo:hi].copy()), torch.from_numpy(b[:, lo:hi].copy())
         out = {}
         if case == "move":
             for f in ("move_mean", "move_sum", "move_std", "move_var"):
-                out[f] = nd.move_sharded(f, ta, window=7, min_count=2, axis=-1, backend=B).numpy()
+                out[f] = nd.move_sharded(f, ta, window=7, min_count=2, axis=-1, shard_lens=lens, backend=B).numpy()
             for f in ("move_cov", "move_corr"):
-                out[f] = nd.move_sharded(f, ta, tb, window=7, min_count=2, axis=-1, backend=B).numpy()
+                out[f] = nd.move_sharded(f, ta, tb, window=7, min_count=2, axis=-1, shard_lens=lens, backend=B).numpy()
             # core axis 0: shards are row blocks of the transposed problem
             tt = torch.from_numpy(a.T[lo:hi].copy())
-            out["move_mean_axis0"] = nd.move_sharded("move_mean", tt, window=7, min_count=2, axis=0, backend=B).numpy().T
+            out["move_mean_axis0"] = nd.move_sharded("move_mean", tt, window=7, min_count=2, axis=0, shard_lens=lens, backend=B).numpy().T
         elif case == "exp":
             for f in ("move_exp_nancount", "move_exp_nanmean", "move_exp_nansum", "move_exp_nanvar", "move_exp_nanstd"):
                 out[f] = nd.move_exp_sharded(f, ta, alpha=0.2, min_weight=0.1, axis=-1, backend=B).numpy()
@@ -65,6 +66,17 @@ def _worker(rank, world, port, case, uneven, results):
             al = np.random.RandomState(3).rand(60) * 0.8 + 0.1
             out["move_exp_nanmean_alpha1d"] = nd.move_exp_sharded(
                 "move_exp_nanmean", ta, alpha=torch.from_numpy(al[lo:hi].copy()), axis=-1, backend=B).numpy()
+        elif case == "exp_single":
+            # long enough for the ONE-pass form: zero-carry scan + aggregate, then only the head
+            # (exp_forget_length) is recomputed with the carry
+            n2 = 2400
+            x = fixture_array((2, n2), seed=11)
+            x[1, 1100:1300] = np.nan  # a NaN run across the boundary
+            c2 = _split(n2, world, uneven)
+            px = torch.from_numpy(x[:, c2[rank]:c2[rank + 1]].copy())
+            assert nd.exp_forget_length(0.9999) * 4 <= px.shape[1] or uneven
+            for f in ("move_exp_nanmean", "move_exp_nansum", "move_exp_nanvar"):
+                out[f] = nd.move_exp_sharded(f, px, alpha=0.9999, axis=-1, backend=B).numpy()
         elif case == "fill":
             x = a.copy()
             x[1, 10:50] = np.nan  # a NaN run across the shard boundary
@@ -72,7 +84,7 @@ def _worker(rank, world, port, case, uneven, results):
             tx = torch.from_numpy(x[:, lo:hi].copy())
             for f in ("ffill", "bfill"):
                 for limit in (None, 2, 25):
-                    out[f"{f}_{limit}"] = nd.fill_sharded(f, tx, limit=limit, axis=-1, backend=B).numpy()
+                    out[f"{f}_{limit}"] = nd.fill_sharded(f, tx, limit=limit, axis=-1, shard_lens=lens, backend=B).numpy()
         elif case == "group":
             rs = np.random.RandomState(5)
             v = np.round(fixture_array((2, 60), seed=6) * 10) / 2
@@ -88,12 +100,12 @@ def _worker(rank, world, port, case, uneven, results):
                 for ax, full in ((-1, x), (0, x.T.copy())):
                     piece = torch.from_numpy((full[:, lo:hi] if ax == -1 else full[lo:hi]).copy())
                     try:
-                        out[f"{f}_{ax}"] = nd.reduce_sharded(f, piece, axis=ax, ddof=1, backend=B).numpy()
+                        out[f"{f}_{ax}"] = nd.reduce_sharded(f, piece, axis=ax, ddof=1, shard_lens=lens, backend=B).numpy()
                     except ValueError as e:
                         out[f"{f}_{ax}"] = str(e)
             y = x[[0, 2, 3]]
             for f in ("nanargmax", "nanargmin"):
-                out[f"{f}_ok"] = nd.reduce_sharded(f, torch.from_numpy(y[:, lo:hi].copy()), axis=-1, backend=B).numpy()
+                out[f"{f}_ok"] = nd.reduce_sharded(f, torch.from_numpy(y[:, lo:hi].copy()), axis=-1, shard_lens=lens, backend=B).numpy()
         results[rank] = (lo, hi, out)
     finally:
         dist.destroy_process_group()
@@ -134,6 +146,29 @@ def test_move_exp_sharded_matches_unsharded(uneven):
         np.testing.assert_allclose(_stitch(res, f), getattr(oracle, f)(a, b, alpha=0.2), rtol=1e-9, equal_nan=True)
     al = np.random.RandomState(3).rand(60) * 0.8 + 0.1
     np.testing.assert_allclose(_stitch(res, "move_exp_nanmean_alpha1d"), oracle.move_exp_nanmean(a, alpha=al), rtol=1e-11, equal_nan=True)
+
+
+@pytest.mark.parametrize("uneven", [False, True])
+def test_move_exp_sharded_single_pass(uneven):
+    res = _run("exp_single", uneven)
+    x = fixture_array((2, 2400), seed=11)
+    x[1, 1100:1300] = np.nan
+    for f in ("move_exp_nanmean", "move_exp_nansum", "move_exp_nanvar"):
+        np.testing.assert_allclose(_stitch(res, f), getattr(oracle, f)(x, alpha=0.9999), rtol=1e-11, equal_nan=True)
+
+
+def test_exp_forget_length():
+    from numbagg_b200.distributed import exp_forget_length
+
+    import math
+
+    for alpha in (0.1, 0.5, 0.9999, 1e-3):
+        k = exp_forget_length(alpha)
+        assert k * math.log2(1.0 - alpha) < -1075.0, (alpha, k)  # below half the smallest subnormal
+        assert (1.0 - alpha) ** k == 0.0
+    assert 7000 < exp_forget_length(0.1) < 7400
+    assert exp_forget_length(0.0) is None and exp_forget_length(-0.5) is None and exp_forget_length(float("nan")) is None
+    assert exp_forget_length(1.0) == 1
 
 
 @pytest.mark.parametrize("uneven", [False, True])
