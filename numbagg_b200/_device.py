@@ -43,9 +43,12 @@ def is_tensor(x: Any) -> bool:
 
 
 def np_dtype_of(x) -> np.dtype:
+    """dtype of a tensor / array in NATIVE byte order (NumPy byte-swaps non-native operands on the
+    way into a gufunc loop; to_device does the same on the way to the GPU)."""
     if is_tensor(x):
         return _TORCH_TO_NP[x.dtype]
-    return np.asarray(x).dtype
+    dt = np.asarray(x).dtype
+    return dt if dt.isnative else dt.newbyteorder("=")
 
 
 def to_device(x, dtype: np.dtype | None = None, device: torch.device | None = None) -> torch.Tensor:

@@ -22,8 +22,10 @@
 //   * the column plan (built once per call from the labels, shared by all rows) lists, per tile
 //     and class, the valid columns stably sorted by label, cut into 64/NCLS label-aligned
 //     ranges, each padded to a multiple of 4 entries so that a sub-warp fetches four entries
-//     with one 16-byte load.  No atomics anywhere: a label range belongs to one sub-warp per
-//     tile and its bins to one lane.
+//     with one 16-byte load, and interleaved so that a group of 4 never holds one label twice:
+//     the four read-modify-writes of a group are independent and cost ONE round trip of
+//     shared-memory latency (the kernel is latency-bound per warp otherwise).  No atomics
+//     anywhere: a label range belongs to one sub-warp per tile and its bins to one lane.
 //   * RANGES MOVE ONLY BETWEEN NEIGHBOURS: the ranges of a tile are balanced per tile (every
 //     sub-warp gets the same number of entries, so the 4 sub-warps of a warp -- which execute in
 //     lock step -- waste no lanes), but boundary j is clamped into a fixed window around its
@@ -52,11 +54,12 @@
 
 namespace nbg {
 
-constexpr int kRb2Consumers = kRbThreads;        // 512 consumer threads = 64 sub-warps of 8 rows
-constexpr int kRb2Threads = kRb2Consumers + 32;  // + one producer warp
-constexpr int kRb2Pad = 64 * 3;                  // worst-case padding entries per tile
+constexpr int kRb2MaxWarps = 31;                 // consumer warps per CTA: 16 or 31 (+ the producer warp = 1024 threads)
+constexpr int kRb2MaxSub = 4 * kRb2MaxWarps;     // sub-warps = label ranges per tile
+constexpr int kRb2Hdr = 136;                     // u32 words per tile header: NCLS * (SUBS + 1) bounds, padded to 16 bytes
+constexpr int kRb2Pad = kRb2MaxSub * 3;          // worst-case padding entries per tile
 constexpr int kRb2MaxStages = 4;
-constexpr int kRb2Header = 384;  // mbarriers: full[4], empty[4], done[16][2]
+constexpr int kRb2Header = 640;  // mbarriers: full[4], empty[4], done[31][2]
 
 // ---------------------------------------------------------------------------------- channel ops
 // Words have the size of V (float/int32 -> 4 bytes, double/int64 -> 8 bytes); counters are the
@@ -244,9 +247,9 @@ __global__ void __launch_bounds__(256) group_cuts2_kernel(const int *__restrict_
 
 template <typename L, int NCLS>
 __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ labels, int64_t n, int K, int C,
-                                                          int ent_cap, int nc, int vsize, const int *__restrict__ cuts,
+                                                          int ent_cap, int nc, int vsize, int runs, int nsub, const int *__restrict__ cuts,
                                                           uint32_t *__restrict__ plan) {
-    constexpr int SUBS = 64 / NCLS;
+    const int SUBS = nsub / NCLS;  // ranges per class
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int NK = NCLS * K;
     int *offs = reinterpret_cast<int *>(smem_raw);               // [NK + 1] histogram -> exclusive offsets
@@ -254,12 +257,13 @@ __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ 
     uint32_t *skey = reinterpret_cast<uint32_t *>(cursor + NK);  // [C] class * K + label, or ~0
     uint32_t *sent = skey + C;                                   // [C] entries in (class, label, column) order
     __shared__ int warp_tot[8];
-    __shared__ int ub[65];   // unpadded range bounds over `sent`, flattened (class, range)
-    __shared__ int pst[65];  // padded start of every range
+    __shared__ int ub[kRb2MaxSub + 1];   // unpadded range bounds over `sent`, flattened (class, range)
+    __shared__ int pst[kRb2MaxSub + 1];  // padded start of every range
+    __shared__ int rseq[kRb2MaxSub];     // range keeps sorted order (sequential read-modify-writes)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = blockIdx.x / nc, rank = blockIdx.x % nc;
     const int64_t c0 = (int64_t)tile * C;
-    uint32_t *out = plan + (size_t)blockIdx.x * (kRbHdr + ent_cap);
+    uint32_t *out = plan + (size_t)blockIdx.x * (kRb2Hdr + ent_cap);
     const int nslots = (K + nc - 1) / nc;
 
     for (int k = tid; k <= NK; k += 256) offs[k] = 0;
@@ -323,9 +327,9 @@ __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ 
     __syncthreads();
     // ranges (unpadded positions), balanced per tile; the first label of range j is clamped into
     // [M(j-1), M(j)], M(j) = midpoint of the nominal cuts j and j+1 (cuts[q][0] = 0, cuts[q][SUBS] = K)
-    if (tid <= 64) {
+    if (tid <= nsub) {
         int b;
-        if (tid == 64) {
+        if (tid == nsub) {
             b = offs[NK];
         } else {
             const int q = tid / SUBS, j = tid % SUBS;
@@ -349,35 +353,70 @@ __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ 
     __syncthreads();
     if (tid == 0) {
         int p = 0;
-        for (int g = 0; g < 64; g++) {
+        for (int g = 0; g < nsub; g++) {
             pst[g] = p;
             p += (ub[g + 1] - ub[g] + 3) & ~3;
         }
-        pst[64] = p;
+        pst[nsub] = p;
+    }
+    __syncthreads();
+    // Layout inside a range of c entries, G = ceil(c / 4) groups of 4: sorted position p goes to slot
+    // 4 * (p % G) + p / G, i.e. a group holds the sorted positions {g, G+g, 2G+g, 3G+g}.  Entries of one
+    // label are contiguous in sorted order, so as long as no label has more than G entries in the range a
+    // group never holds a label twice and its four read-modify-writes are INDEPENDENT (the kernel issues
+    // them together).  Otherwise -- or with `runs` (few labels: register accumulation needs sorted order)
+    // -- the range keeps the sorted order and is flagged sequential (bit 31 of its header word).
+    if (tid < nsub) {
+        const int q = tid / SUBS;
+        const int cnt = ub[tid + 1] - ub[tid];
+        const int G = (cnt + 3) >> 2;
+        int seq = runs;
+        if (!seq && cnt > 0) {
+            // longest label run of this range
+            const int l0 = (int)(sent[ub[tid]] & 0xffffu) * nc + rank, l1 = (int)(sent[ub[tid + 1] - 1] & 0xffffu) * nc + rank;
+            int longest = 0;
+            for (int lab = l0; lab <= l1; lab++) {
+                const int a0 = max(offs[q * K + lab], ub[tid]), a1 = min(offs[q * K + lab + 1], ub[tid + 1]);
+                longest = max(longest, a1 - a0);
+            }
+            seq = longest > G;
+        }
+        rseq[tid] = seq;
     }
     __syncthreads();
     // header: hdr[q * (SUBS + 1) + j], j = 0..SUBS  (entry SUBS of class q = start of class q + 1)
     if (tid < NCLS * (SUBS + 1)) {
         const int q = tid / (SUBS + 1), j = tid % (SUBS + 1);
-        out[tid] = (uint32_t)pst[q * SUBS + j];
+        const int r = q * SUBS + j;
+        out[tid] = (uint32_t)pst[r] | ((j < SUBS && rseq[r]) ? 0x80000000u : 0u);
     }
-    for (int t2 = NCLS * (SUBS + 1) + tid; t2 < kRbHdr; t2 += 256) out[t2] = 0;
-    // entries into their padded places
+    for (int t2 = NCLS * (SUBS + 1) + tid; t2 < kRb2Hdr; t2 += 256) out[t2] = 0;
+    // dummies first (a range's padding slots are scattered in the interleaved layout), then the entries
+    if (tid < nsub) {
+        const int cnt = ub[tid + 1] - ub[tid];
+        const int q = tid / SUBS;
+        const uint32_t dummy = ((uint32_t)(q * vsize) << 16) | (uint32_t)nslots;
+        if (cnt & 3) {
+            const int m = (cnt + 3) & ~3;
+            for (int i = max(0, m - 16); i < m; i++) out[kRb2Hdr + pst[tid] + i] = dummy;  // padding lives in the last 4 groups
+        }
+    }
+    __syncthreads();
     const int total = offs[NK];
     for (int pos = tid; pos < total; pos += 256) {
-        int lo = 0, hi = 63;  // last range g with ub[g] <= pos
+        int lo = 0, hi = nsub - 1;  // last range g with ub[g] <= pos
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
             if (ub[mid] <= pos) lo = mid;
             else hi = mid - 1;
         }
-        out[kRbHdr + pst[lo] + (pos - ub[lo])] = sent[pos];
-    }
-    if (tid < 64) {
-        const int cnt = ub[tid + 1] - ub[tid];
-        const int q = tid / SUBS;
-        const uint32_t dummy = ((uint32_t)(q * vsize) << 16) | (uint32_t)nslots;
-        for (int i = cnt; i < ((cnt + 3) & ~3); i++) out[kRbHdr + pst[tid] + i] = dummy;
+        const int p = pos - ub[lo];
+        int slot = p;
+        if (!rseq[lo]) {
+            const int G = (ub[lo + 1] - ub[lo] + 3) >> 2;
+            slot = 4 * (p % G) + p / G;
+        }
+        out[kRb2Hdr + pst[lo] + slot] = sent[pos];
     }
 }
 
@@ -396,7 +435,7 @@ struct Rb2Params {
 
 template <typename V>
 __host__ __device__ inline size_t rb2_stage_bytes(int C, int ent_cap) {
-    return ((size_t)(kRbHdr + ent_cap) * 4 + (size_t)kRbRows * rb_row_stride<V>(C) * sizeof(V) + 15) & ~(size_t)15;
+    return ((size_t)(kRb2Hdr + ent_cap) * 4 + (size_t)kRbRows * rb_row_stride<V>(C) * sizeof(V) + 15) & ~(size_t)15;
 }
 template <typename V, int CLS>
 __host__ __device__ inline size_t rb2_bins_bytes(int nslots) {
@@ -407,14 +446,16 @@ __host__ __device__ inline size_t rb2_smem_bytes(int nslots, int C, int ent_cap,
     return kRb2Header + rb2_bins_bytes<V, CLS>(nslots) + (size_t)S * rb2_stage_bytes<V>(C, ent_cap);
 }
 
-template <typename V, int CLS, bool RUNS>
-__global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Params p) {
+template <typename V, int CLS, bool RUNS, int NW>
+__global__ void __launch_bounds__(NW * 32 + 32, 1) group_rowbins2_kernel(Rb2Params p) {
+    constexpr int kRb2Consumers = NW * 32;            // consumer threads = NW * 4 sub-warps of 8 rows
+    constexpr int kRb2Threads = kRb2Consumers + 32;   // + one producer warp
     using Op = Rb2Op<V, CLS>;
     using W = typename Op::W;
     using Acc = typename std::conditional<std::is_floating_point<V>::value, double, long long>::type;
     constexpr int NCH = Op::NCH;
     constexpr int NCLS = 16 / (int)sizeof(V);
-    constexpr int SUBS = 64 / NCLS;
+    constexpr int SUBS = NW * 4 / NCLS;
     static_assert(sizeof(W) == NCH * sizeof(V), "channel words are V-sized");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);       // [S]
@@ -461,18 +502,19 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
     if (tid >= kRb2Consumers) {
         // ---------------------------------------------------------------- producer warp
         if (tid == kRb2Consumers) {
-            const uint32_t plan_bytes = (uint32_t)(kRbHdr + p.ent_cap) * 4u;
-            for (int it = 0; it < ntl; it++) {
-                const int st = it % S;
-                mbar_wait(&empty[st], (uint32_t)(((it / S) & 1) ^ 1));  // fresh barrier: passes at once
+            const uint32_t plan_bytes = (uint32_t)(kRb2Hdr + p.ent_cap) * 4u;
+            int st = 0;
+            uint32_t ph = 1;  // fresh barrier: the first pass over the ring does not wait
+            for (int it = 0; it < ntl; it++, st = (st + 1 == S ? 0 : st + 1), ph ^= (st == 0)) {
+                mbar_wait(&empty[st], ph);
                 const int t = t_beg + it;
                 unsigned char *sb = stage0 + (size_t)st * stage_bytes;
                 const int64_t c0 = (int64_t)t * C;
                 const int cols = (int)min((int64_t)C, p.n - c0);
                 const uint32_t row_bytes = (uint32_t)cols * (uint32_t)sizeof(V);
                 mbar_arrive_expect_tx(&full[st], plan_bytes + (uint32_t)nrows * row_bytes);
-                bulk_g2s(sb, p.plan + (size_t)t * (kRbHdr + p.ent_cap), plan_bytes, &full[st]);
-                V *tile = reinterpret_cast<V *>(sb + (size_t)(kRbHdr + p.ent_cap) * 4);
+                bulk_g2s(sb, p.plan + (size_t)t * (kRb2Hdr + p.ent_cap), plan_bytes, &full[st]);
+                V *tile = reinterpret_cast<V *>(sb + (size_t)(kRb2Hdr + p.ent_cap) * 4);
                 for (int rr = 0; rr < nrows; rr++)
                     bulk_g2s(tile + (size_t)rr * stride, vbase + (int64_t)rr * p.n + c0, row_bytes, &full[st]);
                 // L2 prefetch of the tile PD steps ahead (first step: everything up to it)
@@ -494,8 +536,9 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
         const uint32_t bins_s = smem_u32(bins) + (uint32_t)(q * kRbRows + r) * (uint32_t)sizeof(V);
         const bool active = r < nrows;
         const int wrp = tid >> 5;
-        for (int it = 0; it < ntl; it++) {
-            const int st = it % S;
+        int st = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < ntl; it++, st = (st + 1 == S ? 0 : st + 1), ph ^= (st == 0)) {
             if (it > 0) {
                 // labels move only between ADJACENT ranges from one tile to the next: both neighbour
                 // warps must have finished the previous tile before this one touches its bins
@@ -506,12 +549,14 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
                 if (wrp > 0) mbar_wait(&done[2 * (wrp - 1) + (tp & 1)], par);
                 if (wrp < kRb2Consumers / 32 - 1) mbar_wait(&done[2 * (wrp + 1) + (tp & 1)], par);
             }
-            mbar_wait(&full[st], (uint32_t)((it / S) & 1));
+            mbar_wait(&full[st], ph);
             const uint32_t sb = smem_u32(stage0 + (size_t)st * stage_bytes);
             const uint32_t *hdr = reinterpret_cast<const uint32_t *>(__cvta_shared_to_generic(sb));
-            const uint32_t ent_s = sb + kRbHdr * 4;
-            const uint32_t tile_s = sb + (uint32_t)(kRbHdr + p.ent_cap) * 4 + (uint32_t)r * (uint32_t)stride * (uint32_t)sizeof(V);
-            const int b0 = (int)hdr[q * (SUBS + 1) + j], b1 = (int)hdr[q * (SUBS + 1) + j + 1];
+            const uint32_t ent_s = sb + kRb2Hdr * 4;
+            const uint32_t tile_s = sb + (uint32_t)(kRb2Hdr + p.ent_cap) * 4 + (uint32_t)r * (uint32_t)stride * (uint32_t)sizeof(V);
+            const uint32_t h0 = hdr[q * (SUBS + 1) + j];
+            const int b0 = (int)(h0 & 0x7fffffffu), b1 = (int)(hdr[q * (SUBS + 1) + j + 1] & 0x7fffffffu);
+            const bool sequential = (h0 >> 31) != 0;  // a label occurs twice inside some group of 4 (or RUNS)
             auto val_at = [&](uint32_t e) -> V {
                 return *reinterpret_cast<const V *>(__cvta_shared_to_generic(tile_s + (e >> 16)));
             };
@@ -529,14 +574,62 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
             };
             if (active) {
                 if constexpr (!RUNS) {
-                    for (int i = b0; i < b1; i += 4) {
-                        const uint4 e = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ent_s + (uint32_t)i * 4u));
-                        const V v0 = val_at(e.x), v1 = val_at(e.y), v2 = val_at(e.z), v3 = val_at(e.w);
-                        // read-modify-write in entry order: consecutive entries may share a label
-                        rmw(e.x & 0xffffu, v0);
-                        rmw(e.y & 0xffffu, v1);
-                        rmw(e.z & 0xffffu, v2);
-                        rmw(e.w & 0xffffu, v3);
+                    if (!sequential) {
+                        // the plan guarantees four DIFFERENT labels per group: load the four bins together,
+                        // update, store -- one round trip of shared-memory latency per group instead of four
+                        // software pipeline: the NEXT group's entries and values (read-only data, cannot
+                        // alias the bins) are fetched before this group's read-modify-write
+                        auto ld_ent = [&](int i) -> uint4 {
+                            return *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ent_s + (uint32_t)i * 4u));
+                        };
+                        uint4 e = make_uint4(0, 0, 0, 0);
+                        V v0 = (V)0, v1 = (V)0, v2 = (V)0, v3 = (V)0;
+                        if (b0 < b1) {
+                            e = ld_ent(b0);
+                            v0 = val_at(e.x), v1 = val_at(e.y), v2 = val_at(e.z), v3 = val_at(e.w);
+                        }
+                        for (int i = b0; i < b1; i += 4) {
+                            uint4 en = e;
+                            V n0 = v0, n1 = v1, n2 = v2, n3 = v3;
+                            if (i + 4 < b1) {
+                                en = ld_ent(i + 4);
+                                n0 = val_at(en.x), n1 = val_at(en.y), n2 = val_at(en.z), n3 = val_at(en.w);
+                            }
+                            const uint32_t s0 = e.x & 0xffffu, s1 = e.y & 0xffffu, s2 = e.z & 0xffffu, s3 = e.w & 0xffffu;
+                            W w0, w1, w2, w3;
+                            V *p0 = reinterpret_cast<V *>(&w0), *p1 = reinterpret_cast<V *>(&w1);
+                            V *p2 = reinterpret_cast<V *>(&w2), *p3 = reinterpret_cast<V *>(&w3);
+#pragma unroll
+                            for (int ch = 0; ch < NCH; ch++) {
+                                p0[ch] = *bin_ptr(s0, ch);
+                                p1[ch] = *bin_ptr(s1, ch);
+                                p2[ch] = *bin_ptr(s2, ch);
+                                p3[ch] = *bin_ptr(s3, ch);
+                            }
+                            Op::step(w0, v0, !is_nan(v0));
+                            Op::step(w1, v1, !is_nan(v1));
+                            Op::step(w2, v2, !is_nan(v2));
+                            Op::step(w3, v3, !is_nan(v3));
+#pragma unroll
+                            for (int ch = 0; ch < NCH; ch++) {
+                                *bin_ptr(s0, ch) = p0[ch];
+                                *bin_ptr(s1, ch) = p1[ch];
+                                *bin_ptr(s2, ch) = p2[ch];
+                                *bin_ptr(s3, ch) = p3[ch];
+                            }
+                            e = en;
+                            v0 = n0, v1 = n1, v2 = n2, v3 = n3;
+                        }
+                    } else {
+                        for (int i = b0; i < b1; i += 4) {
+                            const uint4 e = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ent_s + (uint32_t)i * 4u));
+                            const V v0 = val_at(e.x), v1 = val_at(e.y), v2 = val_at(e.z), v3 = val_at(e.w);
+                            // read-modify-write in entry order: consecutive entries may share a label
+                            rmw(e.x & 0xffffu, v0);
+                            rmw(e.y & 0xffffu, v1);
+                            rmw(e.z & 0xffffu, v2);
+                            rmw(e.w & 0xffffu, v3);
+                        }
                     }
                 } else {
                     uint32_t cur = 0xffffffffu;
@@ -614,7 +707,7 @@ __global__ void __launch_bounds__(kRb2Threads, 1) group_rowbins2_kernel(Rb2Param
 // ------------------------------------------------------------------------------------ host
 struct Rb2Geometry {
     bool ok;
-    int C, S, ent_cap, ntiles, nseg, tiles_per_seg, runs, PD;
+    int C, S, ent_cap, ntiles, nseg, tiles_per_seg, runs, PD, NW;
     size_t smem, plan_bytes, plan_smem, aux_bytes;
 };
 
@@ -628,7 +721,7 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
     const size_t bins = rb2_bins_bytes<V, CLS>((int)K);
     if (bins + kRb2Header > kMaxSmemOptIn) return g;
     const size_t avail = kMaxSmemOptIn - kRb2Header - bins;
-    int S = 3, C = 0;
+    int S = 2, C = 0;  // two wide stages beat three narrower ones (config 2: 8.6 vs 9.2 ms): per-tile costs dominate
     if (const char *e = getenv("NBG_RB2_S")) S = atoi(e);
     if (S < 2) S = 2;
     if (S > kRb2MaxStages) S = kRb2MaxStages;
@@ -663,21 +756,25 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
     if (nseg < 1) nseg = 1;
     g.tiles_per_seg = (int)((g.ntiles + nseg - 1) / nseg);
     g.nseg = (g.ntiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
-    g.plan_bytes = (size_t)g.ntiles * (kRbHdr + g.ent_cap) * 4 + 256;
+    g.plan_bytes = (size_t)g.ntiles * (kRb2Hdr + g.ent_cap) * 4 + 256;
     // average run of equal labels inside a class range >= 2: accumulate runs in registers
     g.runs = ((int64_t)C / NCLS >= 2 * K) ? 1 : 0;
     if (const char *e = getenv("NBG_RB2_RUNS")) g.runs = atoi(e);
     g.PD = 0;  // measured: no gain on config 2 (the ring already covers the latency at this rate)
     if (const char *e = getenv("NBG_RB2_PD")) g.PD = atoi(e);
     // global histogram per class + group cuts (ints)
-    g.aux_bytes = ((size_t)NCLS * K + (size_t)NCLS * 33 + 64) * 4;
+    g.aux_bytes = ((size_t)NCLS * K + (size_t)NCLS * 65 + 64) * 4;
+    // consumer warps: 16.  31 (+ producer = 1024 threads) was measured SLOWER on config 2 (10.2 vs 8.6 ms):
+    // half-sized ranges double the padding and the per-tile overhead (+28 % instructions)
+    g.NW = 16;
+    if (const char *e = getenv("NBG_RB2_NW")) g.NW = atoi(e) == 31 ? 31 : 16;
     g.ok = true;
     return g;
 }
 
 inline size_t rb2_scratch_bytes(int64_t n) {
     // narrowest tile is 128 columns: header + padding per tile, 4 bytes per column
-    return (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * (kRbHdr + kRb2Pad) * 4 + 4096 + ((size_t)4 * 65536 + 256) * 4;
+    return (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * (kRb2Hdr + kRb2Pad) * 4 + 4096 + ((size_t)4 * 65536 + 256) * 4;
 }
 
 template <typename V, typename L, int CLS>
@@ -691,7 +788,7 @@ static int rb2_launch(const V *values, const L *labels, void *ws_ch[3], int64_t 
     uint32_t *plan = reinterpret_cast<uint32_t *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
     int *hist = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(plan) + ((g.plan_bytes + 255) & ~(size_t)255));
     int *cuts = hist + (size_t)NCLS * K;
-    constexpr int SUBS = 64 / NCLS;  // ranges per class
+    const int SUBS = g.NW * 4 / NCLS;  // ranges per class
     // labels only: global per-class histogram -> group cuts -> per-tile plan
     int rc = check_cuda(cudaMemsetAsync(hist, 0, (size_t)NCLS * K * sizeof(int), stream), "nbg_group(hist2): memset");
     if (rc) return rc;
@@ -704,7 +801,7 @@ static int rb2_launch(const V *values, const L *labels, void *ws_ch[3], int64_t 
     auto pk = group_plan2_kernel<L, NCLS>;
     rc = allow_big_smem(pk, "nbg_group(plan2): cudaFuncSetAttribute");
     if (rc) return rc;
-    pk<<<(unsigned)g.ntiles, 256, g.plan_smem, stream>>>(labels, n, (int)K, g.C, g.ent_cap, 1, (int)sizeof(V), cuts, plan);
+    pk<<<(unsigned)g.ntiles, 256, g.plan_smem, stream>>>(labels, n, (int)K, g.C, g.ent_cap, 1, (int)sizeof(V), g.runs, g.NW * 4, cuts, plan);
     rc = check_launch("nbg_group(plan2)");
     if (rc) return rc;
     Rb2Params p;
@@ -721,10 +818,13 @@ static int rb2_launch(const V *values, const L *labels, void *ws_ch[3], int64_t 
     auto launch = [&](auto kern) -> int {
         int r2 = allow_big_smem(kern, "nbg_group(rowbins2): cudaFuncSetAttribute");
         if (r2) return r2;
-        kern<<<(unsigned)(groups * g.nseg), kRb2Threads, g.smem, stream>>>(p);
+        kern<<<(unsigned)(groups * g.nseg), g.NW * 32 + 32, g.smem, stream>>>(p);
         return check_launch("nbg_group(rowbins2)");
     };
-    rc = g.runs ? launch(group_rowbins2_kernel<V, CLS, true>) : launch(group_rowbins2_kernel<V, CLS, false>);
+    if (g.NW == 31)
+        rc = g.runs ? launch(group_rowbins2_kernel<V, CLS, true, 31>) : launch(group_rowbins2_kernel<V, CLS, false, 31>);
+    else
+        rc = g.runs ? launch(group_rowbins2_kernel<V, CLS, true, 16>) : launch(group_rowbins2_kernel<V, CLS, false, 16>);
     if (rc) return rc;
     *handled = true;
     return NBG_OK;

@@ -85,12 +85,12 @@ def main():
         ab = rows * n * 4 + n * 8 + rows * K * 4
         rb2 = [dict(NBG_RB2_OFF=1), dict(NBG_RB2_S=3)]
         if "sweep" in args:
-            for S in (2, 3):
-                for NSEG in (1, 2, 3, 4):
-                    rb2.append(dict(NBG_RB2_S=S, NBG_RB2_NSEG=NSEG))
-            rb2.append(dict(NBG_RB2_S=2, NBG_RB2_PD=4))
-            rb2.append(dict(NBG_RB2_S=2, NBG_RB2_C=1536))
-            rb2.append(dict(NBG_RB2_S=2, NBG_RB2_C=1280))
+            for NW in (16, 31):
+                for S in (2, 3):
+                    rb2.append(dict(NBG_RB2_NW=NW, NBG_RB2_S=S))
+            rb2.append(dict(NBG_RB2_NW=31, NBG_RB2_S=2, NBG_RB2_NSEG=2))
+            rb2.append(dict(NBG_RB2_NW=31, NBG_RB2_S=2, NBG_RB2_PD=4))
+            rb2.append(dict(NBG_RB2_NW=31, NBG_RB2_S=4))
         for f, sets in (("group_nansum", rb2), ("group_nancount", rb2[:2]), ("group_nansum_of_squares", rb2[:2]),
                         ("group_nanmean", [{}]), ("group_nanstd", [{}]), ("group_nanmax", [{}]), ("group_nanargmax", [{}])):
             run("cfg2_" + f, lambda: D.run_group(f, a, labels, K, 1), ab, sets, steps)

@@ -1,83 +1,47 @@
 """NCCL version of tests/test_distributed_cpu.py with the real CUDA kernels: needs >= 2 GPUs
-(skipped otherwise).  One process per GPU, torch.distributed over NCCL."""
+(skipped otherwise).  One process per GPU, torch.distributed over NCCL (tests/_nccl_check.py,
+which __graft_entry__.smoke() also runs when it sees two GPUs)."""
 
-import os
-import socket
-
-import numpy as np
 import pytest
 import torch
-import torch.distributed as dist
-import torch.multiprocessing as mp
-
-from oracle import oracle
 
 pytestmark = pytest.mark.gpu
 
 
-def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_matches_unsharded_nccl():
+    from tests import _nccl_check
+
+    summary = _nccl_check.run(2)
+    assert summary["checks"] > 20
 
 
-def fixture_array(shape, nan_frac=0.2, seed=0):
-    a = np.random.RandomState(seed).rand(*shape)
-    return np.where(a > nan_frac, a, np.nan)
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs >= 4 GPUs")
+def test_sharded_matches_unsharded_nccl_4():
+    from tests import _nccl_check
 
-
-def _worker(rank, world, port, results):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    try:
-        from numbagg_b200 import distributed as nd
-
-        n = 400_000
-        a = fixture_array((3, n), seed=1)
-        b = a**2 + 1
-        lo, hi = n * rank // world, n * (rank + 1) // world
-        ta = torch.from_numpy(a[:, lo:hi].copy()).cuda()
-        tb = torch.from_numpy(b[:, lo:hi].copy()).cuda()
-        out = {}
-        out["move_std"] = nd.move_sharded("move_std", ta, window=1000, min_count=500).cpu().numpy()
-        out["move_corr"] = nd.move_sharded("move_corr", ta, tb, window=1000, min_count=500).cpu().numpy()
-        out["move_exp_nanmean"] = nd.move_exp_sharded("move_exp_nanmean", ta, alpha=0.1).cpu().numpy()
-        out["ffill"] = nd.fill_sharded("ffill", ta).cpu().numpy()
-        out["bfill"] = nd.fill_sharded("bfill", ta, limit=3).cpu().numpy()
-        labels = np.random.RandomState(5).randint(0, 5000, size=n)
-        tl = torch.from_numpy(labels[lo:hi].copy()).cuda()
-        for f in ("group_nanargmax", "group_nanfirst", "group_nanvar", "group_nansum", "group_nanlast"):
-            out[f] = nd.group_sharded(f, ta, tl, num_labels=5000, index_offset=lo).cpu().numpy()
-        for f in ("nansum", "nanvar", "nanargmax", "nanmax", "nancount", "anynan"):
-            out[f] = nd.reduce_sharded(f, ta, axis=-1).cpu().numpy()
-        results[rank] = out
-    finally:
-        dist.destroy_process_group()
+    _nccl_check.run(4)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_sharded_matches_unsharded_nccl():
-    world = 2
-    mgr = mp.Manager()
-    results = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
-    n = 400_000
-    a = fixture_array((3, n), seed=1)
-    b = a**2 + 1
-    cat = lambda k: np.concatenate([results[r][k] for r in range(world)], axis=1)
-    np.testing.assert_allclose(cat("move_std"), oracle.move_std(a, window=1000, min_count=500), rtol=1e-9, equal_nan=True)
-    np.testing.assert_allclose(cat("move_corr"), oracle.move_corr(a, b, window=1000, min_count=500), rtol=1e-9, equal_nan=True)
-    np.testing.assert_allclose(cat("move_exp_nanmean"), oracle.move_exp_nanmean(a, alpha=0.1), rtol=1e-12, equal_nan=True)
-    np.testing.assert_array_equal(cat("ffill"), oracle.ffill(a))
-    np.testing.assert_array_equal(cat("bfill"), oracle.bfill(a, limit=3))
-    labels = np.random.RandomState(5).randint(0, 5000, size=n)
-    for f in ("group_nanargmax", "group_nanfirst", "group_nanlast"):
-        np.testing.assert_array_equal(results[0][f], getattr(oracle, f)(a, labels, num_labels=5000, axis=-1))
-    for f in ("nanargmax", "nanmax", "nancount", "anynan"):
-        np.testing.assert_array_equal(results[1][f], getattr(oracle, f)(a, axis=-1))
-    for f in ("nansum", "nanvar"):
-        np.testing.assert_allclose(results[0][f], getattr(oracle, f)(a, axis=-1), rtol=1e-12)
-    for f in ("group_nanvar", "group_nansum"):
-        np.testing.assert_allclose(results[1][f], getattr(oracle, f)(a, labels, num_labels=5000, axis=-1), rtol=1e-11, equal_nan=True)
+def test_tensor_on_other_device_runs_there():
+    """a tensor on cuda:1 while cuda:0 is current must be processed on cuda:1 (pointers,
+    workspaces and stream of ONE device); operands on two devices are an error."""
+    import numpy as np
+
+    import numbagg_b200 as nb
+    from oracle import oracle
+
+    torch.cuda.set_device(0)
+    a = np.random.RandomState(0).rand(50, 3000)
+    a[a < 0.2] = np.nan
+    t1 = torch.from_numpy(a).to("cuda:1")
+    got = nb.move_mean(t1, window=20, min_count=1)
+    assert got.device == t1.device and torch.cuda.current_device() == 0
+    np.testing.assert_allclose(got.cpu().numpy(), oracle.move_mean(a, window=20, min_count=1), rtol=1e-12, equal_nan=True)
+    labels = torch.from_numpy(np.random.RandomState(1).randint(0, 7, size=3000)).to("cuda:1")
+    g = nb.group_nansum(t1, labels, num_labels=7, axis=-1)
+    np.testing.assert_allclose(g.cpu().numpy(), oracle.group_nansum(a, labels.cpu().numpy(), num_labels=7, axis=-1), rtol=1e-12)
+    np.testing.assert_array_equal(nb.ffill(t1).cpu().numpy(), oracle.ffill(a))
+    with pytest.raises(ValueError, match="different devices"):
+        nb.move_cov(t1, t1.to("cuda:0"), window=5)

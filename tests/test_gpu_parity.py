@@ -479,12 +479,16 @@ def test_shard_protocol_halo_carry_partials_single_gpu(nb):
     for f in oracle.GROUPED_FUNCS:
         p0 = D.run_group_partial(f, s0a, tl[:cut].contiguous(), 40, 0)
         p1 = D.run_group_partial(f, s1a, tl[cut:].contiguous(), 40, cut)
-        if f in nd._ADDITIVE_GROUP_OPS:
-            sum_slots, count_slots = nd._ADDITIVE_GROUP_OPS[f]
-            for sl in sum_slots:
-                p0[..., sl] = (p0[..., sl].contiguous().view(torch.float64) + p1[..., sl].contiguous().view(torch.float64)).view(torch.int64)
-            for sl in count_slots:
-                p0[..., sl] += p1[..., sl]
+        how = nd._GROUP_COMBINE.get(f, {})
+        if how and all(h in ("sum_v", "sum_i") for h in how.values()):
+            # additive ops: what the all-reduce does, on the channel views of the two states
+            c0 = D.group_state_channels(f, p0, s0a.shape[0], 40)
+            c1 = D.group_state_channels(f, p1, s0a.shape[0], 40)
+            for ch, h in how.items():
+                if h == "sum_v":
+                    c0[ch].copy_((c0[ch].contiguous().view(torch.float64) + c1[ch].contiguous().view(torch.float64)).view(torch.int64))
+                else:
+                    c0[ch].copy_(c0[ch] + c1[ch])
         else:
             D.run_group_combine(f, np.float64, p0, p1)
         got = D.run_group_finalize(f, np.float64, p0, 1).cpu().numpy()
