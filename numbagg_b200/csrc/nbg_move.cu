@@ -26,6 +26,8 @@
 //   into segments and each segment rebuilds its window from the `window` preceding elements.
 //
 // Algorithmic traffic: one read per input element + one write per output element.
+#include <string.h>
+
 #include "nbg_common.cuh"
 
 namespace nbg {
@@ -70,6 +72,7 @@ struct OpMean {
     // rc = 1/count, rc1 = 1/(count-1) from the per-CTA reciprocal table (<= 1 ulp from a
     // true division; see DESIGN.md "finalisation")
     __device__ static __forceinline__ T finalize_fast(const double *s, double rc, double) { return (T)dmul(s[0], rc); }
+    __device__ static __forceinline__ T finalize_pfx(const double *s, double rc, double rc1, bool &) { return finalize_fast(s, rc, rc1); }
 };
 template <typename T>
 struct OpSum {
@@ -79,6 +82,7 @@ struct OpSum {
     __device__ static __forceinline__ void contrib(T a, T, double *c) { c[0] = (double)a; }
     __device__ static __forceinline__ T finalize(const double *s, int) { return (T)s[0]; }
     __device__ static __forceinline__ T finalize_fast(const double *s, double, double) { return (T)s[0]; }
+    __device__ static __forceinline__ T finalize_pfx(const double *s, double rc, double rc1, bool &) { return finalize_fast(s, rc, rc1); }
 };
 template <typename T, bool SQRT>
 struct OpVar {
@@ -109,6 +113,20 @@ struct OpVar {
         }
         return (T)(SQRT ? fast_sqrt(v) : v);
     }
+    // Branch-free form for the prefix kernel: the float32 root of the float32-rounded variance.  `suspect`
+    // is raised when that image is not a normal finite number (zero, subnormal, inf: the double value may
+    // be tiny or huge); the caller then redoes the tile's outputs with finalize_fast (one branch per tile).
+    __device__ static __forceinline__ T finalize_pfx(const double *s, double rc, double rc1, bool &suspect) {
+        const double v = dmul(dsub(s[1], dmul(dmul(s[0], s[0]), rc)), rc1);
+        if constexpr (SQRT && std::is_same<T, float>::value) {
+            const float t = (float)v;
+            suspect |= ((__float_as_uint(t) & 0x7fffffffu) - 0x00800000u) >= 0x7f000000u;
+            float r;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+            return r;
+        }
+        return (T)(SQRT ? fast_sqrt(v) : v);
+    }
 };
 template <typename T>
 struct OpCov {
@@ -127,6 +145,7 @@ struct OpCov {
     __device__ static __forceinline__ T finalize_fast(const double *s, double rc, double rc1) {
         return (T)dmul(dsub(s[2], dmul(dmul(s[0], s[1]), rc)), rc1);
     }
+    __device__ static __forceinline__ T finalize_pfx(const double *s, double rc, double rc1, bool &) { return finalize_fast(s, rc, rc1); }
 };
 template <typename T>
 struct OpCorr {
@@ -160,6 +179,19 @@ struct OpCorr {
             if (vv > 1e-30 && vv < 1e30) return __fmul_rn((float)cov, rsqrtf((float)vv));  // ~2e-7 relative
         }
         return vv > 0 ? (T)dmul(cov, (vv > 1e-35 && vv < 1e35) ? fast_rsqrt(vv) : rsqrt(vv)) : quiet_nan<T>();
+    }
+    __device__ static __forceinline__ T finalize_pfx(const double *s, double rc, double rc1, bool &suspect) {
+        if constexpr (std::is_same<T, float>::value) {
+            const double avg_a = dmul(s[0], rc), avg_b = dmul(s[1], rc);
+            const double var_a = dsub(dmul(s[3], rc), dmul(avg_a, avg_a));
+            const double var_b = dsub(dmul(s[4], rc), dmul(avg_b, avg_b));
+            const double cov = dsub(dmul(s[2], rc), dmul(avg_a, avg_b));
+            const float t = (float)dmul(var_a, var_b);
+            // not a normal positive float (<= 0, subnormal, inf, NaN): exact path decides (NaN gate, tiny products)
+            suspect |= (__float_as_uint(t) - 0x00800000u) >= 0x7f000000u;
+            return __fmul_rn((float)cov, rsqrtf(t));
+        }
+        return finalize_fast(s, rc, rc1);
     }
 };
 
@@ -406,6 +438,10 @@ __global__ void __launch_bounds__(THREADS) move_rowtile_kernel(MoveParams p) {
     if (tid == 0) bulk_wait_read_all();
 }
 
+}  // namespace nbg
+#include "nbg_move_prefix.cuh"
+namespace nbg {
+
 // ------------------------------------------------------------------------ column-walk kernel
 // (outer, n, inner) C-contiguous, inner > 1.  Thread <-> (outer, segment, inner column).
 struct MoveColParams {
@@ -513,6 +549,22 @@ static int launch_move(const void *a, const void *b, void *out, int64_t outer, i
     constexpr int THREADS = TileCfg<T>::THREADS, E = TileCfg<T>::E;
     using SMfast = MoveSmem<T, Op::NIN, Op::NCH, THREADS, E, true>;
     using SMslow = MoveSmem<T, Op::NIN, Op::NCH, THREADS, E, false>;
+    if constexpr (std::is_same<T, float>::value) {
+        // float32 data, wide windows: prefix differences (every observation widened once)
+        // Measured on config 4 (float32, window 1000; running-window kernel -> prefix kernel): move_std 3.91 -> 3.74 ms,
+        // move_cov 6.94 -> 5.91 ms; move_var 3.56 -> 3.58, move_mean 2.50 -> 2.64, move_corr 10.06 -> 10.37 ms.  Only
+        // the ops it wins on take it (NBG_PFX=all / off force it on / off for A-B runs).
+        constexpr bool kWins = std::is_same<Op, OpVar<T, true>>::value || std::is_same<Op, OpCov<T>>::value;
+        const char *pe = getenv("NBG_PFX");
+        const bool want = pe ? (strcmp(pe, "all") == 0 || (strcmp(pe, "off") != 0 && kWins)) : kWins;
+        if (inner == 1 && window > kDirectMax && want && prefix_fits<T, Op>(window)) {
+            MovePfxParams q = {};
+            q.a = a, q.b = b, q.out = out, q.a_halo = a_halo, q.b_halo = b_halo, q.halo_len = halo_len;
+            q.rows = outer, q.n = n, q.window = (int)window;
+            q.min_count = (int)(min_count > INT32_MAX ? INT32_MAX : min_count);
+            return launch_prefix<T, Op>(q, outer, n, stream);
+        }
+    }
     if (inner == 1 && window <= (1 << 20) && SMslow::total((int)window) <= kMaxSmem) {
         MoveParams p;
         p.a = a, p.b = b, p.out = out, p.a_halo = a_halo, p.b_halo = b_halo, p.halo_len = halo_len;
