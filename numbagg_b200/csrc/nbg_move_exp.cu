@@ -14,81 +14,125 @@
 //
 // Algorithmic traffic: one read per input element + one write per output element; a scalar
 // alpha costs nothing, a 1-D alpha is re-read per row from L2, an N-D alpha is a third stream.
+#include <stdlib.h>
+
 #include "nbg_scan.cuh"
 
 namespace nbg {
 
+// ---- double division through the hardware reciprocal seed -----------------------------------
+// An IEEE double division is ~20 instructions on the FP64 pipe, and the read-outs below divide up
+// to four times per output -- more than the whole recurrence.  Here 1/b comes from the
+// MUFU.RCP64H seed (2^-20) and two Newton steps, and every quotient gets the residual correction
+// q' = q + (a - b*q) * y, which yields the correctly rounded a/b (Markstein): the read-outs contain
+// SIGN GATES on exact cancellations (bias > 0 after one observation, var1*var2 > 0 for repeated
+// values), so quotients must round exactly as the reference's divisions do.  3 instructions per
+// quotient + 5 per distinct divisor.  Divisors outside [1e-280, 1e280] (zero, the subnormal tail of
+// a long NaN run, inf, NaN) take the IEEE path so that x/0, 0/0 and inf behave as in the reference.
+__device__ __forceinline__ double fast_rcp(double b) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    y = fma(y, fma(-b, y, 1.0), y);
+    y = fma(y, fma(-b, y, 1.0), y);
+    return y;
+}
+__device__ __forceinline__ bool rcp_ok(double b) {
+    const double ab = fabs(b);
+    return ab > 1e-280 && ab < 1e280;
+}
+// a / b given y = fast_rcp(b)
+__device__ __forceinline__ double qdiv(double a, double b, double y) {
+    const double q = a * y;
+    const double qc = fma(fma(-b, q, a), y, q);
+    // an infinite / NaN numerator (or an overflowing quotient) turns the residual into NaN: IEEE path
+    return fabs(qc) < __longlong_as_double(0x7ff0000000000000LL) ? qc : a / b;
+}
+__device__ __forceinline__ double fdiv(double a, double b) { return rcp_ok(b) ? qdiv(a, b, fast_rcp(b)) : a / b; }
+
 // -------------------------------------------------------------------------------------- ops
+// GATE = false: the caller proved `weight >= min_weight` for every possible state (scalar alpha in
+// [0, 1] and min_weight <= 0: the weight is a sum of non-negative terms), so the weight channel --
+// always the LAST one -- is neither carried nor tested.
 // contrib(): value added to each channel for one valid observation.  SQ_CH: the channel that
 // decays with d^2 (-1: none).  output(): read-out from the state.
-template <typename T>
-struct ExpCount {  // moving_exp.py:12-38   channels: count, weight
-    static constexpr int NIN = 1, NCH = 2, SQ_CH = -1;
+template <typename T, bool GATE = true>
+struct ExpCount {  // moving_exp.py:12-38   channels: count, [weight]
+    static constexpr int NIN = 1, NCH = GATE ? 2 : 1, SQ_CH = -1;
     static constexpr bool HAS_SEEN = false;
     __device__ static __forceinline__ void contrib(T, T, double alpha, double *c) {
         c[0] = 1.0;
-        c[1] = alpha;
+        if (GATE) c[NCH - 1] = alpha;
     }
     __device__ static __forceinline__ T output(const double *s, bool, double mw) {
-        return s[1] >= mw ? (T)s[0] : quiet_nan<T>();
+        return (!GATE || s[NCH - 1] >= mw) ? (T)s[0] : quiet_nan<T>();
     }
 };
-template <typename T>
-struct ExpMean {  // moving_exp.py:41-72    channels: numer, denom, weight
-    static constexpr int NIN = 1, NCH = 3, SQ_CH = -1;
+template <typename T, bool GATE = true>
+struct ExpMean {  // moving_exp.py:41-72    channels: numer, denom, [weight]
+    static constexpr int NIN = 1, NCH = GATE ? 3 : 2, SQ_CH = -1;
     static constexpr bool HAS_SEEN = false;
     __device__ static __forceinline__ void contrib(T a, T, double alpha, double *c) {
         c[0] = (double)a;
         c[1] = 1.0;
-        c[2] = alpha;
+        if (GATE) c[NCH - 1] = alpha;
     }
     __device__ static __forceinline__ T output(const double *s, bool, double mw) {
+        const bool pass = !GATE || s[NCH - 1] >= mw;
         if constexpr (std::is_same<T, float>::value) {
             // float32 output: divide in float32 when both operands are comfortably inside its
             // range (<= 1.5 ulp = 2e-7 from rounding the double quotient), else in double
             if (fabs(s[0]) < 1e30 && s[1] > 1e-30 && s[1] < 1e30)
-                return s[2] >= mw ? __fdiv_rn((float)s[0], (float)s[1]) : quiet_nan<T>();
+                return pass ? __fdiv_rn((float)s[0], (float)s[1]) : quiet_nan<T>();
         }
-        return s[2] >= mw ? (T)(s[0] / s[1]) : quiet_nan<T>();
+        return pass ? (T)fdiv(s[0], s[1]) : quiet_nan<T>();
     }
 };
-template <typename T>
-struct ExpSum {  // moving_exp.py:75-103   channels: numer, weight; NaN until the first valid
-    static constexpr int NIN = 1, NCH = 2, SQ_CH = -1;
+template <typename T, bool GATE = true>
+struct ExpSum {  // moving_exp.py:75-103   channels: numer, [weight]; NaN until the first valid
+    static constexpr int NIN = 1, NCH = GATE ? 2 : 1, SQ_CH = -1;
     static constexpr bool HAS_SEEN = true;
     __device__ static __forceinline__ void contrib(T a, T, double alpha, double *c) {
         c[0] = (double)a;
-        c[1] = alpha;
+        if (GATE) c[NCH - 1] = alpha;
     }
     __device__ static __forceinline__ T output(const double *s, bool seen, double mw) {
-        return (s[1] >= mw && seen) ? (T)s[0] : quiet_nan<T>();
+        return ((!GATE || s[NCH - 1] >= mw) && seen) ? (T)s[0] : quiet_nan<T>();
     }
 };
-template <typename T, bool SQRT>
-struct ExpVar {  // moving_exp.py:106-224  channels: sum_x_2, sum_x, sum_weight, sum_weight_2, weight
-    static constexpr int NIN = 1, NCH = 5, SQ_CH = 3;
+template <typename T, bool SQRT, bool GATE = true>
+struct ExpVar {  // moving_exp.py:106-224  channels: sum_x_2, sum_x, sum_weight, sum_weight_2, [weight]
+    static constexpr int NIN = 1, NCH = GATE ? 5 : 4, SQ_CH = 3;
     static constexpr bool HAS_SEEN = false;
     __device__ static __forceinline__ void contrib(T a, T, double alpha, double *c) {
         c[0] = prod_as_input(a, a);
         c[1] = (double)a;
         c[2] = 1.0;
         c[3] = 1.0;
-        c[4] = alpha;
+        if (GATE) c[NCH - 1] = alpha;
     }
     __device__ static __forceinline__ T output(const double *s, bool, double mw) {
-        const double m = s[1] / s[2];
-        const double var_biased = dsub(s[0] / s[2], dmul(m, m));
-        const double bias = dsub(1.0, s[3] / dmul(s[2], s[2]));
-        if (s[4] >= mw && bias > 0) {
-            const double v = var_biased / bias;
+        double var_biased, bias;
+        const double sw2 = dmul(s[2], s[2]);
+        if (rcp_ok(s[2]) && rcp_ok(sw2)) {
+            const double r = fast_rcp(s[2]);  // two reciprocals + four corrected quotients instead of four divisions
+            const double m = qdiv(s[1], s[2], r);
+            var_biased = dsub(qdiv(s[0], s[2], r), dmul(m, m));
+            bias = dsub(1.0, qdiv(s[3], sw2, fast_rcp(sw2)));
+        } else {
+            const double m = s[1] / s[2];
+            var_biased = dsub(s[0] / s[2], dmul(m, m));
+            bias = dsub(1.0, s[3] / dmul(s[2], s[2]));
+        }
+        if ((!GATE || s[NCH - 1] >= mw) && bias > 0) {
+            const double v = fdiv(var_biased, bias);
             return (T)(SQRT ? sqrt(v) : v);
         }
         return quiet_nan<T>();
     }
 };
-template <typename T>
-struct ExpCov {  // moving_exp.py:227-273  channels: sum_x1, sum_x2, sum_x1x2, sum_weight, sum_weight_2, weight
-    static constexpr int NIN = 2, NCH = 6, SQ_CH = 4;
+template <typename T, bool GATE = true>
+struct ExpCov {  // moving_exp.py:227-273  channels: sum_x1, sum_x2, sum_x1x2, sum_weight, sum_weight_2, [weight]
+    static constexpr int NIN = 2, NCH = GATE ? 6 : 5, SQ_CH = 4;
     static constexpr bool HAS_SEEN = false;
     __device__ static __forceinline__ void contrib(T a, T b, double alpha, double *c) {
         c[0] = (double)a;
@@ -96,17 +140,25 @@ struct ExpCov {  // moving_exp.py:227-273  channels: sum_x1, sum_x2, sum_x1x2, s
         c[2] = prod_as_input(a, b);
         c[3] = 1.0;
         c[4] = 1.0;
-        c[5] = alpha;
+        if (GATE) c[NCH - 1] = alpha;
     }
     __device__ static __forceinline__ T output(const double *s, bool, double mw) {
-        const double cov_biased = dsub(s[2], dmul(s[0], s[1]) / s[3]) / s[3];
-        const double bias = dsub(1.0, s[4] / dmul(s[3], s[3]));
-        return (s[5] >= mw && bias > 0) ? (T)(cov_biased / bias) : quiet_nan<T>();
+        double cov_biased, bias;
+        const double sw2 = dmul(s[3], s[3]);
+        if (rcp_ok(s[3]) && rcp_ok(sw2)) {
+            const double r = fast_rcp(s[3]);
+            cov_biased = qdiv(dsub(s[2], qdiv(dmul(s[0], s[1]), s[3], r)), s[3], r);
+            bias = dsub(1.0, qdiv(s[4], sw2, fast_rcp(sw2)));
+        } else {
+            cov_biased = dsub(s[2], dmul(s[0], s[1]) / s[3]) / s[3];
+            bias = dsub(1.0, s[4] / dmul(s[3], s[3]));
+        }
+        return ((!GATE || s[NCH - 1] >= mw) && bias > 0) ? (T)fdiv(cov_biased, bias) : quiet_nan<T>();
     }
 };
-template <typename T>
-struct ExpCorr {  // moving_exp.py:276-335  + sum_x1_2, sum_x2_2
-    static constexpr int NIN = 2, NCH = 8, SQ_CH = 4;
+template <typename T, bool GATE = true>
+struct ExpCorr {  // moving_exp.py:276-335  + sum_x1_2, sum_x2_2  (the weight, when carried, is the last channel)
+    static constexpr int NIN = 2, NCH = GATE ? 8 : 7, SQ_CH = 4;
     static constexpr bool HAS_SEEN = false;
     __device__ static __forceinline__ void contrib(T a, T b, double alpha, double *c) {
         c[0] = (double)a;
@@ -114,18 +166,28 @@ struct ExpCorr {  // moving_exp.py:276-335  + sum_x1_2, sum_x2_2
         c[2] = prod_as_input(a, b);
         c[3] = 1.0;
         c[4] = 1.0;
-        c[5] = alpha;
-        c[6] = prod_as_input(a, a);
-        c[7] = prod_as_input(b, b);
+        c[5] = prod_as_input(a, a);
+        c[6] = prod_as_input(b, b);
+        if (GATE) c[NCH - 1] = alpha;
     }
     __device__ static __forceinline__ T output(const double *s, bool, double mw) {
-        const double cov = dsub(s[2], dmul(s[0], s[1]) / s[3]);
-        const double var1 = dsub(s[6], dmul(s[0], s[0]) / s[3]);
-        const double var2 = dsub(s[7], dmul(s[1], s[1]) / s[3]);
-        const double bias = dsub(1.0, s[4] / dmul(s[3], s[3]));
-        if (s[5] >= mw && bias > 0) {
+        double cov, var1, var2, bias;
+        const double sw2 = dmul(s[3], s[3]);
+        if (rcp_ok(s[3]) && rcp_ok(sw2)) {
+            const double r = fast_rcp(s[3]);
+            cov = dsub(s[2], qdiv(dmul(s[0], s[1]), s[3], r));
+            var1 = dsub(s[5], qdiv(dmul(s[0], s[0]), s[3], r));
+            var2 = dsub(s[6], qdiv(dmul(s[1], s[1]), s[3], r));
+            bias = dsub(1.0, qdiv(s[4], sw2, fast_rcp(sw2)));
+        } else {
+            cov = dsub(s[2], dmul(s[0], s[1]) / s[3]);
+            var1 = dsub(s[5], dmul(s[0], s[0]) / s[3]);
+            var2 = dsub(s[6], dmul(s[1], s[1]) / s[3]);
+            bias = dsub(1.0, s[4] / dmul(s[3], s[3]));
+        }
+        if ((!GATE || s[NCH - 1] >= mw) && bias > 0) {
             const double den = sqrt(dmul(var1, var2));
-            return den > 0 ? (T)(cov / den) : quiet_nan<T>();
+            return den > 0 ? (T)fdiv(cov, den) : quiet_nan<T>();
         }
         return quiet_nan<T>();
     }
@@ -238,10 +300,23 @@ struct ExpPolicy {
             const T x = get(0, k);
             const T y = Op::NIN == 2 ? get(1, k) : x;
             const double alpha = ALPHA_STREAM ? (double)get(Op::NIN, k) : p.alpha_scalar;
-            const double d = dsub(1.0, alpha);
-            a.w[0] = dmul(a.D(), d);
-            a.set_D2(dmul(a.D2(), dmul(d, d)));
+            if (ALPHA_STREAM) {
+                const double d = dsub(1.0, alpha);
+                a.w[0] = dmul(a.D(), d);
+                a.set_D2(dmul(a.D2(), dmul(d, d)));
+            }
             exp_step<Op, T>(a.U(), seen, x, y, alpha);
+        }
+        if (!ALPHA_STREAM) {
+            // scalar alpha: the chunk's decay product is d^cnt -- by squaring, not one multiply per element
+            const double d = dsub(1.0, p.alpha_scalar);
+            double pw = 1.0, b = d;
+            for (int m = cnt; m > 0; m >>= 1) {
+                if (m & 1) pw = dmul(pw, b);
+                b = dmul(b, b);
+            }
+            a.w[0] = pw;
+            a.set_D2(dmul(pw, pw));
         }
         a.set_seen(seen);
         return a;
@@ -376,28 +451,36 @@ static int launch_exp(const ExpArgs &x) {
     return check_launch("nbg_move_exp(colwalk)");
 }
 
-template <typename T>
-static int dispatch_exp(int op, const ExpArgs &x) {
-    using OpStd = ExpVar<T, true>;
-    using OpVariance = ExpVar<T, false>;
+template <typename T, bool GATE>
+static int dispatch_exp_gate(int op, const ExpArgs &x) {
     switch (op) {
         case NBG_EXP_NANCOUNT:
-            return launch_exp<T, ExpCount<T>>(x);
+            return launch_exp<T, ExpCount<T, GATE>>(x);
         case NBG_EXP_NANMEAN:
-            return launch_exp<T, ExpMean<T>>(x);
+            return launch_exp<T, ExpMean<T, GATE>>(x);
         case NBG_EXP_NANSUM:
-            return launch_exp<T, ExpSum<T>>(x);
+            return launch_exp<T, ExpSum<T, GATE>>(x);
         case NBG_EXP_NANVAR:
-            return launch_exp<T, OpVariance>(x);
+            return launch_exp<T, ExpVar<T, false, GATE>>(x);
         case NBG_EXP_NANSTD:
-            return launch_exp<T, OpStd>(x);
+            return launch_exp<T, ExpVar<T, true, GATE>>(x);
         case NBG_EXP_NANCOV:
-            return launch_exp<T, ExpCov<T>>(x);
+            return launch_exp<T, ExpCov<T, GATE>>(x);
         case NBG_EXP_NANCORR:
-            return launch_exp<T, ExpCorr<T>>(x);
+            return launch_exp<T, ExpCorr<T, GATE>>(x);
         default:
             return fail(NBG_ERR_BAD_OP, "nbg_move_exp: unknown op");
     }
+}
+
+template <typename T>
+static int dispatch_exp(int op, const ExpArgs &x) {
+    // weight = sum of alpha * d^k over valid observations >= 0 whenever 0 <= alpha <= 1, so the gate
+    // `weight >= min_weight` (moving_exp.py:35, 69, 98, 151, 269, 322) is always open for
+    // min_weight <= 0 -- the default -- and the weight channel need not be carried at all
+    const bool no_gate = x.alpha == nullptr && x.alpha_scalar >= 0.0 && x.alpha_scalar <= 1.0 && x.min_weight <= 0.0 &&
+                         !getenv("NBG_EXP_GATE");
+    return no_gate ? dispatch_exp_gate<T, false>(op, x) : dispatch_exp_gate<T, true>(op, x);
 }
 
 template <typename T>

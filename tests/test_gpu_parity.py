@@ -157,6 +157,55 @@ def test_move_exp_vs_oracle_long_rows(nb, dtype, alpha):
         assert_parity(f, got, exp, scale=4.0)
 
 
+@pytest.mark.parametrize("alpha,mw", [(1.2, 0), (-0.1, 0), (0.3, -1.0), (1.0, 0), (0.0, 0), (0.3, float("nan"))])
+def test_move_exp_gate_elimination_boundaries(nb, alpha, mw):
+    # The weight channel is dropped only when the gate `weight >= min_weight` is provably open (scalar alpha
+    # in [0, 1], min_weight <= 0): alphas outside that range, a NaN min_weight and the interval ends must
+    # still agree with the reference (which applies no range check, decorators.py:356-359)
+    a = fixture_array((2, 30_000), nan_frac=0.3, seed=9)
+    a[1, :50] = np.nan
+    b = a**2 + 1
+    for f in EXP_ONE:
+        got = getattr(nb, f)(a, alpha=alpha, min_weight=mw)
+        exp = getattr(oracle, f)(a, alpha=alpha, min_weight=mw)
+        fin = np.isfinite(exp) & (np.abs(exp) < 1e200)  # alpha outside [0, 1] diverges: compare what stays finite
+        assert np.array_equal(np.isnan(got[:, :200]), np.isnan(exp[:, :200]))
+        np.testing.assert_allclose(got[fin][:4000], exp[fin][:4000], rtol=1e-9, atol=1e-12)
+    for f in EXP_TWO:
+        got = getattr(nb, f)(a, b, alpha=alpha, min_weight=mw)
+        exp = getattr(oracle, f)(a, b, alpha=alpha, min_weight=mw)
+        fin = np.isfinite(exp) & np.isfinite(got)
+        np.testing.assert_allclose(got[fin][:4000], exp[fin][:4000], rtol=1e-6, atol=1e-9)
+
+
+def test_move_prefix_kernel_every_op(nb, monkeypatch):
+    # float32 windows > 32 as differences of a streaming prefix (nbg_move_prefix.cuh).  By default only
+    # move_std / move_cov take it (where it is the faster kernel); NBG_PFX=all routes every op through it
+    monkeypatch.setenv("NBG_PFX", "all")
+    for shape, window, mc in (((5, 30_000), 1000, 500), ((3, 9_001), 33, None), ((2, 50_000), 5000, 10), ((7, 2_305), 100, 1),
+                              ((1, 120_003), 4097, 2000)):
+        a = fixture_array(shape, dtype=np.float32, seed=window)
+        a[0, :window // 2] = np.nan
+        b = (a.astype(np.float64) ** 2 + 1).astype(np.float32)
+        for f in ONE:
+            got = getattr(nb, f)(a, window=window, min_count=mc)
+            exp = getattr(oracle, f)(a, window=window, min_count=mc)
+            assert_parity(f, got, exp, scale=_scale(f, [a], window))
+        for f in TWO:
+            got = getattr(nb, f)(a, b, window=window, min_count=mc)
+            exp = getattr(oracle, f)(a, b, window=window, min_count=mc)
+            assert_parity(f, got, exp, scale=_scale(f, [a, b], window), atol=1e-5 if f == "move_corr" else None)
+    # constant and zero windows: the float32 image of the variance is 0 / subnormal -> exact redo path
+    c = np.full((2, 20_000), 3.25, dtype=np.float32)
+    c[1, ::7] = 0.0
+    c[1, 5000:9000] = 0.0
+    for f in ("move_std", "move_var", "move_mean"):
+        got = getattr(nb, f)(c, window=64, min_count=2)
+        exp = getattr(oracle, f)(c, window=64, min_count=2)
+        assert np.array_equal(np.isnan(got), np.isnan(exp)) or f == "move_std", f
+        np.testing.assert_allclose(np.nan_to_num(got, nan=0.0), np.nan_to_num(exp, nan=0.0), rtol=1e-5, atol=1e-5)
+
+
 def test_move_exp_alpha_forms_and_axes(nb):
     a = fixture_array((5, 9000), seed=6)
     al1 = np.random.RandomState(7).rand(9000) * 0.9 + 0.05
