@@ -427,7 +427,10 @@ def parity_checks(torch, nb, D, oracle, wl, tensors, labels, out, step_on, lo_el
                     res[tag]["compared_as"] = "variance"
                     continue
                 if func == "move_corr":
-                    scale = 1e-1  # correlations divide by differences of running sums the reference never re-syncs
+                    # correlations divide by differences of running sums the reference never re-syncs: absolute
+                    # floor 1e-9 (float64) / 1e-4 (float32) on a value in [-1, 1], the same as smoke() and the
+                    # sharded block use (observed on config 1s, window 20: 9e-12)
+                    scale = 1e3 if dt == "f64" else 10.0
             else:
                 exp = f(host[0], axis=-1) if params["axis"] == -1 else None
                 if exp is None:
@@ -473,14 +476,15 @@ def parity_checks(torch, nb, D, oracle, wl, tensors, labels, out, step_on, lo_el
 
 
 # ------------------------------------------------------------------------------ sharded block
-def sharded_block(torch, dist, nd, D, device, rank, world, steps=3):
+def sharded_block(torch, dist, nd, D, device, rank, world, steps=5):
     """Core-axis / element-sharded forms of BASELINE configs 3-5 over NCCL, at
     full size: every rank regenerates the whole input (same seeds), computes the UNSHARDED result on
     its own GPU, runs the sharded form on its contiguous shard and compares its whole shard."""
     results = {}
 
     def timed(fn):
-        fn()
+        for _ in range(3):  # NCCL sets collectives / p2p channels up lazily: first calls are not representative
+            fn()
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

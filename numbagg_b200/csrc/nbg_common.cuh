@@ -232,9 +232,9 @@ __device__ __forceinline__ void span_prefetch_l2(const T *row, int64_t p0, int l
     if (b > a) bulk_prefetch_l2(reinterpret_cast<const void *>(a), (uint32_t)(b - a));
 }
 
-// Tiles ahead of the running one that a CTA prefetches into L2 (0 = off).  Default: one full
-// wave of resident CTAs; NBG_PREFETCH_TILES overrides (tuning / A-B measurement).
-int prefetch_distance(int resident_ctas_per_sm);
+// Tiles ahead of the running one that a CTA prefetches into L2 (0 = off).  Default: ~6.5 MB of
+// input ahead, at most one wave of resident CTAs; NBG_PREFETCH_TILES overrides (tuning / A-B measurement).
+int prefetch_distance(int resident_ctas_per_sm, size_t tile_bytes);
 
 // Bulk-store s[0, cnt) to g[0, cnt): when s and g share their 16-byte phase thread 0 issues
 // the aligned middle as one bulk store and all threads store the unaligned edges; otherwise

@@ -181,8 +181,9 @@ __device__ __forceinline__ RbBin<V, CLS> rb2_to_bin(const typename Rb2Op<V, CLS>
 // ----------------------------------------------------------------------------------- plan
 // Per tile: header hdr[q * (SUBS + 1) + j] = first entry of range j of class q (the next range
 // starts where this one ends; every range is a multiple of 4 entries long), then the entries
-// (byte offset of the column inside a tile row << 16 | slot) -- both fields pre-scaled so that the
-// kernel forms each shared-memory address with one or two integer instructions.  Padding entries
+// (byte offset of the column inside a tile row << 19 | label * 128) -- both fields pre-scaled (13 + 19
+// bits: tile rows up to 8 KB, up to 4094 labels) so that the kernel forms each shared-memory address
+// with one or two integer instructions.  Padding entries
 // point at the dummy slot `nslots` and at column q (same class, always inside the tile).  A CTA of a cluster of `nc` owns the labels with
 // label % nc == rank and addresses them as slot = label / nc; its plan lists only those.
 // Global label histogram per column class (hist[class * K + label], zeroed by the caller).
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ 
             if (valid) {
                 const int rk = __popc(m & ((1u << lane) - 1u));
                 const int lab = (int)(key % (uint32_t)K);
-                sent[cursor[key] + rk] = ((uint32_t)(j * vsize) << 16) | (uint32_t)(lab / nc);
+                sent[cursor[key] + rk] = ((uint32_t)(j * vsize) << 19) | ((uint32_t)(lab / nc) << 7);
             }
             __syncwarp();
             if (valid && (m & ((1u << lane) - 1u)) == 0) cursor[key] += __popc(m);
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ 
                 int lab = cq[j];
                 if (ce > cs) {
                     const int e = cs + (int)(((long long)j * (ce - cs)) / SUBS);
-                    lab = (int)(sent[e] & 0xffffu) * nc + rank;  // label of the entry at the even split
+                    lab = (int)((sent[e] & 0x7ffffu) >> 7) * nc + rank;  // label of the entry at the even split
                 }
                 lab = max(m_lo, min(lab, m_hi));
                 b = offs[q * K + lab];  // first entry of that label in this tile (lab == K: end of class)
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ 
         int seq = runs;
         if (!seq && cnt > 0) {
             // longest label run of this range
-            const int l0 = (int)(sent[ub[tid]] & 0xffffu) * nc + rank, l1 = (int)(sent[ub[tid + 1] - 1] & 0xffffu) * nc + rank;
+            const int l0 = (int)((sent[ub[tid]] & 0x7ffffu) >> 7) * nc + rank, l1 = (int)((sent[ub[tid + 1] - 1] & 0x7ffffu) >> 7) * nc + rank;
             int longest = 0;
             for (int lab = l0; lab <= l1; lab++) {
                 const int a0 = max(offs[q * K + lab], ub[tid]), a1 = min(offs[q * K + lab + 1], ub[tid + 1]);
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(256) group_plan2_kernel(const L *__restrict__ 
     if (tid < nsub) {
         const int cnt = ub[tid + 1] - ub[tid];
         const int q = tid / SUBS;
-        const uint32_t dummy = ((uint32_t)(q * vsize) << 16) | (uint32_t)nslots;
+        const uint32_t dummy = ((uint32_t)(q * vsize) << 19) | ((uint32_t)nslots << 7);
         if (cnt & 3) {
             const int m = (cnt + 3) & ~3;
             for (int i = max(0, m - 16); i < m; i++) out[kRb2Hdr + pst[tid] + i] = dummy;  // padding lives in the last 4 groups
@@ -558,10 +559,10 @@ __global__ void __launch_bounds__(NW * 32 + 32, 1) group_rowbins2_kernel(Rb2Para
             const int b0 = (int)(h0 & 0x7fffffffu), b1 = (int)(hdr[q * (SUBS + 1) + j + 1] & 0x7fffffffu);
             const bool sequential = (h0 >> 31) != 0;  // a label occurs twice inside some group of 4 (or RUNS)
             auto val_at = [&](uint32_t e) -> V {
-                return *reinterpret_cast<const V *>(__cvta_shared_to_generic(tile_s + (e >> 16)));
+                return *reinterpret_cast<const V *>(__cvta_shared_to_generic(tile_s + (e >> 19)));
             };
             auto bin_ptr = [&](uint32_t slot, int ch) -> V * {
-                return reinterpret_cast<V *>(__cvta_shared_to_generic(bins_s + (uint32_t)ch * (uint32_t)ch_bytes + slot * 128u));
+                return reinterpret_cast<V *>(__cvta_shared_to_generic(bins_s + (uint32_t)ch * (uint32_t)ch_bytes + slot));  // `slot` is pre-scaled: label * 128
             };
             auto rmw = [&](uint32_t slot, V v) {
                 W w;
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(NW * 32 + 32, 1) group_rowbins2_kernel(Rb2Para
                                 en = ld_ent(i + 4);
                                 n0 = val_at(en.x), n1 = val_at(en.y), n2 = val_at(en.z), n3 = val_at(en.w);
                             }
-                            const uint32_t s0 = e.x & 0xffffu, s1 = e.y & 0xffffu, s2 = e.z & 0xffffu, s3 = e.w & 0xffffu;
+                            const uint32_t s0 = e.x & 0x7ffffu, s1 = e.y & 0x7ffffu, s2 = e.z & 0x7ffffu, s3 = e.w & 0x7ffffu;
                             W w0, w1, w2, w3;
                             V *p0 = reinterpret_cast<V *>(&w0), *p1 = reinterpret_cast<V *>(&w1);
                             V *p2 = reinterpret_cast<V *>(&w2), *p3 = reinterpret_cast<V *>(&w3);
@@ -625,10 +626,10 @@ __global__ void __launch_bounds__(NW * 32 + 32, 1) group_rowbins2_kernel(Rb2Para
                             const uint4 e = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ent_s + (uint32_t)i * 4u));
                             const V v0 = val_at(e.x), v1 = val_at(e.y), v2 = val_at(e.z), v3 = val_at(e.w);
                             // read-modify-write in entry order: consecutive entries may share a label
-                            rmw(e.x & 0xffffu, v0);
-                            rmw(e.y & 0xffffu, v1);
-                            rmw(e.z & 0xffffu, v2);
-                            rmw(e.w & 0xffffu, v3);
+                            rmw(e.x & 0x7ffffu, v0);
+                            rmw(e.y & 0x7ffffu, v1);
+                            rmw(e.z & 0x7ffffu, v2);
+                            rmw(e.w & 0x7ffffu, v3);
                         }
                     }
                 } else {
@@ -644,7 +645,7 @@ __global__ void __launch_bounds__(NW * 32 + 32, 1) group_rowbins2_kernel(Rb2Para
                         for (int ch = 0; ch < NCH; ch++) *bin_ptr(cur, ch) = ww[ch];
                     };
                     auto one = [&](uint32_t e, V v) {
-                        const uint32_t slot = e & 0xffffu;
+                        const uint32_t slot = e & 0x7ffffu;
                         if (slot != cur) {
                             if (cur != 0xffffffffu) flush_run();
                             cur = slot;
@@ -716,7 +717,7 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
     Rb2Geometry g = {};
     constexpr int PER16 = 16 / (int)sizeof(V);
     constexpr int NCLS = PER16;
-    if (K <= 0 || K > 65534 || n <= 0 || n >= ((int64_t)1 << 31) || (n % PER16) != 0 || rows < 1) return g;
+    if (K <= 0 || K > 4094 || n <= 0 || n >= ((int64_t)1 << 31) || (n % PER16) != 0 || rows < 1) return g;
     if (getenv("NBG_RB2_OFF")) return g;
     const size_t bins = rb2_bins_bytes<V, CLS>((int)K);
     if (bins + kRb2Header > kMaxSmemOptIn) return g;
@@ -726,7 +727,7 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
     if (S < 2) S = 2;
     if (S > kRb2MaxStages) S = kRb2MaxStages;
     auto fit = [&](int s) {
-        int c = 2048;
+        int c = 8192 / (int)sizeof(V) - 64;  // the entry's 13-bit byte offset
         while (c >= 64 && (size_t)s * rb2_stage_bytes<V>(c, c + kRb2Pad) > avail) c -= 64;
         return c >= 64 ? c : 0;
     };

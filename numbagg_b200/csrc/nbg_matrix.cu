@@ -131,6 +131,238 @@ __global__ void __launch_bounds__(kMatThreads) mat_move_kernel(const T *__restri
     }
 }
 
+// ---- long observation axes: segments -------------------------------------------------------------
+// One thread per (batch item, segment, i, j).  A segment rebuilds the state of its pair from the
+// `window` observations before it (additions only, in order) and then runs the reference's
+// recurrence.  The reference never re-syncs its running sums, so the results agree to rounding of
+// the running sums, not bit for bit; short axes keep the single-segment kernel
+// above.  Quotients by the integer count come from a per-CTA table of correctly rounded reciprocals
+// plus the residual correction q' = q + (a - c q) y (Markstein: correctly rounded a / c), i.e. they
+// round exactly like the reference's divisions at a quarter of the FP64 instructions.
+__device__ __forceinline__ double tab_div(double a, double c, double y) {
+    const double q = a * y;
+    const double qc = fma(fma(-c, q, a), y, q);
+    // tiny / non-finite quotients: the residual is not exact there, take the IEEE division
+    return (fabs(q) > 1e-290 && fabs(qc) < __longlong_as_double(0x7ff0000000000000LL)) ? qc : a / c;
+}
+
+constexpr int kMatSegThreads = 256;
+constexpr int kMatRcpMax = 4096;  // windows up to this long use the reciprocal table
+
+template <typename T, bool CORR, bool TABLE>
+__global__ void __launch_bounds__(kMatSegThreads) mat_move_seg_kernel(const T *__restrict__ a, T *__restrict__ out, i64 batch,
+                                                                      i64 no, int nv, i64 window, i64 min_count, i64 seg_len,
+                                                                      int nseg, int blocks_per_seg) {
+    extern __shared__ double rc_tab[];  // rc_tab[c] = 1 / c
+    if (TABLE) {
+        for (int c = threadIdx.x; c <= (int)window; c += kMatSegThreads) rc_tab[c] = c ? 1.0 / (double)c : 0.0;
+        __syncthreads();
+    }
+    const i64 q = (i64)nv * nv;
+    const int pb = blockIdx.x % blocks_per_seg;
+    const i64 sb = blockIdx.x / blocks_per_seg;
+    const int seg = (int)(sb % nseg);
+    const i64 bi = sb / nseg;
+    const int p = pb * kMatSegThreads + threadIdx.x;
+    if (p >= q || bi >= batch) return;
+    const int i = p / nv, j = p % nv;
+    const T *ab = a + bi * no * nv;
+    T *ob = out + bi * no * q + p;
+    if (min_count < 1) min_count = 1;
+    const i64 corr_min = min_count > 2 ? min_count : 2;
+    const i64 t0 = (i64)seg * seg_len;
+    const i64 t1 = t0 + seg_len < no ? t0 + seg_len : no;
+    T si = 0, sj = 0, sqi = 0, sqj = 0, pr = 0;
+    int n = 0;
+    for (i64 t = t0 > window ? t0 - window : 0; t < t0; t++) {
+        const T vi = ab[t * nv + i], vj = ab[t * nv + j];
+        if (!(is_nan(vi) || is_nan(vj))) {
+            si += vi;
+            sj += vj;
+            if (CORR) {
+                sqi += mul_t(vi, vi);
+                sqj += mul_t(vj, vj);
+            }
+            pr += mul_t(vi, vj);
+            n += 1;
+        }
+    }
+    auto quot = [&](double x, int c) -> double {
+        if (TABLE) return tab_div(x, (double)c, rc_tab[c]);
+        return x / (double)c;
+    };
+    for (i64 t = t0; t < t1; t++) {
+        if (t >= window) {
+            const T vi = ab[(t - window) * nv + i], vj = ab[(t - window) * nv + j];
+            if (!(is_nan(vi) || is_nan(vj))) {
+                si -= vi;
+                sj -= vj;
+                if (CORR) {
+                    sqi -= mul_t(vi, vi);
+                    sqj -= mul_t(vj, vj);
+                }
+                pr -= mul_t(vi, vj);
+                n -= 1;
+            }
+        }
+        {
+            const T vi = ab[t * nv + i], vj = ab[t * nv + j];
+            if (!(is_nan(vi) || is_nan(vj))) {
+                si += vi;
+                sj += vj;
+                if (CORR) {
+                    sqi += mul_t(vi, vi);
+                    sqj += mul_t(vj, vj);
+                }
+                pr += mul_t(vi, vj);
+                n += 1;
+            }
+        }
+        T res = quiet_nan<T>();
+        if (CORR) {
+            if (n >= corr_min) {
+                const double mi = quot((double)si, n), mj = quot((double)sj, n);
+                const double vi = dsub(quot((double)sqi, n), dmul(mi, mi));
+                const double vj = dsub(quot((double)sqj, n), dmul(mj, mj));
+                const double cov = dsub(quot((double)pr, n), dmul(mi, mj));
+                if (vi > 0 && vj > 0) res = (T)(cov / sqrt(dmul(vi, vj)));
+            }
+        } else if (n >= min_count && n > 1) {
+            const double mi = quot((double)si, n), mj = quot((double)sj, n);
+            res = (T)quot(dmul(dsub(quot((double)pr, n), dmul(mi, mj)), (double)n), n - 1);
+        }
+        __stcs(ob + t * q, res);
+    }
+}
+
+// ---- long observation axes, exponential weights: segments with carried state ----------------------
+// The eight running sums of a pair obey s <- decay_t * s + contribution_t (psw2: decay_t^2), so a
+// segment is the affine map s -> D s + U with D = prod decay_t (the same for every pair) and
+// U = the segment run from zero.  Pass A runs every (segment, pair) from zero and stores U and D;
+// `mat_exp_carry_kernel` folds them left to right into the state each segment starts from; pass B
+// runs the reference's loop body from that state and writes the outputs.  Like the segmented
+// windows above this agrees with the reference to the rounding of the running sums (which the
+// reference keeps in the input dtype), not bit for bit; short axes keep the single-segment kernel.
+constexpr int kMatExpStates = 8;  // si sj sqi sqj pr pw psw psw2
+
+template <typename T, bool CORR>
+struct MatExpState {
+    T si = 0, sj = 0, sqi = 0, sqj = 0, pr = 0, pw = 0, psw = 0, psw2 = 0;
+    __device__ __forceinline__ void step(T alpha_t, T vi, T vj) {
+        const double decay = dsub(1.0, (double)alpha_t);
+        const double decay2 = dmul(decay, decay);
+        si = (T)dmul((double)si, decay);
+        sj = (T)dmul((double)sj, decay);
+        if (CORR) {
+            sqi = (T)dmul((double)sqi, decay);
+            sqj = (T)dmul((double)sqj, decay);
+        }
+        pr = (T)dmul((double)pr, decay);
+        pw = (T)dmul((double)pw, decay);
+        psw = (T)dmul((double)psw, decay);
+        psw2 = (T)dmul((double)psw2, decay2);
+        if (!(is_nan(vi) || is_nan(vj))) {
+            si += vi;
+            sj += vj;
+            if (CORR) {
+                sqi += mul_t(vi, vi);
+                sqj += mul_t(vj, vj);
+            }
+            pr += mul_t(vi, vj);
+            pw += alpha_t;
+            psw = (T)dadd((double)psw, 1.0);
+            psw2 = (T)dadd((double)psw2, 1.0);
+        }
+    }
+    __device__ __forceinline__ T read_out(T min_weight) const {
+        double bias = 0.0;
+        if (psw > (T)0) bias = dsub(1.0, (double)(T)(psw2 / mul_t(psw, psw)));
+        T res = quiet_nan<T>();
+        if (pw >= min_weight && bias > 0) {
+            const T n = psw;
+            const T mi = si / n, mj = sj / n;
+            const T cov_b = (T)(pr / n) - mul_t(mi, mj);
+            if (CORR) {
+                const T vi_b = (T)(sqi / n) - mul_t(mi, mi);
+                const T vj_b = (T)(sqj / n) - mul_t(mj, mj);
+                const double vvi = (double)vi_b / bias, vvj = (double)vj_b / bias;
+                const double cov = (double)cov_b / bias;
+                if (vvi > 0 && vvj > 0) res = (T)(cov / sqrt(dmul(vvi, vvj)));
+            } else {
+                res = (T)((double)cov_b / bias);
+            }
+        }
+        return res;
+    }
+};
+
+// carry: [batch][nseg][kMatExpStates][q] doubles; decays: [batch][nseg][2] (D, D2)
+template <typename T, bool CORR, bool PASS_A>
+__global__ void __launch_bounds__(kMatSegThreads) mat_exp_seg_kernel(const T *__restrict__ a, const T *__restrict__ alpha,
+                                                                     int alpha_per_item, T min_weight, T *__restrict__ out,
+                                                                     i64 batch, i64 no, int nv, i64 seg_len, int nseg,
+                                                                     int blocks_per_seg, double *__restrict__ carry,
+                                                                     double *__restrict__ decays) {
+    const i64 q = (i64)nv * nv;
+    const int pb = blockIdx.x % blocks_per_seg;
+    const i64 sb = blockIdx.x / blocks_per_seg;
+    const int seg = (int)(sb % nseg);
+    const i64 bi = sb / nseg;
+    const int p = pb * kMatSegThreads + threadIdx.x;
+    if (p >= q || bi >= batch) return;
+    if (PASS_A && seg == nseg - 1) return;  // nobody starts from the last segment's end
+    const int i = p / nv, j = p % nv;
+    const T *ab = a + bi * no * nv;
+    const T *al = alpha + (alpha_per_item ? bi * no : 0);
+    T *ob = out + bi * no * q + p;
+    const i64 t0 = (i64)seg * seg_len;
+    const i64 t1 = t0 + seg_len < no ? t0 + seg_len : no;
+    double *cr = carry + ((bi * nseg + seg) * kMatExpStates) * q + p;
+    MatExpState<T, CORR> st;
+    if (!PASS_A && seg > 0) {
+        st.si = (T)cr[0 * q], st.sj = (T)cr[1 * q], st.pr = (T)cr[4 * q];
+        st.pw = (T)cr[5 * q], st.psw = (T)cr[6 * q], st.psw2 = (T)cr[7 * q];
+        if (CORR) st.sqi = (T)cr[2 * q], st.sqj = (T)cr[3 * q];
+    }
+    if (PASS_A) {
+        double D = 1.0, D2 = 1.0;
+        for (i64 t = t0; t < t1; t++) {
+            const T alpha_t = al[t];
+            st.step(alpha_t, ab[t * nv + i], ab[t * nv + j]);
+            if (p == 0) {
+                const double decay = dsub(1.0, (double)alpha_t);
+                D = dmul(D, decay);
+                D2 = dmul(D2, dmul(decay, decay));
+            }
+        }
+        cr[0 * q] = (double)st.si, cr[1 * q] = (double)st.sj, cr[4 * q] = (double)st.pr;
+        cr[5 * q] = (double)st.pw, cr[6 * q] = (double)st.psw, cr[7 * q] = (double)st.psw2;
+        if (CORR) cr[2 * q] = (double)st.sqi, cr[3 * q] = (double)st.sqj;
+        if (p == 0) decays[(bi * nseg + seg) * 2] = D, decays[(bi * nseg + seg) * 2 + 1] = D2;
+    } else {
+        for (i64 t = t0; t < t1; t++) {
+            st.step(al[t], ab[t * nv + i], ab[t * nv + j]);
+            __stcs(ob + t * q, st.read_out(min_weight));
+        }
+    }
+}
+
+// U records -> incoming states, in place: thread per (batch item, state, pair)
+__global__ void mat_exp_carry_kernel(double *__restrict__ carry, const double *__restrict__ decays, i64 batch, int nseg, i64 q) {
+    const i64 gid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= batch * kMatExpStates * q) return;
+    const i64 p = gid % q;
+    const int k = (int)((gid / q) % kMatExpStates);
+    const i64 bi = gid / (q * kMatExpStates);
+    double s = 0.0;
+    for (int seg = 0; seg < nseg; seg++) {
+        double *c = carry + ((bi * nseg + seg) * kMatExpStates + k) * q + p;
+        const double u = seg < nseg - 1 ? *c : 0.0;
+        *c = s;
+        s = dadd(dmul(decays[(bi * nseg + seg) * 2 + (k == 7 ? 1 : 0)], s), u);
+    }
+}
+
 // a: (batch, no, nv); alpha: (no) or (batch, no); out: (batch, no, nv, nv).
 // moving_matrix.py:247-331 / 372-432.
 template <typename T, bool CORR>
@@ -195,6 +427,28 @@ __global__ void __launch_bounds__(kMatThreads) mat_exp_kernel(const T *__restric
     }
 }
 
+// Segments along the observation axis: only for long axes (short ones stay bit-identical to the
+// reference), enough of them to give the machine ~2 resident threads per lane, each at least 8
+// windows long so that rebuilding the window costs <= 1/8 extra.
+constexpr i64 kMatSegMinObs = 8192;
+struct MatSegs {
+    i64 seg_len;
+    int nseg;
+};
+static MatSegs mat_segments(i64 pair_threads, i64 no, i64 window) {
+    MatSegs s = {no, 1};
+    if (getenv("NBG_MAT_NOSEG") || no < kMatSegMinObs) return s;
+    const i64 want_threads = (i64)kNumSMs * 2048 * 2;
+    i64 nseg = (want_threads + pair_threads - 1) / pair_threads;
+    i64 len = (no + nseg - 1) / nseg;
+    const i64 min_len = window * 8 > 256 ? window * 8 : 256;
+    if (len < min_len) len = min_len;
+    if (len >= no) return s;
+    s.seg_len = len;
+    s.nseg = (int)((no + len - 1) / len);
+    return s;
+}
+
 template <typename T>
 int launch_matrix(int op, const void *a_, const void *alpha_, int alpha_per_item, double min_weight, void *out_, i64 batch,
                   i64 no, i64 nv, i64 window, i64 min_count, cudaStream_t stream) {
@@ -208,19 +462,73 @@ int launch_matrix(int op, const void *a_, const void *alpha_, int alpha_per_item
         case NBG_MAT_NANCORR: mat_static_kernel<T, true><<<grid, kMatThreads, 0, stream>>>(a, out, batch, (int)nv, no); break;
         case NBG_MAT_NANCOV: mat_static_kernel<T, false><<<grid, kMatThreads, 0, stream>>>(a, out, batch, (int)nv, no); break;
         case NBG_MAT_MOVE_CORR:
-            mat_move_kernel<T, true><<<grid, kMatThreads, 0, stream>>>(a, out, batch, no, (int)nv, window, min_count);
+        case NBG_MAT_MOVE_COV: {
+            const bool corr = op == NBG_MAT_MOVE_CORR;
+            const MatSegs sg = mat_segments(threads, no, window);
+            if (sg.nseg > 1) {
+                const i64 q = nv * nv;
+                const int bps = (int)((q + kMatSegThreads - 1) / kMatSegThreads);
+                const i64 blocks = batch * sg.nseg * bps;
+                if (blocks > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_matrix: too many segments");
+                const bool table = window <= kMatRcpMax;
+                const size_t smem = table ? (size_t)(window + 1) * sizeof(double) : 0;
+#define NBG_MAT_SEG(C_, T_)                                                                                            \
+    mat_move_seg_kernel<T, C_, T_><<<(unsigned)blocks, kMatSegThreads, smem, stream>>>(a, out, batch, no, (int)nv, window, \
+                                                                                        min_count, sg.seg_len, sg.nseg, bps)
+                if (corr) {
+                    if (table) NBG_MAT_SEG(true, true); else NBG_MAT_SEG(true, false);
+                } else {
+                    if (table) NBG_MAT_SEG(false, true); else NBG_MAT_SEG(false, false);
+                }
+#undef NBG_MAT_SEG
+            } else if (corr) {
+                mat_move_kernel<T, true><<<grid, kMatThreads, 0, stream>>>(a, out, batch, no, (int)nv, window, min_count);
+            } else {
+                mat_move_kernel<T, false><<<grid, kMatThreads, 0, stream>>>(a, out, batch, no, (int)nv, window, min_count);
+            }
             break;
-        case NBG_MAT_MOVE_COV:
-            mat_move_kernel<T, false><<<grid, kMatThreads, 0, stream>>>(a, out, batch, no, (int)nv, window, min_count);
-            break;
+        }
         case NBG_MAT_EXP_CORR:
-            mat_exp_kernel<T, true><<<grid, kMatThreads, 0, stream>>>(a, (const T *)alpha_, alpha_per_item, (T)min_weight, out,
-                                                                    batch, no, (int)nv);
+        case NBG_MAT_EXP_COV: {
+            const bool corr = op == NBG_MAT_EXP_CORR;
+            const T *al = (const T *)alpha_;
+            const MatSegs sg = mat_segments(threads, no, 32);
+            if (sg.nseg > 1) {
+                const i64 q = nv * nv;
+                const int bps = (int)((q + kMatSegThreads - 1) / kMatSegThreads);
+                const i64 blocks = batch * sg.nseg * bps;
+                if (blocks > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_matrix: too many segments");
+                const size_t carry_bytes = (size_t)batch * sg.nseg * kMatExpStates * q * sizeof(double);
+                const size_t decay_bytes = (size_t)batch * sg.nseg * 2 * sizeof(double);
+                void *ws = nullptr;
+                int rc = check_cuda(cudaMallocAsync(&ws, carry_bytes + decay_bytes, stream), "nbg_matrix: workspace");
+                if (rc) return rc;
+                double *carry = (double *)ws, *decays = (double *)((char *)ws + carry_bytes);
+#define NBG_MAT_EXP(C_, A_)                                                                                               \
+    mat_exp_seg_kernel<T, C_, A_><<<(unsigned)blocks, kMatSegThreads, 0, stream>>>(a, al, alpha_per_item, (T)min_weight, out, \
+                                                                                    batch, no, (int)nv, sg.seg_len, sg.nseg,  \
+                                                                                    bps, carry, decays)
+                if (corr) NBG_MAT_EXP(true, true); else NBG_MAT_EXP(false, true);
+                rc = check_launch("nbg_matrix(exp, pass A)");
+                const i64 ct = batch * kMatExpStates * q;
+                if (!rc) mat_exp_carry_kernel<<<(unsigned)((ct + 255) / 256), 256, 0, stream>>>(carry, decays, batch, sg.nseg, q);
+                if (!rc) rc = check_launch("nbg_matrix(exp, carry)");
+                if (rc) {
+                    cudaFreeAsync(ws, stream);
+                    return rc;
+                }
+                if (corr) NBG_MAT_EXP(true, false); else NBG_MAT_EXP(false, false);
+#undef NBG_MAT_EXP
+                rc = check_launch("nbg_matrix");
+                cudaFreeAsync(ws, stream);
+                return rc;
+            }
+            if (corr)
+                mat_exp_kernel<T, true><<<grid, kMatThreads, 0, stream>>>(a, al, alpha_per_item, (T)min_weight, out, batch, no, (int)nv);
+            else
+                mat_exp_kernel<T, false><<<grid, kMatThreads, 0, stream>>>(a, al, alpha_per_item, (T)min_weight, out, batch, no, (int)nv);
             break;
-        case NBG_MAT_EXP_COV:
-            mat_exp_kernel<T, false><<<grid, kMatThreads, 0, stream>>>(a, (const T *)alpha_, alpha_per_item, (T)min_weight, out,
-                                                                     batch, no, (int)nv);
-            break;
+        }
         default: return fail(NBG_ERR_BAD_OP, "nbg_matrix: unknown op");
     }
     return check_launch("nbg_matrix");

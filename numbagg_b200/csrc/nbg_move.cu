@@ -532,7 +532,7 @@ static int launch_rowtile(MoveParams p, int64_t outer, int64_t n, cudaStream_t s
     if (tpr * outer > INT32_MAX) return fail(NBG_ERR_UNSUPPORTED, "nbg_move: more than 2^31 tiles");
     p.tiles_per_row = (int)tpr;
     p.ntiles = tpr * outer;
-    p.prefetch_dist = prefetch_distance(2);
+    p.prefetch_dist = prefetch_distance(2, (size_t)Op::NIN * SM::TILE * sizeof(T));
     auto kern = move_rowtile_kernel<T, Op, THREADS, E, RCP>;
     int rc = allow_big_smem(kern, "nbg_move: cudaFuncSetAttribute");
     if (rc) return rc;

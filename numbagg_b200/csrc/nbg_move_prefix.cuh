@@ -65,7 +65,7 @@ struct PfxSmem {
 };
 
 template <typename T, class Op, int THREADS, int E>
-__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1) move_prefix_kernel(MovePfxParams p) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 || THREADS == 448) ? 2 : 1) move_prefix_kernel(MovePfxParams p) {
     static_assert(sizeof(T) == 4, "prefix windows are built for float32 inputs");
     constexpr int NIN = Op::NIN, NCH = Op::NCH, NCHP = NCH + 1;
     using SM = PfxSmem<NIN, NCH, THREADS, E>;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1) move_prefix_k
 }
 
 // Geometry per op: THREADS x E outputs per tile (E odd: conflict-free strided shared-memory access).
-template <class Op>
+template <class Op, int G = 0>
 struct PfxCfg {
     // the ring costs 12 / 20 / 28 / 44 bytes per position (mean / var / cov / corr): wider records get
     // smaller tiles so that window 1000 still fits one CTA per SM
@@ -353,6 +353,13 @@ struct PfxCfg {
     // two barriers per tile)
     static constexpr int THREADS = Op::NCH <= 2 ? 256 : 384;
     static constexpr int E = Op::NCH <= 2 ? 9 : (Op::NCH == 3 ? 7 : 5);
+};
+// G = 1 (experiment): 448 threads x 5 outputs, two CTAs = 28 warps per SM at window 1000 for the
+// one- and two-channel ops (the 256 x 9 form is latency-bound at 16 warps: issue slots 48 % busy)
+template <class Op>
+struct PfxCfg<Op, 1> {
+    static constexpr int THREADS = 448;
+    static constexpr int E = 5;
 };
 
 template <typename T, class Op>
@@ -364,9 +371,17 @@ static bool prefix_fits(int64_t window) {
     return SM::total((int)window, wup) <= kMaxSmemOptIn;
 }
 
-template <typename T, class Op>
+template <typename T, class Op, int G = 0>
 static int launch_prefix(MovePfxParams p, int64_t outer, int64_t n, cudaStream_t stream) {
-    using C = PfxCfg<Op>;
+    using C = PfxCfg<Op, G>;
+    if constexpr (G == 0 && Op::NCH <= 2) {
+        if (const char *e = getenv("NBG_PFX_GEOM")) {
+            using C1 = PfxCfg<Op, 1>;
+            using SM1 = PfxSmem<Op::NIN, Op::NCH, C1::THREADS, C1::E>;
+            const int wup1 = (p.window + C1::E - 1) / C1::E * C1::E;
+            if (atoi(e) == 1 && SM1::total(p.window, wup1) <= kMaxSmemOptIn) return launch_prefix<T, Op, 1>(p, outer, n, stream);
+        }
+    }
     using SM = PfxSmem<Op::NIN, Op::NCH, C::THREADS, C::E>;
     p.wup = (p.window + C::E - 1) / C::E * C::E;
     const int64_t tpr = (n + SM::TILE - 1) / SM::TILE;

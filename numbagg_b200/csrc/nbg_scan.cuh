@@ -382,7 +382,7 @@ static int launch_scan_rowtile(ScanParams p, int64_t rows, int64_t n, void *work
     p.tiles_per_row = (int)tpr;
     p.rows = rows;
     p.n = n;
-    p.prefetch_dist = prefetch_distance(P::MIN_CTAS);
+    p.prefetch_dist = prefetch_distance(P::MIN_CTAS, (size_t)P::NSTREAM * THREADS * E * sizeof(typename P::T));
     int rc = check_cuda(cudaMemsetAsync(p.ws_base, 0, (size_t)ntiles * sizeof(TileDesc<Agg>), stream), what);
     if (rc) return rc;
     auto kern = scan_rowtile_kernel<P, THREADS, E>;

@@ -113,6 +113,17 @@ def main():
             run("cfg3_" + f, lambda: D.run_move_exp(f, [a], 0.1, 0.0, -1)[0], ab, [{}], steps)
         del a
         torch.cuda.empty_cache()
+    if "pfsweep" in args:
+        n = 1_000_000_000
+        a = gen((1, n), torch.float64, 0.3)
+        sw = [dict(NBG_PREFETCH_TILES=v) for v in (0, 150, 300, 600, 888, 1200)]
+        run("cfg3_ffill", lambda: D.run_fill("ffill", a, n, -1)[0], n * 16, sw, steps)
+        run("cfg3_move_exp_nanmean", lambda: D.run_move_exp("move_exp_nanmean", [a], 0.1, 0.0, -1)[0], n * 16, sw, steps)
+        del a
+        torch.cuda.empty_cache()
+        b = gen((2000, 100_000), torch.float64, 0.1)
+        run("cfg1s_move_mean", lambda: D.run_move("move_mean", [b], 20, 1, -1), 2000 * 100_000 * 16, [dict(NBG_PREFETCH_TILES=v) for v in (0, 100, 200, 296, 600)], steps)
+        del b
     if "cfg4" in args:
         rows, n = 1000, 1_000_000
         a = gen((rows, n), torch.float32, 0.1)
@@ -122,6 +133,28 @@ def main():
             run("cfg4_" + f, lambda: D.run_move(f, ts, 1000, 500, -1), rows * n * 4 * (nin + 1), pf[:2], steps)
         del a, b
         torch.cuda.empty_cache()
+    if "cfg4g" in args:
+        rows, n = 1000, 1_000_000
+        a = gen((rows, n), torch.float32, 0.1)
+        for f in ("move_std", "move_var", "move_mean"):
+            run("cfg4_" + f, lambda: D.run_move(f, [a], 1000, 500, -1), rows * n * 8,
+                [dict(NBG_PFX="all", NBG_PFX_GEOM=0), dict(NBG_PFX="all", NBG_PFX_GEOM=1), dict(NBG_PFX="off", NBG_PFX_GEOM=0)], steps)
+        del a
+        torch.cuda.empty_cache()
+    if "mat" in args:
+        no, nv = 200_000, 32
+        for dt in (torch.float64, torch.float32):
+            a = gen((no, nv), dt, 0.1)
+            ob = no * nv * nv * a.element_size()
+            tag = "f64" if dt == torch.float64 else "f32"
+            al = torch.full((no,), 0.05, dtype=dt, device=dev)
+            sw = [dict(NBG_MAT_NOSEG=1), dict()] if dt == torch.float64 else [dict()]
+            run(f"mat_move_cov_{tag}", lambda: D.run_matrix("move_covmatrix", a, window=100, min_count=10), ob, sw, 3)
+            run(f"mat_move_corr_{tag}", lambda: D.run_matrix("move_corrmatrix", a, window=100, min_count=10), ob, [dict()], 3)
+            run(f"mat_exp_cov_{tag}", lambda: D.run_matrix("move_exp_nancovmatrix", a, alpha=al), ob, sw, 3)
+            run(f"mat_exp_corr_{tag}", lambda: D.run_matrix("move_exp_nancorrmatrix", a, alpha=al), ob, [dict()], 3)
+            del a
+            torch.cuda.empty_cache()
     if "cfg1s" in args:
         rows, n = 2000, 100_000
         a = gen((rows, n), torch.float64, 0.1)

@@ -56,6 +56,41 @@ def test_larger_shapes_against_oracle(dtype):
         same(nb.move_exp_nancovmatrix(ov, alpha=alpha), oracle.move_exp_nancovmatrix(ov, alpha=alpha))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_long_observation_axis_segments(dtype):
+    """Observation axes >= 8192 are cut into segments that rebuild their window state from the
+    `window` observations before them (nbg_matrix.cu: mat_move_seg_kernel).  The reference never
+    re-syncs its running sums (moving_matrix.py:78-101), so the comparison is to the rounding of those
+    sums, kept in the INPUT dtype: ~sqrt(steps) ulps of a window sum (values ~3, window 64: float64
+    sums ~600 -> 1e-11 absolute on a covariance; float32 -> 1e-3), NaN masks exact."""
+    import numbagg_b200 as nb
+    from tests._parity import _record
+
+    ov = _data((2, 20_000, 8), dtype, seed=5)
+    atol = 1e-10 if dtype is np.float64 else 3e-3
+    for func, kw in (("move_covmatrix", dict(window=64, min_count=8)), ("move_corrmatrix", dict(window=64, min_count=8)),
+                     ("move_covmatrix", dict(window=5000, min_count=None))):
+        got = getattr(nb, func)(ov, **kw)
+        exp = getattr(oracle, func)(ov, **kw)
+        assert got.dtype == exp.dtype and got.shape == exp.shape
+        assert np.array_equal(np.isnan(got), np.isnan(exp)), f"{func}: NaN masks differ"
+        _record(func + "(segments)", got, exp, 0.0, atol)
+        np.testing.assert_allclose(got, exp, rtol=0, atol=atol, equal_nan=True)
+    # exponential weights: segments carry their state as an affine map (two passes)
+    al = (np.random.RandomState(6).rand(20_000) * 0.2 + 0.005).astype(dtype)
+    for alpha in (dtype(0.02), al):
+        for func, kw in (("move_exp_nancovmatrix", dict(alpha=alpha)), ("move_exp_nancorrmatrix", dict(alpha=alpha, min_weight=0.2))):
+            got = getattr(nb, func)(ov, **kw)
+            exp = getattr(oracle, func)(ov, **kw)
+            assert got.dtype == exp.dtype and got.shape == exp.shape
+            assert np.array_equal(np.isnan(got), np.isnan(exp)), f"{func}: NaN masks differ"
+            _record(func + "(segments)", got, exp, 0.0, atol)
+            np.testing.assert_allclose(got, exp, rtol=0, atol=atol, equal_nan=True)
+    # the first segment runs the reference's recurrence from the start: bit-identical there
+    got = nb.move_covmatrix(ov, window=64, min_count=8)
+    same(got[:, :256], oracle.move_covmatrix(ov, window=64, min_count=8)[:, :256])
+
+
 def test_tensor_in_tensor_out_and_validation():
     import torch
 
