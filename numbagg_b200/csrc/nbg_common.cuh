@@ -84,6 +84,36 @@ __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a,
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 
+// ---- double division through the hardware reciprocal seed -----------------------------------
+// An IEEE double division is ~20 instructions on the FP64 pipe, and the read-outs below divide up
+// to four times per output -- more than the whole recurrence.  Here 1/b comes from the
+// MUFU.RCP64H seed (2^-20) and two Newton steps, and every quotient gets the residual correction
+// q' = q + (a - b*q) * y, which yields the correctly rounded a/b (Markstein): the read-outs contain
+// SIGN GATES on exact cancellations (bias > 0 after one observation, var1*var2 > 0 for repeated
+// values), so quotients must round exactly as the reference's divisions do.  3 instructions per
+// quotient + 5 per distinct divisor.  Divisors outside [1e-280, 1e280] (zero, the subnormal tail of
+// a long NaN run, inf, NaN) take the IEEE path so that x/0, 0/0 and inf behave as in the reference.
+__device__ __forceinline__ double fast_rcp(double b) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    y = fma(y, fma(-b, y, 1.0), y);
+    y = fma(y, fma(-b, y, 1.0), y);
+    return y;
+}
+__device__ __forceinline__ bool rcp_ok(double b) {
+    const double ab = fabs(b);
+    return ab > 1e-280 && ab < 1e280;
+}
+// a / b given y = fast_rcp(b)
+__device__ __forceinline__ double qdiv(double a, double b, double y) {
+    const double q = a * y;
+    const double qc = fma(fma(-b, q, a), y, q);
+    // an infinite / NaN numerator (or an overflowing quotient) turns the residual into NaN: IEEE path
+    return fabs(qc) < __longlong_as_double(0x7ff0000000000000LL) ? qc : a / b;
+}
+__device__ __forceinline__ double fdiv(double a, double b) { return rcp_ok(b) ? qdiv(a, b, fast_rcp(b)) : a / b; }
+
+
 // Product of two inputs in the INPUT type, then widened: numba types float32*float32 as
 // float32 (verified bit-for-bit against the reference in tests/test_gpu_golden.py).
 __device__ __forceinline__ double prod_as_input(float a, float b) { return (double)__fmul_rn(a, b); }

@@ -139,16 +139,24 @@ __global__ void __launch_bounds__(kMatThreads) mat_move_kernel(const T *__restri
 // above.  Quotients by the integer count come from a per-CTA table of correctly rounded reciprocals
 // plus the residual correction q' = q + (a - c q) y (Markstein: correctly rounded a / c), i.e. they
 // round exactly like the reference's divisions at a quarter of the FP64 instructions.
-__device__ __forceinline__ double tab_div(double a, double c, double y) {
-    const double q = a * y;
-    const double qc = fma(fma(-c, q, a), y, q);
-    // tiny / non-finite quotients: the residual is not exact there, take the IEEE division
-    return (fabs(q) > 1e-290 && fabs(qc) < __longlong_as_double(0x7ff0000000000000LL)) ? qc : a / c;
-}
-
 constexpr int kMatSegThreads = 256;
 constexpr int kMatRcpMax = 4096;  // windows up to this long use the reciprocal table
 
+// The matrices are symmetric and so is every loop body above (the reference computes all nv^2 pairs
+// separately; swapping i and j only swaps commutative operands), so the segmented kernels compute
+// the nv (nv + 1) / 2 pairs with j >= i and store each result twice.  k -> (i, j), row-major over
+// the upper triangle: consecutive threads are consecutive j of one row (coalesced primary store).
+__device__ __forceinline__ void tri_pair(int k, int nv, int &i, int &j) {
+    int row = 0, rem = k;
+    while (rem >= nv - row) {
+        rem -= nv - row;
+        row++;
+    }
+    i = row;
+    j = row + rem;
+}
+
+// (tried: prefetch.global.L1 of the rows 8 steps ahead -- slower, 1.10 vs 0.81 ms on 200 000 x 32 float64)
 template <typename T, bool CORR, bool TABLE>
 __global__ void __launch_bounds__(kMatSegThreads) mat_move_seg_kernel(const T *__restrict__ a, T *__restrict__ out, i64 batch,
                                                                       i64 no, int nv, i64 window, i64 min_count, i64 seg_len,
@@ -159,17 +167,21 @@ __global__ void __launch_bounds__(kMatSegThreads) mat_move_seg_kernel(const T *_
         __syncthreads();
     }
     const i64 q = (i64)nv * nv;
+    const int npairs = nv * (nv + 1) / 2;
     const int pb = blockIdx.x % blocks_per_seg;
     const i64 sb = blockIdx.x / blocks_per_seg;
     const int seg = (int)(sb % nseg);
     const i64 bi = sb / nseg;
-    const int p = pb * kMatSegThreads + threadIdx.x;
-    if (p >= q || bi >= batch) return;
-    const int i = p / nv, j = p % nv;
+    const int k = pb * kMatSegThreads + threadIdx.x;
+    if (k >= npairs || bi >= batch) return;
+    int i, j;
+    tri_pair(k, nv, i, j);
     const T *ab = a + bi * no * nv;
-    T *ob = out + bi * no * q + p;
+    T *ob = out + bi * no * q;
+    const int oij = i * nv + j, oji = j * nv + i;
     if (min_count < 1) min_count = 1;
-    const i64 corr_min = min_count > 2 ? min_count : 2;
+    const int corr_min = (int)(min_count > 2 ? min_count : 2);
+    const int cov_min = (int)(min_count > 2 ? min_count : 2);  // n >= min_count && n > 1
     const i64 t0 = (i64)seg * seg_len;
     const i64 t1 = t0 + seg_len < no ? t0 + seg_len : no;
     T si = 0, sj = 0, sqi = 0, sqj = 0, pr = 0;
@@ -187,13 +199,23 @@ __global__ void __launch_bounds__(kMatSegThreads) mat_move_seg_kernel(const T *_
             n += 1;
         }
     }
-    auto quot = [&](double x, int c) -> double {
-        if (TABLE) return tab_div(x, (double)c, rc_tab[c]);
-        return x / (double)c;
-    };
-    for (i64 t = t0; t < t1; t++) {
-        if (t >= window) {
-            const T vi = ab[(t - window) * nv + i], vj = ab[(t - window) * nv + j];
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    const T *lead = ab + t0 * nv, *trail = ab + (t0 - window) * nv;  // trail is only dereferenced once t >= window
+    T *o = ob + t0 * q;
+    // the observations of step t + 1 are fetched while step t computes (the loads feed a NaN test at the
+    // top of a long dependent chain: without this the kernel sits in long_scoreboard half of the time)
+    const T kNaN = quiet_nan<T>();
+    T n_li = t0 < t1 ? lead[i] : kNaN, n_lj = t0 < t1 ? lead[j] : kNaN;
+    T n_ti = t0 >= window && t0 < t1 ? trail[i] : kNaN, n_tj = t0 >= window && t0 < t1 ? trail[j] : kNaN;
+    for (i64 t = t0; t < t1; t++, lead += nv, trail += nv, o += q) {
+        const T li = n_li, lj = n_lj, ti = n_ti, tj = n_tj;
+        if (t + 1 < t1) {
+            n_li = lead[nv + i], n_lj = lead[nv + j];
+            if (t + 1 >= window) n_ti = trail[nv + i], n_tj = trail[nv + j];
+        }
+        {
+            // a step before the window is full has nothing leaving: ti / tj are NaN there
+            const T vi = ti, vj = tj;
             if (!(is_nan(vi) || is_nan(vj))) {
                 si -= vi;
                 sj -= vj;
@@ -206,7 +228,7 @@ __global__ void __launch_bounds__(kMatSegThreads) mat_move_seg_kernel(const T *_
             }
         }
         {
-            const T vi = ab[t * nv + i], vj = ab[t * nv + j];
+            const T vi = li, vj = lj;
             if (!(is_nan(vi) || is_nan(vj))) {
                 si += vi;
                 sj += vj;
@@ -219,19 +241,61 @@ __global__ void __launch_bounds__(kMatSegThreads) mat_move_seg_kernel(const T *_
             }
         }
         T res = quiet_nan<T>();
-        if (CORR) {
-            if (n >= corr_min) {
-                const double mi = quot((double)si, n), mj = quot((double)sj, n);
-                const double vi = dsub(quot((double)sqi, n), dmul(mi, mi));
-                const double vj = dsub(quot((double)sqj, n), dmul(mj, mj));
-                const double cov = dsub(quot((double)pr, n), dmul(mi, mj));
-                if (vi > 0 && vj > 0) res = (T)(cov / sqrt(dmul(vi, vj)));
+        if (TABLE) {
+            // quotients by the count: q' = q + (a - c q) y with y = the correctly rounded 1 / c rounds like
+            // the division itself (Markstein) unless a quotient is tiny or not finite -- ONE test for all
+            // of them, then the IEEE path
+            if (n >= (CORR ? corr_min : cov_min)) {
+                const double c = (double)n, y = rc_tab[n];
+                auto qd = [&](double x) {
+                    const double q0 = x * y;
+                    return fma(fma(-c, q0, x), y, q0);
+                };
+                const double mi = qd((double)si), mj = qd((double)sj), mp = qd((double)pr);
+                double small = fmin(fmin(fabs(mi), fabs(mj)), fabs(mp)), big = fabs(mi) + fabs(mj) + fabs(mp);
+                if (CORR) {
+                    const double qi = qd((double)sqi), qj = qd((double)sqj);
+                    small = fmin(small, fmin(fabs(qi), fabs(qj)));
+                    big += fabs(qi) + fabs(qj);
+                    if (small > 1e-290 && big < kInf) {
+                        const double vi = dsub(qi, dmul(mi, mi)), vj = dsub(qj, dmul(mj, mj));
+                        const double cov = dsub(mp, dmul(mi, mj));
+                        if (vi > 0 && vj > 0) res = (T)(cov / sqrt(dmul(vi, vj)));
+                    } else {
+                        const double mi2 = (double)si / c, mj2 = (double)sj / c;
+                        const double vi = dsub((double)sqi / c, dmul(mi2, mi2));
+                        const double vj = dsub((double)sqj / c, dmul(mj2, mj2));
+                        const double cov = dsub((double)pr / c, dmul(mi2, mj2));
+                        if (vi > 0 && vj > 0) res = (T)(cov / sqrt(dmul(vi, vj)));
+                    }
+                } else {
+                    const double c1 = (double)(n - 1), y1 = rc_tab[n - 1];
+                    const double num = dmul(dsub(mp, dmul(mi, mj)), c);
+                    const double q0 = num * y1;
+                    const double r = fma(fma(-c1, q0, num), y1, q0);
+                    if (small > 1e-290 && big < kInf && fabs(q0) > 1e-290)
+                        res = (T)r;
+                    else
+                        res = (T)(dmul(dsub((double)pr / c, dmul((double)si / c, (double)sj / c)), c) / c1);
+                }
             }
-        } else if (n >= min_count && n > 1) {
-            const double mi = quot((double)si, n), mj = quot((double)sj, n);
-            res = (T)quot(dmul(dsub(quot((double)pr, n), dmul(mi, mj)), (double)n), n - 1);
+        } else {
+            const double c = (double)n;
+            if (CORR) {
+                if (n >= corr_min) {
+                    const double mi = (double)si / c, mj = (double)sj / c;
+                    const double vi = dsub((double)sqi / c, dmul(mi, mi));
+                    const double vj = dsub((double)sqj / c, dmul(mj, mj));
+                    const double cov = dsub((double)pr / c, dmul(mi, mj));
+                    if (vi > 0 && vj > 0) res = (T)(cov / sqrt(dmul(vi, vj)));
+                }
+            } else if (n >= cov_min) {
+                const double mi = (double)si / c, mj = (double)sj / c;
+                res = (T)(dmul(dsub((double)pr / c, dmul(mi, mj)), c) / (double)(n - 1));
+            }
         }
-        __stcs(ob + t * q, res);
+        __stcs(o + oij, res);
+        if (i != j) __stcs(o + oji, res);
     }
 }
 
@@ -275,6 +339,42 @@ struct MatExpState {
         }
     }
     __device__ __forceinline__ T read_out(T min_weight) const {
+        if constexpr (sizeof(T) == 8) {
+            // double: every quotient of the reference's read-out through one reciprocal per distinct
+            // divisor + the residual correction (correctly rounded, nbg_common.cuh) -- 3 instructions per
+            // quotient instead of an IEEE division each
+            const double n = psw, n2 = dmul(psw, psw);
+            if (rcp_ok(n) && rcp_ok(n2)) {
+                T res = quiet_nan<T>();
+                if (!(psw > 0)) return res;  // bias stays 0
+                const double bias = dsub(1.0, qdiv(psw2, n2, fast_rcp(n2)));
+                if (pw >= min_weight && bias > 0) {
+                    const double y = fast_rcp(n);
+                    const double mi = qdiv(si, n, y), mj = qdiv(sj, n, y);
+                    const double cov_b = dsub(qdiv(pr, n, y), dmul(mi, mj));
+                    if (rcp_ok(bias)) {
+                        const double yb = fast_rcp(bias);
+                        if (CORR) {
+                            const double vi_b = dsub(qdiv(sqi, n, y), dmul(mi, mi));
+                            const double vj_b = dsub(qdiv(sqj, n, y), dmul(mj, mj));
+                            const double vvi = qdiv(vi_b, bias, yb), vvj = qdiv(vj_b, bias, yb);
+                            const double cov = qdiv(cov_b, bias, yb);
+                            if (vvi > 0 && vvj > 0) res = (T)fdiv(cov, sqrt(dmul(vvi, vvj)));
+                        } else {
+                            res = (T)qdiv(cov_b, bias, yb);
+                        }
+                    } else if (CORR) {
+                        const double vi_b = dsub(qdiv(sqi, n, y), dmul(mi, mi));
+                        const double vj_b = dsub(qdiv(sqj, n, y), dmul(mj, mj));
+                        const double vvi = vi_b / bias, vvj = vj_b / bias, cov = cov_b / bias;
+                        if (vvi > 0 && vvj > 0) res = (T)(cov / sqrt(dmul(vvi, vvj)));
+                    } else {
+                        res = (T)(cov_b / bias);
+                    }
+                }
+                return res;
+            }
+        }
         double bias = 0.0;
         if (psw > (T)0) bias = dsub(1.0, (double)(T)(psw2 / mul_t(psw, psw)));
         T res = quiet_nan<T>();
@@ -296,7 +396,7 @@ struct MatExpState {
     }
 };
 
-// carry: [batch][nseg][kMatExpStates][q] doubles; decays: [batch][nseg][2] (D, D2)
+// carry: [batch][nseg][kMatExpStates][npairs] doubles; decays: [batch][nseg][2] (D, D2)
 template <typename T, bool CORR, bool PASS_A>
 __global__ void __launch_bounds__(kMatSegThreads) mat_exp_seg_kernel(const T *__restrict__ a, const T *__restrict__ alpha,
                                                                      int alpha_per_item, T min_weight, T *__restrict__ out,
@@ -304,45 +404,55 @@ __global__ void __launch_bounds__(kMatSegThreads) mat_exp_seg_kernel(const T *__
                                                                      int blocks_per_seg, double *__restrict__ carry,
                                                                      double *__restrict__ decays) {
     const i64 q = (i64)nv * nv;
+    const i64 np = (i64)nv * (nv + 1) / 2;
     const int pb = blockIdx.x % blocks_per_seg;
     const i64 sb = blockIdx.x / blocks_per_seg;
     const int seg = (int)(sb % nseg);
     const i64 bi = sb / nseg;
-    const int p = pb * kMatSegThreads + threadIdx.x;
-    if (p >= q || bi >= batch) return;
+    const int k = pb * kMatSegThreads + threadIdx.x;
+    if (k >= np || bi >= batch) return;
     if (PASS_A && seg == nseg - 1) return;  // nobody starts from the last segment's end
-    const int i = p / nv, j = p % nv;
-    const T *ab = a + bi * no * nv;
+    int i, j;
+    tri_pair(k, nv, i, j);
     const T *al = alpha + (alpha_per_item ? bi * no : 0);
-    T *ob = out + bi * no * q + p;
     const i64 t0 = (i64)seg * seg_len;
     const i64 t1 = t0 + seg_len < no ? t0 + seg_len : no;
-    double *cr = carry + ((bi * nseg + seg) * kMatExpStates) * q + p;
+    const T *lead = a + (bi * no + t0) * nv;
+    double *cr = carry + ((bi * nseg + seg) * kMatExpStates) * np + k;
     MatExpState<T, CORR> st;
     if (!PASS_A && seg > 0) {
-        st.si = (T)cr[0 * q], st.sj = (T)cr[1 * q], st.pr = (T)cr[4 * q];
-        st.pw = (T)cr[5 * q], st.psw = (T)cr[6 * q], st.psw2 = (T)cr[7 * q];
-        if (CORR) st.sqi = (T)cr[2 * q], st.sqj = (T)cr[3 * q];
+        st.si = (T)cr[0 * np], st.sj = (T)cr[1 * np], st.pr = (T)cr[4 * np];
+        st.pw = (T)cr[5 * np], st.psw = (T)cr[6 * np], st.psw2 = (T)cr[7 * np];
+        if (CORR) st.sqi = (T)cr[2 * np], st.sqj = (T)cr[3 * np];
     }
     if (PASS_A) {
         double D = 1.0, D2 = 1.0;
-        for (i64 t = t0; t < t1; t++) {
-            const T alpha_t = al[t];
-            st.step(alpha_t, ab[t * nv + i], ab[t * nv + j]);
-            if (p == 0) {
+        T n_i = t0 < t1 ? lead[i] : (T)0, n_j = t0 < t1 ? lead[j] : (T)0, n_al = t0 < t1 ? al[t0] : (T)0;
+        for (i64 t = t0; t < t1; t++, lead += nv) {
+            const T alpha_t = n_al, vi = n_i, vj = n_j;
+            if (t + 1 < t1) n_i = lead[nv + i], n_j = lead[nv + j], n_al = al[t + 1];
+            st.step(alpha_t, vi, vj);
+            if (k == 0) {
                 const double decay = dsub(1.0, (double)alpha_t);
                 D = dmul(D, decay);
                 D2 = dmul(D2, dmul(decay, decay));
             }
         }
-        cr[0 * q] = (double)st.si, cr[1 * q] = (double)st.sj, cr[4 * q] = (double)st.pr;
-        cr[5 * q] = (double)st.pw, cr[6 * q] = (double)st.psw, cr[7 * q] = (double)st.psw2;
-        if (CORR) cr[2 * q] = (double)st.sqi, cr[3 * q] = (double)st.sqj;
-        if (p == 0) decays[(bi * nseg + seg) * 2] = D, decays[(bi * nseg + seg) * 2 + 1] = D2;
+        cr[0 * np] = (double)st.si, cr[1 * np] = (double)st.sj, cr[4 * np] = (double)st.pr;
+        cr[5 * np] = (double)st.pw, cr[6 * np] = (double)st.psw, cr[7 * np] = (double)st.psw2;
+        if (CORR) cr[2 * np] = (double)st.sqi, cr[3 * np] = (double)st.sqj;
+        if (k == 0) decays[(bi * nseg + seg) * 2] = D, decays[(bi * nseg + seg) * 2 + 1] = D2;
     } else {
-        for (i64 t = t0; t < t1; t++) {
-            st.step(al[t], ab[t * nv + i], ab[t * nv + j]);
-            __stcs(ob + t * q, st.read_out(min_weight));
+        T *o = out + (bi * no + t0) * q;
+        const int oij = i * nv + j, oji = j * nv + i;
+        T n_i = t0 < t1 ? lead[i] : (T)0, n_j = t0 < t1 ? lead[j] : (T)0, n_al = t0 < t1 ? al[t0] : (T)0;
+        for (i64 t = t0; t < t1; t++, lead += nv, o += q) {
+            const T alpha_t = n_al, vi = n_i, vj = n_j;
+            if (t + 1 < t1) n_i = lead[nv + i], n_j = lead[nv + j], n_al = al[t + 1];
+            st.step(alpha_t, vi, vj);
+            const T res = st.read_out(min_weight);
+            __stcs(o + oij, res);
+            if (i != j) __stcs(o + oji, res);
         }
     }
 }
@@ -355,11 +465,24 @@ __global__ void mat_exp_carry_kernel(double *__restrict__ carry, const double *_
     const int k = (int)((gid / q) % kMatExpStates);
     const i64 bi = gid / (q * kMatExpStates);
     double s = 0.0;
-    for (int seg = 0; seg < nseg; seg++) {
-        double *c = carry + ((bi * nseg + seg) * kMatExpStates + k) * q + p;
-        const double u = seg < nseg - 1 ? *c : 0.0;
-        *c = s;
-        s = dadd(dmul(decays[(bi * nseg + seg) * 2 + (k == 7 ? 1 : 0)], s), u);
+    const i64 stride = (i64)kMatExpStates * q;
+    double *c0 = carry + ((bi * nseg) * kMatExpStates + k) * q + p;
+    const double *dc = decays + bi * nseg * 2 + (k == 7 ? 1 : 0);
+    constexpr int B = 8;  // records in flight: the loads of a batch are independent of the running state
+    for (int seg0 = 0; seg0 < nseg; seg0 += B) {
+        double u[B], d[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const int seg = seg0 + b;
+            u[b] = seg < nseg - 1 ? c0[seg * stride] : 0.0;
+            d[b] = seg < nseg - 1 ? dc[seg * 2] : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const int seg = seg0 + b;
+            if (seg < nseg) c0[seg * stride] = s;
+            s = dadd(dmul(d[b], s), u[b]);
+        }
     }
 }
 
@@ -428,18 +551,19 @@ __global__ void __launch_bounds__(kMatThreads) mat_exp_kernel(const T *__restric
 }
 
 // Segments along the observation axis: only for long axes (short ones stay bit-identical to the
-// reference), enough of them to give the machine ~2 resident threads per lane, each at least 8
-// windows long so that rebuilding the window costs <= 1/8 extra.
+// reference).  All CTAs do the same amount of work, so the best grid is exactly ONE wave of resident
+// CTAs (`resident` = SMs x occupancy of the kernel; 1.27 waves cost two): as many segments as fit,
+// each at least 8 windows long so that rebuilding the window costs <= 1/8 extra.
 constexpr i64 kMatSegMinObs = 8192;
 struct MatSegs {
     i64 seg_len;
     int nseg;
 };
-static MatSegs mat_segments(i64 pair_threads, i64 no, i64 window) {
+static MatSegs mat_segments(i64 ctas_per_seg, i64 resident, i64 no, i64 window) {
     MatSegs s = {no, 1};
-    if (getenv("NBG_MAT_NOSEG") || no < kMatSegMinObs) return s;
-    const i64 want_threads = (i64)kNumSMs * 2048 * 2;
-    i64 nseg = (want_threads + pair_threads - 1) / pair_threads;
+    if (getenv("NBG_MAT_NOSEG") || no < kMatSegMinObs || ctas_per_seg <= 0) return s;
+    i64 nseg = resident / ctas_per_seg;
+    if (nseg < 2) return s;
     i64 len = (no + nseg - 1) / nseg;
     const i64 min_len = window * 8 > 256 ? window * 8 : 256;
     if (len < min_len) len = min_len;
@@ -447,6 +571,27 @@ static MatSegs mat_segments(i64 pair_threads, i64 no, i64 window) {
     s.seg_len = len;
     s.nseg = (int)((no + len - 1) / len);
     return s;
+}
+template <class K>
+static i64 resident_ctas(K kern, int threads, size_t smem) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+    return (i64)occ * kNumSMs;
+}
+
+// The carry workspace of the exponential forms comes from the device's stream-ordered pool.  By
+// default the pool hands freed memory back to the driver at the next synchronisation, which turns
+// every call after a sync into a real allocation (~1-2 ms measured); keep it cached instead.
+static void keep_pool_memory() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = (uint64_t)1 << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
 }
 
 template <typename T>
@@ -464,14 +609,18 @@ int launch_matrix(int op, const void *a_, const void *alpha_, int alpha_per_item
         case NBG_MAT_MOVE_CORR:
         case NBG_MAT_MOVE_COV: {
             const bool corr = op == NBG_MAT_MOVE_CORR;
-            const MatSegs sg = mat_segments(threads, no, window);
+            const i64 np = nv * (nv + 1) / 2;
+            const int bps = (int)((np + kMatSegThreads - 1) / kMatSegThreads);
+            const bool table = window <= kMatRcpMax;
+            const size_t smem = table ? (size_t)(window + 1) * sizeof(double) : 0;
+            const i64 resident = corr ? (table ? resident_ctas(mat_move_seg_kernel<T, true, true>, kMatSegThreads, smem)
+                                               : resident_ctas(mat_move_seg_kernel<T, true, false>, kMatSegThreads, smem))
+                                      : (table ? resident_ctas(mat_move_seg_kernel<T, false, true>, kMatSegThreads, smem)
+                                               : resident_ctas(mat_move_seg_kernel<T, false, false>, kMatSegThreads, smem));
+            const MatSegs sg = mat_segments(batch * bps, resident, no, window);
             if (sg.nseg > 1) {
-                const i64 q = nv * nv;
-                const int bps = (int)((q + kMatSegThreads - 1) / kMatSegThreads);
                 const i64 blocks = batch * sg.nseg * bps;
                 if (blocks > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_matrix: too many segments");
-                const bool table = window <= kMatRcpMax;
-                const size_t smem = table ? (size_t)(window + 1) * sizeof(double) : 0;
 #define NBG_MAT_SEG(C_, T_)                                                                                            \
     mat_move_seg_kernel<T, C_, T_><<<(unsigned)blocks, kMatSegThreads, smem, stream>>>(a, out, batch, no, (int)nv, window, \
                                                                                         min_count, sg.seg_len, sg.nseg, bps)
@@ -492,15 +641,18 @@ int launch_matrix(int op, const void *a_, const void *alpha_, int alpha_per_item
         case NBG_MAT_EXP_COV: {
             const bool corr = op == NBG_MAT_EXP_CORR;
             const T *al = (const T *)alpha_;
-            const MatSegs sg = mat_segments(threads, no, 32);
+            const i64 np = nv * (nv + 1) / 2;
+            const int bps = (int)((np + kMatSegThreads - 1) / kMatSegThreads);
+            const i64 resident = corr ? resident_ctas(mat_exp_seg_kernel<T, true, false>, kMatSegThreads, 0)
+                                      : resident_ctas(mat_exp_seg_kernel<T, false, false>, kMatSegThreads, 0);
+            const MatSegs sg = mat_segments(batch * bps, resident, no, 32);
             if (sg.nseg > 1) {
-                const i64 q = nv * nv;
-                const int bps = (int)((q + kMatSegThreads - 1) / kMatSegThreads);
                 const i64 blocks = batch * sg.nseg * bps;
                 if (blocks > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_matrix: too many segments");
-                const size_t carry_bytes = (size_t)batch * sg.nseg * kMatExpStates * q * sizeof(double);
+                const size_t carry_bytes = (size_t)batch * sg.nseg * kMatExpStates * np * sizeof(double);
                 const size_t decay_bytes = (size_t)batch * sg.nseg * 2 * sizeof(double);
                 void *ws = nullptr;
+                keep_pool_memory();
                 int rc = check_cuda(cudaMallocAsync(&ws, carry_bytes + decay_bytes, stream), "nbg_matrix: workspace");
                 if (rc) return rc;
                 double *carry = (double *)ws, *decays = (double *)((char *)ws + carry_bytes);
@@ -510,8 +662,8 @@ int launch_matrix(int op, const void *a_, const void *alpha_, int alpha_per_item
                                                                                     bps, carry, decays)
                 if (corr) NBG_MAT_EXP(true, true); else NBG_MAT_EXP(false, true);
                 rc = check_launch("nbg_matrix(exp, pass A)");
-                const i64 ct = batch * kMatExpStates * q;
-                if (!rc) mat_exp_carry_kernel<<<(unsigned)((ct + 255) / 256), 256, 0, stream>>>(carry, decays, batch, sg.nseg, q);
+                const i64 ct = batch * kMatExpStates * np;
+                if (!rc) mat_exp_carry_kernel<<<(unsigned)((ct + 255) / 256), 256, 0, stream>>>(carry, decays, batch, sg.nseg, np);
                 if (!rc) rc = check_launch("nbg_matrix(exp, carry)");
                 if (rc) {
                     cudaFreeAsync(ws, stream);
