@@ -111,7 +111,13 @@ __device__ __forceinline__ double qdiv(double a, double b, double y) {
     // an infinite / NaN numerator (or an overflowing quotient) turns the residual into NaN: IEEE path
     return fabs(qc) < __longlong_as_double(0x7ff0000000000000LL) ? qc : a / b;
 }
-__device__ __forceinline__ double fdiv(double a, double b) { return rcp_ok(b) ? qdiv(a, b, fast_rcp(b)) : a / b; }
+__device__ __forceinline__ double fdiv(double a, double b) {
+    // straight-line fast path, ONE test, one IEEE fallback (two nested fallbacks cost registers in the scans)
+    const double y = fast_rcp(b);
+    const double q = a * y;
+    const double qc = fma(fma(-b, q, a), y, q);
+    return (rcp_ok(b) && fabs(qc) < __longlong_as_double(0x7ff0000000000000LL)) ? qc : a / b;
+}
 
 
 // Product of two inputs in the INPUT type, then widened: numba types float32*float32 as

@@ -251,16 +251,28 @@ __global__ void __launch_bounds__(256) group_atomic_kernel(const V *__restrict__
     long long *idx1 = reinterpret_cast<long long *>(ws.ch[1]) + row * K * ws.stride;
     constexpr int PER = 8;
     const int64_t base = blk * (256 * PER);
+    // All 16 loads of a thread are issued before the first one is used: with a label test between
+    // the label load and the value load the kernel exposed two DRAM latencies per element and sat
+    // in long_scoreboard at 43 % of the DRAM bandwidth (ncu, config 5).  Streaming loads
+    // (evict-first): the inputs are read once and must not push the accumulator table out of L2,
+    // where the atomics are resolved.
+    int64_t labs[PER];
+    V vals[PER];
+    const bool whole = base + 256 * PER <= n;
 #pragma unroll
     for (int q = 0; q < PER; q++) {
         const int64_t i = base + (int64_t)q * 256 + threadIdx.x;
-        if (i >= n) break;
-        // streaming loads (evict-first): the inputs are read once and must not push the
-        // accumulator table out of L2, where the atomics are resolved
-        int64_t label = (int64_t)__ldcs(lrow + i);
+        const bool in = whole || i < n;
+        labs[q] = in ? (int64_t)__ldcs(lrow + i) : (int64_t)-1;
+        vals[q] = in ? __ldcs(vrow + i) : (V)0;
+    }
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        const int64_t i = base + (int64_t)q * 256 + threadIdx.x;
+        int64_t label = labs[q];
         if (label < 0 || label >= K) continue;
         label *= ws.stride;  // record offset in 8-byte words
-        const V v = __ldcs(vrow + i);
+        const V v = vals[q];
         if (is_nan(v)) continue;
         const int64_t gi = index_offset + i;
         if (OP == NBG_GROUP_NANSUM) {

@@ -431,6 +431,8 @@ struct Rb2Params {
     int K, C, S, ent_cap;
     int ntiles, tiles_per_seg, nseg;
     int PD;  // tiles beyond the ring that the producer prefetches into L2 (0: off)
+    int nc;      // label split: nc CTAs share a row group, CTA `rank` owns the labels with label % nc == rank
+    int nslots;  // ceil(K / nc) bins per CTA
     int64_t index_offset;
 };
 
@@ -464,7 +466,8 @@ __global__ void __launch_bounds__(NW * 32 + 32, 1) group_rowbins2_kernel(Rb2Para
     uint64_t *done = empty + kRb2MaxStages;                        // [16][2]: warp w finished a tile of parity b
     unsigned char *bins = smem_raw + kRb2Header;
     const int C = p.C, K = p.K, S = p.S;
-    const int nslots = K;  // single-CTA ownership: slot == label
+    const int nc = p.nc, rank = (int)(blockIdx.x % (unsigned)nc);
+    const int nslots = p.nslots;  // this CTA's labels: rank, rank + nc, ... (slot = label / nc)
     const size_t bins_bytes = rb2_bins_bytes<V, CLS>(nslots);
     const size_t ch_bytes = (size_t)(nslots + 1) * 128;
     unsigned char *stage0 = bins + bins_bytes;
@@ -472,8 +475,9 @@ __global__ void __launch_bounds__(NW * 32 + 32, 1) group_rowbins2_kernel(Rb2Para
     const int stride = rb_row_stride<V>(C);
 
     const int tid = threadIdx.x;
-    const int64_t g = blockIdx.x / p.nseg;
-    const int seg = blockIdx.x % p.nseg;
+    const int64_t gs = blockIdx.x / (unsigned)nc;  // the nc CTAs of a row group are adjacent: they stream the same tiles
+    const int64_t g = gs / p.nseg;
+    const int seg = (int)(gs % p.nseg);
     const int64_t r0 = g * kRbRows;
     const int nrows = (int)min((int64_t)kRbRows, p.rows - r0);
     const int t_beg = seg * p.tiles_per_seg;
@@ -514,7 +518,7 @@ __global__ void __launch_bounds__(NW * 32 + 32, 1) group_rowbins2_kernel(Rb2Para
                 const int cols = (int)min((int64_t)C, p.n - c0);
                 const uint32_t row_bytes = (uint32_t)cols * (uint32_t)sizeof(V);
                 mbar_arrive_expect_tx(&full[st], plan_bytes + (uint32_t)nrows * row_bytes);
-                bulk_g2s(sb, p.plan + (size_t)t * (kRb2Hdr + p.ent_cap), plan_bytes, &full[st]);
+                bulk_g2s(sb, p.plan + ((size_t)t * nc + rank) * (kRb2Hdr + p.ent_cap), plan_bytes, &full[st]);
                 V *tile = reinterpret_cast<V *>(sb + (size_t)(kRb2Hdr + p.ent_cap) * 4);
                 for (int rr = 0; rr < nrows; rr++)
                     bulk_g2s(tile + (size_t)rr * stride, vbase + (int64_t)rr * p.n + c0, row_bytes, &full[st]);
@@ -680,19 +684,20 @@ __global__ void __launch_bounds__(NW * 32 + 32, 1) group_rowbins2_kernel(Rb2Para
     const bool atomic = p.nseg > 1;
     constexpr int WPS = 128 / (int)sizeof(V);
     const V *bw = reinterpret_cast<const V *>(bins);
-    for (int idx = tid; idx < K * kRbRows; idx += kRb2Threads) {
-        const int rr = idx & (kRbRows - 1), k = idx >> 3;  // row fastest: 8 lanes read 8 neighbouring banks
-        if (rr >= nrows) continue;
+    for (int idx = tid; idx < nslots * kRbRows; idx += kRb2Threads) {
+        const int rr = idx & (kRbRows - 1), slot = idx >> 3;  // row fastest: 8 lanes read 8 neighbouring banks
+        const int k = slot * nc + rank;                        // the label behind this CTA's slot
+        if (rr >= nrows || k >= K) continue;
         W tot;
         V *tw = reinterpret_cast<V *>(&tot);
 #pragma unroll
-        for (int ch = 0; ch < NCH; ch++) tw[ch] = bw[((size_t)ch * (nslots + 1) + k) * WPS + rr];
+        for (int ch = 0; ch < NCH; ch++) tw[ch] = bw[((size_t)ch * (nslots + 1) + slot) * WPS + rr];
 #pragma unroll
         for (int qq = 1; qq < NCLS; qq++) {
             W o;
             V *ow = reinterpret_cast<V *>(&o);
 #pragma unroll
-            for (int ch = 0; ch < NCH; ch++) ow[ch] = bw[((size_t)ch * (nslots + 1) + k) * WPS + qq * kRbRows + rr];
+            for (int ch = 0; ch < NCH; ch++) ow[ch] = bw[((size_t)ch * (nslots + 1) + slot) * WPS + qq * kRbRows + rr];
             Op::merge(tot, o);
         }
         const RbBin<V, CLS> b = rb2_to_bin<V, CLS>(tot);
@@ -708,7 +713,7 @@ __global__ void __launch_bounds__(NW * 32 + 32, 1) group_rowbins2_kernel(Rb2Para
 // ------------------------------------------------------------------------------------ host
 struct Rb2Geometry {
     bool ok;
-    int C, S, ent_cap, ntiles, nseg, tiles_per_seg, runs, PD, NW;
+    int C, S, ent_cap, ntiles, nseg, tiles_per_seg, runs, PD, NW, nc, nslots;
     size_t smem, plan_bytes, plan_smem, aux_bytes;
 };
 
@@ -719,9 +724,21 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
     constexpr int NCLS = PER16;
     if (K <= 0 || K > 4094 || n <= 0 || n >= ((int64_t)1 << 31) || (n % PER16) != 0 || rows < 1) return g;
     if (getenv("NBG_RB2_OFF")) return g;
-    const size_t bins = rb2_bins_bytes<V, CLS>((int)K);
+    // Label split (NBG_RB2_NC, experiment): the class-private bins cost 128 bytes per (channel, label), so
+    // mean / var at 1000 float32 labels (256 / 384 KB) do not fit one CTA.  nc CTAs can share a row group
+    // -- adjacent in the grid, streaming the same tiles, CTA `rank` owning the labels with
+    // label % nc == rank -- but every one of them still stages whole tiles and pays the per-tile costs
+    // for 1/nc of the entries.  Measured on config 2: nansum 8.4 ms (nc = 1) / 10.2 (2) / 18.5 (4);
+    // nanmean 15.1 (nc = 2) against 13.7 ms for the round-1 kernel; nanstd 23.9 (nc = 3) against 20.9.
+    // Off by default: ops whose bins do not fit keep the round-1 kernel.
+    int nc = 1;
+    if (const char *e = getenv("NBG_RB2_NC")) nc = atoi(e) > 0 ? atoi(e) : 1;
+    if (nc > K) nc = (int)K;
+    const int nslots = (int)((K + nc - 1) / nc);
+    const size_t bins = rb2_bins_bytes<V, CLS>(nslots);
     if (bins + kRb2Header > kMaxSmemOptIn) return g;
     const size_t avail = kMaxSmemOptIn - kRb2Header - bins;
+    g.nc = nc, g.nslots = nslots;
     int S = 2, C = 0;  // two wide stages beat three narrower ones (config 2: 8.6 vs 9.2 ms): per-tile costs dominate
     if (const char *e = getenv("NBG_RB2_S")) S = atoi(e);
     if (S < 2) S = 2;
@@ -742,7 +759,7 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
     const int64_t n_up = (n + 63) / 64 * 64;
     if (C > n_up) C = (int)n_up;
     g.C = C, g.S = S, g.ent_cap = C + kRb2Pad;
-    g.smem = rb2_smem_bytes<V, CLS>((int)K, C, g.ent_cap, S);
+    g.smem = rb2_smem_bytes<V, CLS>(nslots, C, g.ent_cap, S);
     if (g.smem > kMaxSmemOptIn) return g;
     g.plan_smem = (size_t)(2 * NCLS * K + 1) * 4 + (size_t)2 * C * 4 + 16;
     if (g.plan_smem > kMaxSmem) return g;
@@ -751,13 +768,13 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
     // one CTA per SM: whole rows per CTA once there are >= 4 waves of row groups, otherwise column
     // segments (~8 waves) merged into the workspace with atomics
     const int64_t slots = kNumSMs;
-    int64_t nseg = groups >= 4 * slots ? 1 : (8 * slots + groups - 1) / groups;
+    int64_t nseg = groups * nc >= 4 * slots ? 1 : (8 * slots + groups * nc - 1) / (groups * nc);
     if (const char *e = getenv("NBG_RB2_NSEG")) nseg = atoi(e);
     if (nseg > g.ntiles) nseg = g.ntiles;
     if (nseg < 1) nseg = 1;
     g.tiles_per_seg = (int)((g.ntiles + nseg - 1) / nseg);
     g.nseg = (g.ntiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
-    g.plan_bytes = (size_t)g.ntiles * (kRb2Hdr + g.ent_cap) * 4 + 256;
+    g.plan_bytes = (size_t)g.ntiles * nc * (kRb2Hdr + g.ent_cap) * 4 + 256;
     // average run of equal labels inside a class range >= 2: accumulate runs in registers
     g.runs = ((int64_t)C / NCLS >= 2 * K) ? 1 : 0;
     if (const char *e = getenv("NBG_RB2_RUNS")) g.runs = atoi(e);
@@ -774,8 +791,9 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
 }
 
 inline size_t rb2_scratch_bytes(int64_t n) {
-    // narrowest tile is 128 columns: header + padding per tile, 4 bytes per column
-    return (size_t)(n + 2048) * 4 + (size_t)(n / 128 + 4) * (kRb2Hdr + kRb2Pad) * 4 + 4096 + ((size_t)4 * 65536 + 256) * 4;
+    // narrowest tile is 128 columns: header + padding per tile, 4 bytes per column -- times the label
+    // split (every rank's plan block has room for a whole tile; up to 4 ranks fit, else the split is refused)
+    return (size_t)(n + 2048) * 16 + (size_t)(n / 128 + 4) * (kRb2Hdr + kRb2Pad) * 4 + 4096 + ((size_t)4 * 65536 + 256) * 4;
 }
 
 template <typename V, typename L, int CLS>
@@ -802,7 +820,7 @@ static int rb2_launch(const V *values, const L *labels, void *ws_ch[3], int64_t 
     auto pk = group_plan2_kernel<L, NCLS>;
     rc = allow_big_smem(pk, "nbg_group(plan2): cudaFuncSetAttribute");
     if (rc) return rc;
-    pk<<<(unsigned)g.ntiles, 256, g.plan_smem, stream>>>(labels, n, (int)K, g.C, g.ent_cap, 1, (int)sizeof(V), g.runs, g.NW * 4, cuts, plan);
+    pk<<<(unsigned)(g.ntiles * g.nc), 256, g.plan_smem, stream>>>(labels, n, (int)K, g.C, g.ent_cap, g.nc, (int)sizeof(V), g.runs, g.NW * 4, cuts, plan);
     rc = check_launch("nbg_group(plan2)");
     if (rc) return rc;
     Rb2Params p;
@@ -814,12 +832,13 @@ static int rb2_launch(const V *values, const L *labels, void *ws_ch[3], int64_t 
     p.rows = rows, p.n = n, p.K = (int)K, p.C = g.C, p.S = g.S, p.ent_cap = g.ent_cap;
     p.ntiles = g.ntiles, p.tiles_per_seg = g.tiles_per_seg, p.nseg = g.nseg;
     p.PD = g.PD;
+    p.nc = g.nc, p.nslots = g.nslots;
     const int64_t groups = (rows + kRbRows - 1) / kRbRows;
-    if (groups * g.nseg > INT32_MAX) return NBG_OK;
+    if (groups * g.nseg * g.nc > INT32_MAX) return NBG_OK;
     auto launch = [&](auto kern) -> int {
         int r2 = allow_big_smem(kern, "nbg_group(rowbins2): cudaFuncSetAttribute");
         if (r2) return r2;
-        kern<<<(unsigned)(groups * g.nseg), g.NW * 32 + 32, g.smem, stream>>>(p);
+        kern<<<(unsigned)(groups * g.nseg * g.nc), g.NW * 32 + 32, g.smem, stream>>>(p);
         return check_launch("nbg_group(rowbins2)");
     };
     if (g.NW == 31)

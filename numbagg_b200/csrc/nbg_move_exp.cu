@@ -26,6 +26,41 @@ namespace nbg {
 // GATE = false: the caller proved `weight >= min_weight` for every possible state (scalar alpha in
 // [0, 1] and min_weight <= 0: the weight is a sum of non-negative terms), so the weight channel --
 // always the LAST one -- is neither carried nor tested.
+// ---- read-outs ---------------------------------------------------------------------------------
+// Every read-out has ONE straight-line fast path -- reciprocals from the hardware seed, corrected
+// quotients (nbg_common.cuh: they round exactly like the reference's divisions) -- followed by a single
+// test that all divisors were inside the seed's range and every quotient came out finite; anything
+// else (zero / subnormal / infinite sums) goes to an out-of-line copy of the reference's formula with
+// IEEE divisions.  Inlining a division fallback behind each of the 4-5 quotients cost 130-250 bytes of
+// spills per thread under the 64-register cap (config 3: move_exp_nanvar 7.9 -> 10.5 ms).
+#define kExpInf __longlong_as_double(0x7ff0000000000000LL)
+__device__ __forceinline__ double qd(double a, double b, double y) {  // unguarded corrected quotient
+    const double q = a * y;
+    return fma(fma(-b, q, a), y, q);
+}
+__device__ __noinline__ double exp_var_ieee(double s0, double s1, double s2, double s3) {
+    const double m = s1 / s2;
+    const double var_biased = dsub(s0 / s2, dmul(m, m));
+    const double bias = dsub(1.0, s3 / dmul(s2, s2));
+    return bias > 0 ? var_biased / bias : __longlong_as_double(0x7ff8000000000000LL);
+}
+__device__ __noinline__ double exp_cov_ieee(double s0, double s1, double s2, double s3, double s4) {
+    const double cov_biased = dsub(s2, dmul(s0, s1) / s3) / s3;
+    const double bias = dsub(1.0, s4 / dmul(s3, s3));
+    return bias > 0 ? cov_biased / bias : __longlong_as_double(0x7ff8000000000000LL);
+}
+__device__ __noinline__ double exp_corr_ieee(double s0, double s1, double s2, double s3, double s4, double s5, double s6) {
+    const double cov = dsub(s2, dmul(s0, s1) / s3);
+    const double var1 = dsub(s5, dmul(s0, s0) / s3);
+    const double var2 = dsub(s6, dmul(s1, s1) / s3);
+    const double bias = dsub(1.0, s4 / dmul(s3, s3));
+    if (bias > 0) {
+        const double den = sqrt(dmul(var1, var2));
+        if (den > 0) return cov / den;
+    }
+    return __longlong_as_double(0x7ff8000000000000LL);
+}
+
 // contrib(): value added to each channel for one valid observation.  SQ_CH: the channel that
 // decays with d^2 (-1: none).  output(): read-out from the state.
 template <typename T, bool GATE = true>
@@ -84,23 +119,22 @@ struct ExpVar {  // moving_exp.py:106-224  channels: sum_x_2, sum_x, sum_weight,
         if (GATE) c[NCH - 1] = alpha;
     }
     __device__ static __forceinline__ T output(const double *s, bool, double mw) {
-        double var_biased, bias;
+        if (GATE && !(s[NCH - 1] >= mw)) return quiet_nan<T>();
         const double sw2 = dmul(s[2], s[2]);
-        if (rcp_ok(s[2]) && rcp_ok(sw2)) {
-            const double r = fast_rcp(s[2]);  // two reciprocals + four corrected quotients instead of four divisions
-            const double m = qdiv(s[1], s[2], r);
-            var_biased = dsub(qdiv(s[0], s[2], r), dmul(m, m));
-            bias = dsub(1.0, qdiv(s[3], sw2, fast_rcp(sw2)));
+        const double r = fast_rcp(s[2]);
+        const double m = qd(s[1], s[2], r), e = qd(s[0], s[2], r);
+        const double var_biased = dsub(e, dmul(m, m));
+        const double t = qd(s[3], sw2, fast_rcp(sw2));
+        const double bias = dsub(1.0, t);
+        double v;
+        if (rcp_ok(s[2]) && rcp_ok(sw2) && fabs(m) + fabs(e) + fabs(t) < kExpInf) {
+            if (!(bias > 0)) return quiet_nan<T>();
+            v = qd(var_biased, bias, fast_rcp(bias));
+            if (!(rcp_ok(bias) && fabs(v) < kExpInf)) v = var_biased / bias;
         } else {
-            const double m = s[1] / s[2];
-            var_biased = dsub(s[0] / s[2], dmul(m, m));
-            bias = dsub(1.0, s[3] / dmul(s[2], s[2]));
+            v = exp_var_ieee(s[0], s[1], s[2], s[3]);
         }
-        if ((!GATE || s[NCH - 1] >= mw) && bias > 0) {
-            const double v = fdiv(var_biased, bias);
-            return (T)(SQRT ? sqrt(v) : v);
-        }
-        return quiet_nan<T>();
+        return (T)(SQRT ? sqrt(v) : v);
     }
 };
 template <typename T, bool GATE = true>
@@ -116,17 +150,22 @@ struct ExpCov {  // moving_exp.py:227-273  channels: sum_x1, sum_x2, sum_x1x2, s
         if (GATE) c[NCH - 1] = alpha;
     }
     __device__ static __forceinline__ T output(const double *s, bool, double mw) {
-        double cov_biased, bias;
+        if (GATE && !(s[NCH - 1] >= mw)) return quiet_nan<T>();
         const double sw2 = dmul(s[3], s[3]);
-        if (rcp_ok(s[3]) && rcp_ok(sw2)) {
-            const double r = fast_rcp(s[3]);
-            cov_biased = qdiv(dsub(s[2], qdiv(dmul(s[0], s[1]), s[3], r)), s[3], r);
-            bias = dsub(1.0, qdiv(s[4], sw2, fast_rcp(sw2)));
+        const double r = fast_rcp(s[3]);
+        const double a = qd(dmul(s[0], s[1]), s[3], r);
+        const double cov_biased = qd(dsub(s[2], a), s[3], r);
+        const double t = qd(s[4], sw2, fast_rcp(sw2));
+        const double bias = dsub(1.0, t);
+        double v;
+        if (rcp_ok(s[3]) && rcp_ok(sw2) && fabs(a) + fabs(cov_biased) + fabs(t) < kExpInf) {
+            if (!(bias > 0)) return quiet_nan<T>();
+            v = qd(cov_biased, bias, fast_rcp(bias));
+            if (!(rcp_ok(bias) && fabs(v) < kExpInf)) v = cov_biased / bias;
         } else {
-            cov_biased = dsub(s[2], dmul(s[0], s[1]) / s[3]) / s[3];
-            bias = dsub(1.0, s[4] / dmul(s[3], s[3]));
+            v = exp_cov_ieee(s[0], s[1], s[2], s[3], s[4]);
         }
-        return ((!GATE || s[NCH - 1] >= mw) && bias > 0) ? (T)fdiv(cov_biased, bias) : quiet_nan<T>();
+        return (T)v;
     }
 };
 template <typename T, bool GATE = true>
@@ -144,25 +183,24 @@ struct ExpCorr {  // moving_exp.py:276-335  + sum_x1_2, sum_x2_2  (the weight, w
         if (GATE) c[NCH - 1] = alpha;
     }
     __device__ static __forceinline__ T output(const double *s, bool, double mw) {
-        double cov, var1, var2, bias;
+        if (GATE && !(s[NCH - 1] >= mw)) return quiet_nan<T>();
         const double sw2 = dmul(s[3], s[3]);
-        if (rcp_ok(s[3]) && rcp_ok(sw2)) {
-            const double r = fast_rcp(s[3]);
-            cov = dsub(s[2], qdiv(dmul(s[0], s[1]), s[3], r));
-            var1 = dsub(s[5], qdiv(dmul(s[0], s[0]), s[3], r));
-            var2 = dsub(s[6], qdiv(dmul(s[1], s[1]), s[3], r));
-            bias = dsub(1.0, qdiv(s[4], sw2, fast_rcp(sw2)));
-        } else {
-            cov = dsub(s[2], dmul(s[0], s[1]) / s[3]);
-            var1 = dsub(s[5], dmul(s[0], s[0]) / s[3]);
-            var2 = dsub(s[6], dmul(s[1], s[1]) / s[3]);
-            bias = dsub(1.0, s[4] / dmul(s[3], s[3]));
-        }
-        if ((!GATE || s[NCH - 1] >= mw) && bias > 0) {
+        const double r = fast_rcp(s[3]);
+        const double a = qd(dmul(s[0], s[1]), s[3], r), b = qd(dmul(s[0], s[0]), s[3], r), c = qd(dmul(s[1], s[1]), s[3], r);
+        const double cov = dsub(s[2], a), var1 = dsub(s[5], b), var2 = dsub(s[6], c);
+        const double t = qd(s[4], sw2, fast_rcp(sw2));
+        const double bias = dsub(1.0, t);
+        double v;
+        if (rcp_ok(s[3]) && rcp_ok(sw2) && fabs(a) + fabs(b) + fabs(c) + fabs(t) < kExpInf) {
+            if (!(bias > 0)) return quiet_nan<T>();
             const double den = sqrt(dmul(var1, var2));
-            return den > 0 ? (T)fdiv(cov, den) : quiet_nan<T>();
+            if (!(den > 0)) return quiet_nan<T>();
+            v = qd(cov, den, fast_rcp(den));
+            if (!(rcp_ok(den) && fabs(v) < kExpInf)) v = cov / den;
+        } else {
+            v = exp_corr_ieee(s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
         }
-        return quiet_nan<T>();
+        return (T)v;
     }
 };
 
@@ -239,7 +277,7 @@ struct ExpPolicy {
     using Op = Op_;
     using Agg = ExpAgg<Op>;
     static constexpr int NSTREAM = Op::NIN + (ALPHA_STREAM ? 1 : 0);
-    static constexpr int MIN_CTAS = (Op::NCH <= 3 && !ALPHA_STREAM) ? 5 : (Op::NCH <= 5 ? 4 : 3);  // register caps: 51 / 64 / 85
+    static constexpr int MIN_CTAS = (Op::NCH <= 3 && !ALPHA_STREAM) ? 5 : (Op::NCH <= 4 ? 4 : (Op::NCH <= 5 ? 3 : 2));  // register caps: 51 / 64 / 85 / 128 (measured, config 3)
     static constexpr bool REV = false;
     static constexpr bool OVERLAP_INDEPENDENT = false;  // a chunk is carry-free only after ~7k elements of decay
     __device__ static __forceinline__ const T *stream_row(const ScanParams &p, int s, int64_t row) {

@@ -11,11 +11,11 @@
 //     bitonic network and reads the order statistics off (quant_sort_kernel);
 //   rows of <= 4096 elements: the radix select below, run by one CTA on the row's keys in
 //     shared memory (quant_smem_select_kernel);
-//   longer rows: radix select, 8 bits per pass from the top: every pass histograms the digit
-//     of the elements that match each target's prefix so far (shared-memory histograms, warp-
-//     aggregated, flushed to global), a tiny kernel picks the bucket holding the target rank
-//     and extends the prefix; after 8 passes the prefix IS the key of the order statistic.
-//     8 reads of the data, no scratch copy, any number of rows per launch.
+//   longer rows: radix select, 11 bits per pass from the top (shared-memory histograms per distinct
+//     target prefix, flushed to global; a warp per target picks the bucket holding its rank);
+//     after two passes the elements still matching a 22-bit prefix are compacted into a small
+//     per-row candidate list, which one CTA sorts: 3 reads of the data (rows with more ties than
+//     the list holds go on with histogram passes), any number of rows per launch.
 #include "nbg_common.cuh"
 
 namespace nbg {
@@ -228,14 +228,33 @@ __global__ void __launch_bounds__(kQThreads) quant_smem_select_kernel(const doub
 }
 
 // ------------------------------------------------------------------ long rows: radix select
-// Workspace per row: valid count, and per target (2 per quantile) the key prefix found so far
-// and the rank that remains inside that prefix's bucket (-1: inactive target).
+// 11-bit digits from the top (6 passes would finish the key: 5 x 11 + 9 bits), but after TWO
+// histogram passes a target's bucket is 2^-22 of the key space -- a few hundred elements of a
+// million -- so the third read of the data only COMPACTS the elements that still match some
+// target's 22-bit prefix into a per-row candidate list (<= kQCap keys), and one CTA per row sorts
+// that list in shared memory and reads every order statistic off it.  3 reads of the data instead
+// of 8.  A row whose buckets hold more than kQCap candidates (heavy ties: every copy of a repeated
+// value shares all 64 bits) keeps going with histogram passes 2..5; rows are independent, so the
+// kernel sequence is fixed and finished rows simply skip the tail.
+// Workspace per row: valid count; per target (2 per quantile) the key prefix found so far, the
+// rank that remains inside that prefix's bucket (-1: inactive target) and the size of that bucket.
+constexpr int kQBins = 2048;
+constexpr int kQPasses = 6;
+constexpr int kQCap = 2048;    // candidate keys per row (16 KB of shared memory in the finishing CTA)
+constexpr int kQChunk = 12;    // quantiles per internal round: 24 histograms x 8 KB of shared memory
+__host__ __device__ inline int q_shift(int pass) { return pass < 5 ? 53 - 11 * pass : 0; }
+__host__ __device__ inline int q_bits(int pass) { return pass < 5 ? 11 : 9; }
+
 struct QuantWs {
-    i64 *valid;        // [rows]
-    u64 *prefix;       // [rows][T2]
-    i64 *remaining;    // [rows][T2]
-    unsigned *hist;    // [rows][T2][256]
-    int *alias;        // [rows][T2]: first target with the same prefix (its histogram serves both)
+    i64 *valid;         // [rows]
+    u64 *prefix;        // [rows][T2]
+    i64 *remaining;     // [rows][T2]
+    unsigned *bucket;   // [rows][T2]: elements in the bucket chosen by the last select
+    int *alias;         // [rows][T2]: first target with the same prefix (its histogram serves both)
+    unsigned *hist;     // [rows][T2][kQBins]
+    int *done;          // [rows]: 1 = finished from the candidate list
+    unsigned *ncand;    // [rows]
+    u64 *cand;          // [rows][kQCap]
 };
 
 // bin += 1 for every lane with `pred`, one shared-memory atomic per distinct digit in the warp
@@ -246,60 +265,72 @@ __device__ __forceinline__ void warp_hist_add(unsigned *bins, unsigned digit, bo
     if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&bins[digit], (unsigned)__popc(peers));
 }
 
-// pass = 0: one histogram of the top digit per row (+ the count of non-NaN elements);
-// pass >= 1: per target, the next digit of the elements that match the target's prefix.
-// grid = (segments, rows)
-__global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__restrict__ a, QuantWs ws, i64 n, int T2,
-                                                               int pass) {
-    extern __shared__ __align__(16) unsigned char quant_smem[];
-    unsigned *h = reinterpret_cast<unsigned *>(quant_smem);  // [ntab][256]
+// The distinct prefixes among a row's active targets, as a compact (prefix, owner target) list in
+// shared memory; returns their number.  alias_out (may be null): first target with the same prefix.
+__device__ __forceinline__ int quant_distinct(const QuantWs &ws, i64 row, int T2, u64 *s_pre, int *s_tab, unsigned *s_cnt,
+                                              int *alias_out) {
     __shared__ u64 s_prefix[2 * kQMaxQ];
     __shared__ int s_active[2 * kQMaxQ];
-    __shared__ int s_valid;
+    __shared__ int s_first[2 * kQMaxQ];
+    __shared__ int s_n;
     const int tid = threadIdx.x;
-    const i64 row = blockIdx.y;
-    const int ntab = pass == 0 ? 1 : T2;
-    for (int i = tid; i < ntab * 256; i += kQThreads) h[i] = 0;
     if (tid < T2) {
         s_prefix[tid] = ws.prefix[row * T2 + tid];
         s_active[tid] = ws.remaining[row * T2 + tid] >= 0 ? 1 : 0;
     }
-    if (tid == 0) s_valid = 0;
     __syncthreads();
-    // targets that still share their prefix (floor and ceil rank of one quantile, usually up
-    // to the last bits) share one histogram: only the first of them is counted
-    int counted = 0;
-    if (pass > 0 && tid < T2) {
+    if (tid < T2) {
         int first = tid;
         for (int t = tid - 1; t >= 0; t--)
             if (s_active[t] && s_prefix[t] == s_prefix[tid]) first = t;
-        counted = s_active[tid] && first == tid;
-        if (blockIdx.x == 0) ws.alias[row * T2 + tid] = first;
+        s_first[tid] = first;
+        if (alias_out) alias_out[row * T2 + tid] = first;
     }
-    __syncthreads();  // every thread: all reads of s_active above precede the update below
-    if (pass > 0 && tid < T2) s_active[tid] = counted;
     __syncthreads();
-    // compact list of the histograms to fill: (prefix, table) pairs; one entry in the common
-    // case of a single quantile whose floor and ceil ranks still share their prefix
-    __shared__ int s_ncounted;
-    __shared__ int s_tab[2 * kQMaxQ];
-    __shared__ u64 s_pre[2 * kQMaxQ];
     if (tid == 0) {
         int c = 0;
-        for (int t = 0; t < T2 && pass > 0; t++)
-            if (s_active[t]) {
+        for (int t = 0; t < T2; t++)
+            if (s_active[t] && s_first[t] == t) {
                 s_tab[c] = t;
                 s_pre[c] = s_prefix[t];
+                if (s_cnt) s_cnt[c] = ws.bucket[row * T2 + t];
                 c++;
             }
-        s_ncounted = c;
+        s_n = c;
     }
     __syncthreads();
-    const int ncounted = s_ncounted;
+    return s_n;
+}
+
+// pass = 0: one histogram of the top digit per row (+ the count of non-NaN elements);
+// pass >= 1: per distinct prefix, the next digit of the elements that match it.
+// grid = (segments, rows)
+__global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__restrict__ a, QuantWs ws, i64 n, int T2,
+                                                               int pass) {
+    extern __shared__ __align__(16) unsigned char quant_smem[];
+    unsigned *h = reinterpret_cast<unsigned *>(quant_smem);  // [ntab][kQBins]
+    __shared__ int s_tab[2 * kQMaxQ];
+    __shared__ u64 s_pre[2 * kQMaxQ];
+    __shared__ int s_valid;
+    const int tid = threadIdx.x;
+    const i64 row = blockIdx.y;
+    if (pass >= 2 && ws.done[row]) return;
+    int ncounted = 0;
+    if (pass > 0) ncounted = quant_distinct(ws, row, T2, s_pre, s_tab, nullptr, blockIdx.x == 0 ? ws.alias : nullptr);
+    const int nbins = 1 << q_bits(pass);
+    if (pass == 0) {
+        for (int i = tid; i < nbins; i += kQThreads) h[i] = 0;
+    } else {
+        for (int c = 0; c < ncounted; c++)
+            for (int i = tid; i < nbins; i += kQThreads) h[s_tab[c] * kQBins + i] = 0;
+    }
+    if (tid == 0) s_valid = 0;
+    __syncthreads();
     const u64 pre0 = s_pre[0];
-    unsigned *h0 = h + (ncounted > 0 ? s_tab[0] : 0) * 256;
+    unsigned *h0 = h + (ncounted > 0 ? s_tab[0] : 0) * kQBins;
     const double *p = a + row * n;
-    const int shift = 56 - 8 * pass;
+    const int shift = q_shift(pass), hshift = shift + q_bits(pass);
+    const unsigned mask = (unsigned)nbins - 1u;
     int local_valid = 0;
     // whole warps iterate together (the histogram update uses warp votes)
     const i64 per_cta = ((n + gridDim.x - 1) / gridDim.x + 31) & ~(i64)31;
@@ -318,19 +349,18 @@ __global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__r
             const bool in = base + (i64)u * kQThreads + tid < hi;
             const double x = xs[u];
             const u64 key = quant_key(x);
-            const unsigned digit = (unsigned)(key >> shift) & 255u;
+            const unsigned digit = (unsigned)(key >> shift) & mask;
             if (pass == 0) {
                 local_valid += (in && x == x) ? 1 : 0;
+                // sign and exponent: a handful of distinct digits per warp -> warp-aggregated update
                 warp_hist_add(h, digit, in);
             } else {
-                // (pass 0 sees a handful of digits -- sign and top exponent bits -- and needs
-                // the warp-aggregated update; from here on the digits spread out)
-                const u64 head = key >> (shift + 8);
+                const u64 head = key >> hshift;
                 if (ncounted == 1) {
                     if (in && head == pre0) atomicAdd(&h0[digit], 1u);
                 } else {
                     for (int c = 0; c < ncounted; c++)
-                        if (in && head == s_pre[c]) atomicAdd(&h[s_tab[c] * 256 + digit], 1u);
+                        if (in && head == s_pre[c]) atomicAdd(&h[s_tab[c] * kQBins + digit], 1u);
                 }
             }
         }
@@ -340,20 +370,30 @@ __global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__r
         if ((tid & 31) == 0 && local_valid) atomicAdd(&s_valid, local_valid);
     }
     __syncthreads();
-    unsigned *g = ws.hist + (size_t)row * T2 * 256;
-    for (int i = tid; i < ntab * 256; i += kQThreads)
-        if (h[i]) atomicAdd(&g[i], h[i]);
+    unsigned *g = ws.hist + (size_t)row * T2 * kQBins;
+    if (pass == 0) {
+        for (int i = tid; i < nbins; i += kQThreads)
+            if (h[i]) atomicAdd(&g[i], h[i]);
+    } else {
+        for (int c = 0; c < ncounted; c++)
+            for (int i = tid; i < nbins; i += kQThreads) {
+                const int w = s_tab[c] * kQBins + i;
+                if (h[w]) atomicAdd(&g[w], h[w]);
+            }
+    }
     if (pass == 0 && tid == 0 && s_valid) atomicAdd(reinterpret_cast<u64 *>(&ws.valid[row]), (u64)s_valid);
 }
 
-// one thread per (row, target): pick the bucket that holds the remaining rank, extend the
-// prefix, clear the histogram for the next pass.  After pass 0 the targets are created first.
-__global__ void quant_select_kernel(QuantWs ws, const double *__restrict__ q, i64 rows, int T2, int pass) {
-    const i64 gid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+// one WARP per (row, target): pick the bucket that holds the remaining rank and extend the prefix.
+// After pass 0 the targets are created first.
+__global__ void __launch_bounds__(128) quant_select_kernel(QuantWs ws, const double *__restrict__ q, i64 rows, int T2, int pass) {
+    const i64 gid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (gid >= rows * T2) return;
     const i64 row = gid / T2;
     const int t = (int)(gid % T2);
-    unsigned *h = ws.hist + ((size_t)row * T2 + (pass == 0 ? 0 : ws.alias[gid])) * 256;
+    if (pass >= 2 && ws.done[row]) return;
+    const unsigned *h = ws.hist + ((size_t)row * T2 + (pass == 0 ? 0 : ws.alias[gid])) * kQBins;
     i64 rem = ws.remaining[gid];
     u64 prefix = ws.prefix[gid];
     if (pass == 0) {
@@ -368,27 +408,142 @@ __global__ void quant_select_kernel(QuantWs ws, const double *__restrict__ q, i6
             rem = (t & 1) ? hi : lo;
         }
     }
-    if (rem >= 0) {
-        i64 cum = 0;
-        int d = 0;
-        for (; d < 255; d++) {
-            const i64 c = (i64)h[d];
-            if (rem < cum + c) break;
-            cum += c;
+    unsigned bucket = 0;
+    if (rem >= 0) {  // uniform across the warp
+        const int nbins = 1 << q_bits(pass), per = nbins / 32;
+        const unsigned *hl = h + lane * per;
+        unsigned mine = 0;
+        for (int b = 0; b < per; b++) mine += hl[b];
+        unsigned inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
         }
-        rem -= cum;
-        prefix = (prefix << 8) | (u64)d;
+        const unsigned before = inc - mine;
+        const bool here = rem >= (i64)before && rem < (i64)inc;
+        const unsigned who = __ballot_sync(0xffffffffu, here);
+        const int owner = who ? __ffs(who) - 1 : 31;  // (the last lane takes over if the counts were inconsistent)
+        int d = 0;
+        i64 r2 = 0;
+        if (lane == owner) {
+            r2 = rem - (i64)before;
+            for (; d < per - 1; d++) {
+                const i64 c = (i64)hl[d];
+                if (r2 < c) break;
+                r2 -= c;
+            }
+            bucket = hl[d];
+            d += lane * per;
+        }
+        d = __shfl_sync(0xffffffffu, d, owner);
+        r2 = __shfl_sync(0xffffffffu, r2, owner);
+        bucket = __shfl_sync(0xffffffffu, bucket, owner);
+        rem = r2;
+        prefix = (prefix << q_bits(pass)) | (u64)d;
     }
-    ws.remaining[gid] = rem;
-    ws.prefix[gid] = prefix;
+    if (lane == 0) {
+        ws.remaining[gid] = rem;
+        ws.prefix[gid] = prefix;
+        ws.bucket[gid] = bucket;
+    }
 }
 
-__global__ void quant_clear_kernel(unsigned *hist, i64 count) {
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) hist[i] = 0;
+// Third read of the data (after passes 0 and 1): elements that match a target's 22-bit prefix go to
+// the row's candidate list -- if the buckets of the row's distinct prefixes fit in it.
+__global__ void __launch_bounds__(kQThreads) quant_compact_kernel(const double *__restrict__ a, QuantWs ws, i64 n, int T2) {
+    __shared__ int s_tab[2 * kQMaxQ];
+    __shared__ u64 s_pre[2 * kQMaxQ];
+    __shared__ unsigned s_cnt[2 * kQMaxQ];
+    const int tid = threadIdx.x;
+    const i64 row = blockIdx.y;
+    const int nd = quant_distinct(ws, row, T2, s_pre, s_tab, s_cnt, nullptr);
+    unsigned total = 0;
+    for (int c = 0; c < nd; c++) total += s_cnt[c];
+    if (nd == 0 || total > (unsigned)kQCap) return;  // no active target / too many ties: histogram passes go on
+    const u64 pre0 = s_pre[0];
+    const double *p = a + row * n;
+    u64 *cand = ws.cand + (size_t)row * kQCap;
+    const int hshift = q_shift(1);  // the prefix is the top 22 bits
+    const i64 per_cta = (n + gridDim.x - 1) / gridDim.x;
+    const i64 lo = (i64)blockIdx.x * per_cta;
+    const i64 hi = lo + per_cta < n ? lo + per_cta : n;
+    constexpr int U = 8;
+    for (i64 base = lo; base < hi; base += (i64)U * kQThreads) {
+        double xs[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const i64 i = base + (i64)u * kQThreads + tid;
+            xs[u] = i < hi ? __ldcs(p + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool in = base + (i64)u * kQThreads + tid < hi;
+            const u64 key = quant_key(xs[u]);
+            const u64 head = key >> hshift;
+            bool hit = in && head == pre0;
+            for (int c = 1; c < nd; c++) hit = hit || (in && head == s_pre[c]);
+            if (hit) {
+                const unsigned pos = atomicAdd(&ws.ncand[row], 1u);
+                if (pos < (unsigned)kQCap) cand[pos] = key;
+            }
+        }
+    }
 }
 
-__global__ void quant_finish_kernel(QuantWs ws, const double *__restrict__ q, double *__restrict__ out, i64 rows, int m) {
+// One CTA per row: sort the candidate list, read the order statistics off.  The candidates of
+// different prefixes occupy disjoint key ranges, so target t is at (first key >= prefix << 42) + rank
+// inside its bucket.
+__global__ void __launch_bounds__(kQThreads) quant_candidates_kernel(QuantWs ws, int T2) {
+    __shared__ u64 keys[kQCap];
+    __shared__ int s_tab[2 * kQMaxQ];
+    __shared__ u64 s_pre[2 * kQMaxQ];
+    __shared__ unsigned s_cnt[2 * kQMaxQ];
+    const int tid = threadIdx.x;
+    const i64 row = blockIdx.x;
+    const int nd = quant_distinct(ws, row, T2, s_pre, s_tab, s_cnt, nullptr);
+    unsigned total = 0;
+    for (int c = 0; c < nd; c++) total += s_cnt[c];
+    if (nd == 0 || total > (unsigned)kQCap) return;
+    const int cnt = (int)min(ws.ncand[row], (unsigned)kQCap);  // == total
+    int npad = 2;
+    while (npad < cnt) npad <<= 1;
+    const u64 *cand = ws.cand + (size_t)row * kQCap;
+    for (int i = tid; i < npad; i += kQThreads) keys[i] = i < cnt ? cand[i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (npad >> 1); t += kQThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int pp = i | j;
+                const bool up = (i & k) == 0;
+                const u64 x = keys[i], y = keys[pp];
+                if ((x > y) == up) {
+                    keys[i] = y;
+                    keys[pp] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < T2) {
+        const i64 rem = ws.remaining[row * T2 + tid];
+        if (rem >= 0) {
+            const u64 first = ws.prefix[row * T2 + tid] << q_shift(1);
+            int lo = 0, hi = cnt;  // first index with keys[idx] >= first
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (keys[mid] < first) lo = mid + 1; else hi = mid;
+            }
+            const int at = lo + (int)rem;
+            ws.prefix[row * T2 + tid] = keys[at < cnt ? at : cnt - 1];
+        }
+    }
+    if (tid == 0) ws.done[row] = 1;
+}
+
+__global__ void quant_finish_kernel(QuantWs ws, const double *__restrict__ q, double *__restrict__ out, i64 rows, int m,
+                                    int m_total, int t_off) {
     const i64 gid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= rows * m) return;
     const i64 row = gid / m;
@@ -404,23 +559,34 @@ __global__ void quant_finish_kernel(QuantWs ws, const double *__restrict__ q, do
         const double cv = key_to_double(ws.prefix[(row * m + t) * 2 + 1]);
         r = quant_interpolate(fv, cv, rank, lo);
     }
-    out[gid] = r;
+    out[row * m_total + t_off + t] = r;
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct QuantLayout {
-    size_t valid, prefix, remaining, alias, hist, total;
+    size_t valid, prefix, remaining, bucket, alias, done, ncand, hist, cand, zero_bytes, total;
 };
 QuantLayout quant_layout(i64 rows, i64 m) {
     QuantLayout l;
-    const size_t T2 = 2 * (size_t)m;
-    l.valid = 0;
-    l.prefix = align256((size_t)rows * 8);
-    l.remaining = l.prefix + align256((size_t)rows * T2 * 8);
-    l.alias = l.remaining + align256((size_t)rows * T2 * 8);
-    l.hist = l.alias + align256((size_t)rows * T2 * 4);
-    l.total = l.hist + align256((size_t)rows * T2 * 256 * 4);
+    const size_t T2 = 2 * (size_t)(m < kQChunk ? m : kQChunk);
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = o;
+        o += align256(bytes);
+        return at;
+    };
+    l.valid = take((size_t)rows * 8);
+    l.prefix = take((size_t)rows * T2 * 8);
+    l.remaining = take((size_t)rows * T2 * 8);
+    l.bucket = take((size_t)rows * T2 * 4);
+    l.alias = take((size_t)rows * T2 * 4);
+    l.done = take((size_t)rows * 4);
+    l.ncand = take((size_t)rows * 4);
+    l.hist = take((size_t)rows * T2 * kQBins * 4);
+    l.zero_bytes = o;  // everything up to here starts at zero
+    l.cand = take((size_t)rows * kQCap * 8);
+    l.total = o;
     return l;
 }
 
@@ -463,30 +629,42 @@ extern "C" int nbg_quantile(const void *a, const void *q, void *out, int64_t row
     if (workspace == nullptr || workspace_bytes < l.total + 256)
         return fail(NBG_ERR_WORKSPACE, "nbg_quantile: workspace smaller than nbg_quantile_workspace_bytes()");
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    QuantWs ws{(i64 *)(base + l.valid), (u64 *)(base + l.prefix), (i64 *)(base + l.remaining),
-               (unsigned *)(base + l.hist), (int *)(base + l.alias)};
-    const int T2 = 2 * (int)m;
-    int rc = check_cuda(cudaMemsetAsync(base, 0, l.total, stream), "nbg_quantile: workspace memset");
-    if (rc) return rc;
+    QuantWs ws{(i64 *)(base + l.valid), (u64 *)(base + l.prefix), (i64 *)(base + l.remaining), (unsigned *)(base + l.bucket),
+               (int *)(base + l.alias), (unsigned *)(base + l.hist), (int *)(base + l.done), (unsigned *)(base + l.ncand),
+               (u64 *)(base + l.cand)};
     if (rows > 65535) return fail(NBG_ERR_UNSUPPORTED, "nbg_quantile: more than 65535 rows longer than 4096 elements");
     // about one wave of CTAs over all rows; every CTA at least 4096 elements
     int64_t segs = ((int64_t)kNumSMs * 8 + rows - 1) / rows;
     const int64_t max_segs = (n + 4095) / 4096;
     if (segs > max_segs) segs = max_segs;
     if (segs < 1) segs = 1;
-    const int64_t sel_threads = rows * T2;
-    const int64_t hist_words = rows * T2 * 256;
-    for (int pass = 0; pass < 8; pass++) {
-        const size_t smem = (size_t)(pass == 0 ? 1 : T2) * 256 * sizeof(unsigned);
-        quant_hist_kernel<<<dim3((unsigned)segs, (unsigned)rows), kQThreads, smem, stream>>>(ad, ws, n, T2, pass);
-        if ((rc = check_launch("nbg_quantile hist"))) return rc;
-        quant_select_kernel<<<(unsigned)((sel_threads + 127) / 128), 128, 0, stream>>>(ws, qd, rows, T2, pass);
-        if ((rc = check_launch("nbg_quantile select"))) return rc;
-        if (pass < 7) {
-            quant_clear_kernel<<<(unsigned)((hist_words + 255) / 256), 256, 0, stream>>>(ws.hist, hist_words);
-            if ((rc = check_launch("nbg_quantile clear"))) return rc;
+    int rc = allow_big_smem(quant_hist_kernel, "nbg_quantile: cudaFuncSetAttribute");
+    if (rc) return rc;
+    for (int64_t q0 = 0; q0 < m; q0 += kQChunk) {  // rounds of <= 12 quantiles: 24 histograms of 8 KB in shared memory
+        const int mc = (int)(m - q0 < kQChunk ? m - q0 : kQChunk);
+        const int T2 = 2 * mc;
+        const size_t hist_bytes = (size_t)rows * T2 * kQBins * sizeof(unsigned);
+        if ((rc = check_cuda(cudaMemsetAsync(base, 0, l.zero_bytes, stream), "nbg_quantile: workspace memset"))) return rc;
+        const int64_t sel_threads = rows * T2 * 32;
+        for (int pass = 0; pass < kQPasses; pass++) {
+            if (pass == 2) {
+                // the third read compacts the candidates; rows that fit are finished from their list
+                quant_compact_kernel<<<dim3((unsigned)segs, (unsigned)rows), kQThreads, 0, stream>>>(ad, ws, n, T2);
+                if ((rc = check_launch("nbg_quantile compact"))) return rc;
+                quant_candidates_kernel<<<(unsigned)rows, kQThreads, 0, stream>>>(ws, T2);
+                if ((rc = check_launch("nbg_quantile candidates"))) return rc;
+            }
+            if (pass > 0 && (rc = check_cuda(cudaMemsetAsync(ws.hist, 0, hist_bytes, stream), "nbg_quantile: histogram memset")))
+                return rc;
+            const size_t smem = (size_t)(pass == 0 ? 1 : T2) * kQBins * sizeof(unsigned);
+            quant_hist_kernel<<<dim3((unsigned)segs, (unsigned)rows), kQThreads, smem, stream>>>(ad, ws, n, T2, pass);
+            if ((rc = check_launch("nbg_quantile hist"))) return rc;
+            quant_select_kernel<<<(unsigned)((sel_threads + 127) / 128), 128, 0, stream>>>(ws, qd + q0, rows, T2, pass);
+            if ((rc = check_launch("nbg_quantile select"))) return rc;
         }
+        quant_finish_kernel<<<(unsigned)((rows * mc + 127) / 128), 128, 0, stream>>>(ws, qd + q0, (double *)out, rows, mc, (int)m,
+                                                                                    (int)q0);
+        if ((rc = check_launch("nbg_quantile finish"))) return rc;
     }
-    quant_finish_kernel<<<(unsigned)((rows * m + 127) / 128), 128, 0, stream>>>(ws, qd, (double *)out, rows, (int)m);
-    return check_launch("nbg_quantile finish");
+    return NBG_OK;
 }

@@ -971,10 +971,13 @@ def run_quantile(t: torch.Tensor, q: torch.Tensor, axes: tuple[int, ...]) -> tor
     flat = cube.reshape(rows, view.n)
     out = torch.empty((rows, m_all), dtype=torch.float64, device=t.device)
     # the C entry takes <= 16 quantiles and (on its long-row path) <= 65535 rows per call; the long-row
-    # workspace holds rows * 2m * 256 histogram words, so the row block shrinks with the number of
-    # quantiles to keep it at <= ~128 MB, and it is allocated once
+    # workspace (histograms of 2048 words per target + a 2048-key candidate list per row) is kept at
+    # <= ~256 MB by shrinking the row block with the number of quantiles, and it is allocated once
     m_max = min(m_all, _lib.NBG_QUANTILE_MAX_Q)
-    row_step = rows if view.n <= 4096 else max(256, min(32768, (128 << 20) // max(1, 2 * m_max * 256 * 4)))
+    row_step = rows
+    if view.n > 4096 and rows and m_all:
+        per_row = max(1, int(L.nbg_quantile_workspace_bytes(1024, view.n, max(m_max, 1))) // 1024)
+        row_step = max(64, min(32768, (256 << 20) // per_row))
     ws_cap = int(L.nbg_quantile_workspace_bytes(min(rows, row_step), view.n, max(m_max, 1))) if rows and m_all else 0
     ws_all = torch.empty(max(ws_cap, 1), dtype=torch.uint8, device=t.device)
     for r0 in range(0, rows, max(row_step, 1)):

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -q -x -k "group" > gpurun_out/exp24_pytest.log 2>&1; tail -4 gpurun_out/exp24_pytest.log
+timeout 900 python scripts/r02_quick.py cfg2nc --steps 6 > gpurun_out/exp24_cfg2.jsonl 2> gpurun_out/exp24_cfg2.err; cat gpurun_out/exp24_cfg2.jsonl; tail -3 gpurun_out/exp24_cfg2.err

@@ -155,6 +155,42 @@ def main():
             run(f"mat_exp_corr_{tag}", lambda: D.run_matrix("move_exp_nancorrmatrix", a, alpha=al), ob, [dict()], 3)
             del a
             torch.cuda.empty_cache()
+    if "cfg3x" in args:
+        n = 1_000_000_000
+        a = gen((1, n), torch.float64, 0.3)
+        for f in ("move_exp_nanmean", "move_exp_nanvar", "move_exp_nanstd"):
+            run("cfg3_" + f, lambda: D.run_move_exp(f, [a], 0.1, 0.0, -1)[0], n * 16, [{}], steps)
+        run("cfg3_move_exp_nanvar_gate", lambda: D.run_move_exp("move_exp_nanvar", [a], 0.1, 0.5, -1)[0], n * 16, [{}], steps)
+        del a
+        torch.cuda.empty_cache()
+        n = 500_000_000
+        a = gen((1, n), torch.float64, 0.3)
+        b = a * a + 1
+        for f in ("move_exp_nancov", "move_exp_nancorr"):
+            run("cfg3h_" + f, lambda: D.run_move_exp(f, [a, b], 0.1, 0.0, -1)[0], n * 24, [{}], steps)
+        del a, b
+        torch.cuda.empty_cache()
+    if "cfg5q" in args:
+        n, K = 2_000_000_000, 10_000_000
+        a = gen((n,), torch.float64, 0.1)
+        g = torch.Generator(device=dev).manual_seed(1)
+        labels = torch.randint(0, K, (n,), generator=g, device=dev, dtype=torch.int64)
+        ab = n * 16 + K * 8
+        v2 = a.view(1, -1)
+        for f in ("group_nansum", "group_nanmean", "group_nanvar", "group_nanargmax", "group_nanfirst", "group_nanmax"):
+            run("cfg5_" + f, lambda: D.run_group(f, v2, labels, K, 1), ab, [{}], max(3, steps // 2))
+        del a, labels, v2
+        torch.cuda.empty_cache()
+    if "cfg2nc" in args:
+        rows, n, K = 10_000, 1_000_000, 1000
+        a = gen((rows, n), torch.float32, 0.1)
+        labels = torch.from_numpy(np.random.RandomState(0).randint(0, K, size=n)).to(dev)
+        ab = rows * n * 4 + n * 8 + rows * K * 4
+        run("cfg2_group_nansum", lambda: D.run_group("group_nansum", a, labels, K, 1), ab, [dict(NBG_RB2_NC=1), dict(NBG_RB2_NC=2), dict(NBG_RB2_NC=4)], steps)
+        run("cfg2_group_nanmean", lambda: D.run_group("group_nanmean", a, labels, K, 1), ab, [dict(NBG_RB2_OFF=1), dict(NBG_RB2_NC=2), dict(NBG_RB2_NC=3), dict(NBG_RB2_NC=4)], steps)
+        run("cfg2_group_nanstd", lambda: D.run_group("group_nanstd", a, labels, K, 1), ab, [dict(NBG_RB2_OFF=1), dict(NBG_RB2_NC=3), dict(NBG_RB2_NC=4), dict(NBG_RB2_NC=6)], steps)
+        del a
+        torch.cuda.empty_cache()
     if "cfg1s" in args:
         rows, n = 2000, 100_000
         a = gen((rows, n), torch.float64, 0.1)
