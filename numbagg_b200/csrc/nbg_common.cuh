@@ -104,19 +104,26 @@ __device__ __forceinline__ bool rcp_ok(double b) {
     const double ab = fabs(b);
     return ab > 1e-280 && ab < 1e280;
 }
+// The IEEE division behind the rare cases, OUT OF LINE: written as `cond ? fast : a / b` the compiler
+// if-converts the select and evaluates the division's own inline fast path (MUFU.RCP64H + 7 FP64
+// instructions) next to ours for every element (seen in the SASS of the exp scans: two Newton chains
+// per quotient).
+static __device__ __noinline__ double ieee_div(double a, double b) { return a / b; }
 // a / b given y = fast_rcp(b)
 __device__ __forceinline__ double qdiv(double a, double b, double y) {
     const double q = a * y;
     const double qc = fma(fma(-b, q, a), y, q);
     // an infinite / NaN numerator (or an overflowing quotient) turns the residual into NaN: IEEE path
-    return fabs(qc) < __longlong_as_double(0x7ff0000000000000LL) ? qc : a / b;
+    if (fabs(qc) < __longlong_as_double(0x7ff0000000000000LL)) return qc;
+    return ieee_div(a, b);
 }
 __device__ __forceinline__ double fdiv(double a, double b) {
-    // straight-line fast path, ONE test, one IEEE fallback (two nested fallbacks cost registers in the scans)
+    // straight-line fast path, ONE test, one IEEE fallback
     const double y = fast_rcp(b);
     const double q = a * y;
     const double qc = fma(fma(-b, q, a), y, q);
-    return (rcp_ok(b) && fabs(qc) < __longlong_as_double(0x7ff0000000000000LL)) ? qc : a / b;
+    if (rcp_ok(b) && fabs(qc) < __longlong_as_double(0x7ff0000000000000LL)) return qc;
+    return ieee_div(a, b);
 }
 
 

@@ -130,7 +130,7 @@ struct ExpVar {  // moving_exp.py:106-224  channels: sum_x_2, sum_x, sum_weight,
         if (rcp_ok(s[2]) && rcp_ok(sw2) && fabs(m) + fabs(e) + fabs(t) < kExpInf) {
             if (!(bias > 0)) return quiet_nan<T>();
             v = qd(var_biased, bias, fast_rcp(bias));
-            if (!(rcp_ok(bias) && fabs(v) < kExpInf)) v = var_biased / bias;
+            if (!(rcp_ok(bias) && fabs(v) < kExpInf)) v = ieee_div(var_biased, bias);
         } else {
             v = exp_var_ieee(s[0], s[1], s[2], s[3]);
         }
@@ -161,7 +161,7 @@ struct ExpCov {  // moving_exp.py:227-273  channels: sum_x1, sum_x2, sum_x1x2, s
         if (rcp_ok(s[3]) && rcp_ok(sw2) && fabs(a) + fabs(cov_biased) + fabs(t) < kExpInf) {
             if (!(bias > 0)) return quiet_nan<T>();
             v = qd(cov_biased, bias, fast_rcp(bias));
-            if (!(rcp_ok(bias) && fabs(v) < kExpInf)) v = cov_biased / bias;
+            if (!(rcp_ok(bias) && fabs(v) < kExpInf)) v = ieee_div(cov_biased, bias);
         } else {
             v = exp_cov_ieee(s[0], s[1], s[2], s[3], s[4]);
         }
@@ -196,7 +196,7 @@ struct ExpCorr {  // moving_exp.py:276-335  + sum_x1_2, sum_x2_2  (the weight, w
             const double den = sqrt(dmul(var1, var2));
             if (!(den > 0)) return quiet_nan<T>();
             v = qd(cov, den, fast_rcp(den));
-            if (!(rcp_ok(den) && fabs(v) < kExpInf)) v = cov / den;
+            if (!(rcp_ok(den) && fabs(v) < kExpInf)) v = ieee_div(cov, den);
         } else {
             v = exp_corr_ieee(s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
         }
