@@ -96,6 +96,114 @@ __global__ void __launch_bounds__(kQThreads) quant_sort_kernel(const double *__r
     }
 }
 
+// ------------------------------------------------- rows of <= 1024 elements: one WARP per row
+// The row's keys live in registers (KPL per lane, blocked: element index = lane * KPL + r) and are
+// sorted by a bitonic network: exchanges at distance < KPL stay inside a lane (two compares + four
+// selects per pair), larger distances are one shuffle pair per key.  No shared memory, no barriers:
+// at n = 1000 the CTA-per-row kernels below spend their time in ~130 CTA-wide barriers per row (31 ms
+// on 10^6 x 1000); this one issues ~10 000 instructions per lane and row whatever the number of
+// quantiles and runs at the limit of the integer pipe (17.6 ms; ncu `gpurun_out/exp27_ncu_quant_short.txt`).
+// Only the exchanges inside a lane need compile-time register indices; the block loop (kk) and the
+// cross-lane distances (lj) are RUNTIME loops -- fully unrolled the network is 10 000 instructions
+// (160 KB of code) and the four warps of a scheduler, each somewhere else in it, stalled on
+// instruction fetch 70 % of the time (`no_instruction` 7.3 per issue, 31 ms).  Tried: sorting the
+// values as doubles with fmin / fmax (they are not single instructions here: 21 000 per row, 27.6 ms).
+// Loads are coalesced (the initial order of the keys is irrelevant to a sort).
+template <int KPL>
+__device__ __forceinline__ u64 key_at(const u64 (&k)[KPL], int r) {
+    u64 v = k[0];
+#pragma unroll
+    for (int i = 1; i < KPL; i++) v = r == i ? k[i] : v;
+    return v;
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(128) quant_warp_sort_kernel(const double *__restrict__ a, const double *__restrict__ q,
+                                                              double *__restrict__ out, i64 rows, i64 n, int m) {
+    constexpr int N = 32 * KPL;
+    const int lane = threadIdx.x & 31;
+    const i64 row = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;  // whole warps leave together
+    const double *p = a + row * n;
+    u64 k[KPL];
+    int valid = 0;
+#pragma unroll
+    for (int r = 0; r < KPL; r++) {
+        const int i = r * 32 + lane;
+        u64 key = ~0ull;
+        if (i < n) {
+            const double x = __ldcs(p + i);
+            key = quant_key(x);
+            valid += x == x ? 1 : 0;
+        }
+        k[r] = key;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, d);
+    // blocks shorter than a lane's share: direction and partners are register bits
+#pragma unroll
+    for (int kk = 2; kk < KPL; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < KPL; r++) {
+                if ((r & j) == 0) {
+                    const int r2 = r | j;
+                    const bool up = (r & kk) == 0;
+                    const u64 x = k[r], y = k[r2];
+                    const bool sw = (x > y) == up;
+                    k[r] = sw ? y : x;
+                    k[r2] = sw ? x : y;
+                }
+            }
+        }
+    }
+#pragma unroll 1
+    for (int kk = KPL; kk <= N; kk <<= 1) {
+        const bool up = ((lane * KPL) & kk) == 0;  // the block's direction is a lane bit from here on
+        // partner in lane ^ lj, same register; this lane keeps the smaller key iff it is the lower index of
+        // the pair in an ascending block (or the upper one in a descending block)
+#pragma unroll 1
+        for (int lj = kk / (2 * KPL); lj > 0; lj >>= 1) {
+            const bool keep_min = ((lane & lj) == 0) == up;
+#pragma unroll
+            for (int r = 0; r < KPL; r++) {
+                const u64 mine = k[r];
+                const u64 other = __shfl_xor_sync(0xffffffffu, mine, lj);
+                const bool take_other = keep_min ? (other < mine) : (other > mine);
+                k[r] = take_other ? other : mine;
+            }
+        }
+#pragma unroll
+        for (int j = KPL >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < KPL; r++) {
+                if ((r & j) == 0) {
+                    const int r2 = r | j;
+                    const u64 x = k[r], y = k[r2];
+                    const bool sw = (x > y) == up;
+                    k[r] = sw ? y : x;
+                    k[r2] = sw ? x : y;
+                }
+            }
+        }
+    }
+    for (int t = 0; t < m; t++) {
+        const double qq = q[t];
+        double res = quiet_nan<double>();
+        if (valid > 0 && qq == qq) {  // uniform across the warp
+            double rank;
+            i64 lo, hi;
+            quant_rank((i64)valid, qq, rank, lo, hi);
+            const u64 mine_lo = key_at<KPL>(k, (int)(lo % KPL)), mine_hi = key_at<KPL>(k, (int)(hi % KPL));
+            const u64 klo = __shfl_sync(0xffffffffu, mine_lo, (int)(lo / KPL));
+            const u64 khi = __shfl_sync(0xffffffffu, mine_hi, (int)(hi / KPL));
+            res = quant_interpolate(key_to_double(klo), key_to_double(khi), rank, lo);
+        }
+        if (lane == 0) out[row * m + t] = res;
+    }
+}
+
 // ------------------------------------------------- medium rows: radix select in shared memory
 // Same selection as the long-row path below, but the row's keys sit in shared memory, so the
 // eight passes cost no DRAM traffic: ~10 instructions per element and pass, against ~900 per
@@ -610,6 +718,22 @@ extern "C" int nbg_quantile(const void *a, const void *q, void *out, int64_t row
     if (rows > 0x7fffffff || n >= ((int64_t)1 << 31))
         return fail(NBG_ERR_BAD_ARG, "nbg_quantile: rows and n must be below 2^31 (the reference indexes with int32)");
     const double *ad = (const double *)a, *qd = (const double *)q;
+    if (n <= 1024 && !getenv("NBG_QUANT_NOWARP")) {
+        const unsigned blocks = (unsigned)((rows + 3) / 4);
+        if (n <= 32)
+            quant_warp_sort_kernel<1><<<blocks, 128, 0, stream>>>(ad, qd, (double *)out, rows, n, (int)m);
+        else if (n <= 64)
+            quant_warp_sort_kernel<2><<<blocks, 128, 0, stream>>>(ad, qd, (double *)out, rows, n, (int)m);
+        else if (n <= 128)
+            quant_warp_sort_kernel<4><<<blocks, 128, 0, stream>>>(ad, qd, (double *)out, rows, n, (int)m);
+        else if (n <= 256)
+            quant_warp_sort_kernel<8><<<blocks, 128, 0, stream>>>(ad, qd, (double *)out, rows, n, (int)m);
+        else if (n <= 512)
+            quant_warp_sort_kernel<16><<<blocks, 128, 0, stream>>>(ad, qd, (double *)out, rows, n, (int)m);
+        else
+            quant_warp_sort_kernel<32><<<blocks, 128, 0, stream>>>(ad, qd, (double *)out, rows, n, (int)m);
+        return check_launch("nbg_quantile warp sort");
+    }
     if (n <= kQSortMax && n > 512) {
         const size_t smem = (((size_t)n * 8 + 15) & ~(size_t)15) + (size_t)2 * m * 256 * sizeof(unsigned);
         int rc = allow_big_smem(quant_smem_select_kernel, "nbg_quantile: cudaFuncSetAttribute");
