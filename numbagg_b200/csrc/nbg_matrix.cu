@@ -131,6 +131,98 @@ __global__ void __launch_bounds__(kMatThreads) mat_move_kernel(const T *__restri
     }
 }
 
+// ---- static forms, long observation axes: partial sums per segment, folded in order ------------------
+// Thread per (batch item, segment, pair with j >= i): the reference's accumulation over the segment's
+// observations, in the reference's types; a second kernel folds the segments' partial sums left to
+// right (still in the input dtype) and applies the reference's read-out.  Like every segmented form
+// here this agrees with the reference to the rounding of its running sums; axes < 8192 keep the
+// single-pass kernel (bit-identical).  part: [batch][nseg][6][npairs] doubles (float sums are exact there).
+__device__ __forceinline__ void tri_pair_static(int k, int nv, int &i, int &j) {
+    int row = 0, rem = k;
+    while (rem >= nv - row) {
+        rem -= nv - row;
+        row++;
+    }
+    i = row;
+    j = row + rem;
+}
+
+template <typename T, bool CORR>
+__global__ void __launch_bounds__(256) mat_static_part_kernel(const T *__restrict__ a, double *__restrict__ part, i64 batch,
+                                                              int nv, i64 no, i64 seg_len, int nseg, int blocks_per_seg) {
+    const i64 np = (i64)nv * (nv + 1) / 2;
+    const int pb = blockIdx.x % blocks_per_seg;
+    const i64 sb = blockIdx.x / blocks_per_seg;
+    const int seg = (int)(sb % nseg);
+    const i64 bi = sb / nseg;
+    const int k = pb * 256 + threadIdx.x;
+    if (k >= np || bi >= batch) return;
+    int i, j;
+    tri_pair_static(k, nv, i, j);
+    const i64 k0 = (i64)seg * seg_len, k1 = k0 + seg_len < no ? k0 + seg_len : no;
+    const T *ri = a + (bi * nv + i) * no, *rj = a + (bi * nv + j) * no;
+    T si = 0, sj = 0, sqi = 0, sqj = 0, sij = 0;
+    i64 count = 0;
+    for (i64 t = k0; t < k1; t++) {
+        const T vi = ri[t], vj = rj[t];
+        if (is_nan(vi) || is_nan(vj)) continue;
+        si += vi;
+        sj += vj;
+        if (CORR) {
+            sqi += mul_t(vi, vi);
+            sqj += mul_t(vj, vj);
+        }
+        sij += mul_t(vi, vj);
+        count += 1;
+    }
+    double *o = part + ((bi * nseg + seg) * 6) * np + k;
+    o[0 * np] = (double)si, o[1 * np] = (double)sj, o[2 * np] = (double)sqi, o[3 * np] = (double)sqj;
+    o[4 * np] = (double)sij, o[5 * np] = (double)count;
+}
+
+template <typename T, bool CORR>
+__global__ void __launch_bounds__(256) mat_static_fold_kernel(const double *__restrict__ part, T *__restrict__ out, i64 batch,
+                                                              int nv, int nseg) {
+    const i64 np = (i64)nv * (nv + 1) / 2;
+    const i64 gid = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (gid >= batch * np) return;
+    const i64 bi = gid / np;
+    const int k = (int)(gid % np);
+    int i, j;
+    tri_pair_static(k, nv, i, j);
+    T si = 0, sj = 0, sqi = 0, sqj = 0, sij = 0;
+    i64 count = 0;
+    for (int seg = 0; seg < nseg; seg++) {
+        const double *o = part + ((bi * nseg + seg) * 6) * np + k;
+        si += (T)o[0 * np];
+        sj += (T)o[1 * np];
+        if (CORR) {
+            sqi += (T)o[2 * np];
+            sqj += (T)o[3 * np];
+        }
+        sij += (T)o[4 * np];
+        count += (i64)o[5 * np];
+    }
+    T res = quiet_nan<T>();
+    if (count > 1) {  // funcs.py:423-474 / 503-532, as in mat_static_kernel
+        const double c = (double)count, c1 = (double)(count - 1);
+        const double mi = (double)si / c, mj = (double)sj / c;
+        const double cov = dsub((double)sij / c, dmul(mi, mj));
+        const double cov_u = dmul(cov, c) / c1;
+        if (CORR) {
+            const double vi = dsub((double)sqi / c, dmul(mi, mi));
+            const double vj = dsub((double)sqj / c, dmul(mj, mj));
+            const double vi_u = dmul(vi, c) / c1, vj_u = dmul(vj, c) / c1;
+            if (vi_u > 0 && vj_u > 0) res = (T)(cov_u / sqrt(dmul(vi_u, vj_u)));
+        } else {
+            res = (T)cov_u;
+        }
+    }
+    const i64 q = (i64)nv * nv;
+    out[bi * q + (i64)i * nv + j] = res;
+    out[bi * q + (i64)j * nv + i] = res;
+}
+
 // ---- long observation axes: segments -------------------------------------------------------------
 // One thread per (batch item, segment, i, j).  A segment rebuilds the state of its pair from the
 // `window` observations before it (additions only, in order) and then runs the reference's
@@ -604,8 +696,43 @@ int launch_matrix(int op, const void *a_, const void *alpha_, int alpha_per_item
     if ((threads + kMatThreads - 1) / kMatThreads > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_matrix: too many pairs");
     const unsigned grid = (unsigned)((threads + kMatThreads - 1) / kMatThreads);
     switch (op) {
-        case NBG_MAT_NANCORR: mat_static_kernel<T, true><<<grid, kMatThreads, 0, stream>>>(a, out, batch, (int)nv, no); break;
-        case NBG_MAT_NANCOV: mat_static_kernel<T, false><<<grid, kMatThreads, 0, stream>>>(a, out, batch, (int)nv, no); break;
+        case NBG_MAT_NANCORR:
+        case NBG_MAT_NANCOV: {
+            const bool corr = op == NBG_MAT_NANCORR;
+            const i64 np = nv * (nv + 1) / 2;
+            const int bps = (int)((np + 255) / 256);
+            const i64 resident = corr ? resident_ctas(mat_static_part_kernel<T, true>, 256, 0)
+                                      : resident_ctas(mat_static_part_kernel<T, false>, 256, 0);
+            const MatSegs sg = mat_segments(batch * bps, resident, no, 128);
+            if (sg.nseg > 1) {
+                const i64 blocks = batch * sg.nseg * bps;
+                if (blocks > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_matrix: too many segments");
+                void *ws = nullptr;
+                keep_pool_memory();
+                int rc = check_cuda(cudaMallocAsync(&ws, (size_t)batch * sg.nseg * 6 * np * sizeof(double), stream), "nbg_matrix: workspace");
+                if (rc) return rc;
+                if (corr)
+                    mat_static_part_kernel<T, true><<<(unsigned)blocks, 256, 0, stream>>>(a, (double *)ws, batch, (int)nv, no, sg.seg_len, sg.nseg, bps);
+                else
+                    mat_static_part_kernel<T, false><<<(unsigned)blocks, 256, 0, stream>>>(a, (double *)ws, batch, (int)nv, no, sg.seg_len, sg.nseg, bps);
+                rc = check_launch("nbg_matrix(static, partial sums)");
+                if (!rc) {
+                    const unsigned fb = (unsigned)((batch * np + 255) / 256);
+                    if (corr)
+                        mat_static_fold_kernel<T, true><<<fb, 256, 0, stream>>>((const double *)ws, out, batch, (int)nv, sg.nseg);
+                    else
+                        mat_static_fold_kernel<T, false><<<fb, 256, 0, stream>>>((const double *)ws, out, batch, (int)nv, sg.nseg);
+                    rc = check_launch("nbg_matrix(static, fold)");
+                }
+                cudaFreeAsync(ws, stream);
+                return rc;
+            }
+            if (corr)
+                mat_static_kernel<T, true><<<grid, kMatThreads, 0, stream>>>(a, out, batch, (int)nv, no);
+            else
+                mat_static_kernel<T, false><<<grid, kMatThreads, 0, stream>>>(a, out, batch, (int)nv, no);
+            break;
+        }
         case NBG_MAT_MOVE_CORR:
         case NBG_MAT_MOVE_COV: {
             const bool corr = op == NBG_MAT_MOVE_CORR;

@@ -153,6 +153,10 @@ def main():
             run(f"mat_move_corr_{tag}", lambda: D.run_matrix("move_corrmatrix", a, window=100, min_count=10), ob, [dict()], 3)
             run(f"mat_exp_cov_{tag}", lambda: D.run_matrix("move_exp_nancovmatrix", a, alpha=al), ob, sw, 3)
             run(f"mat_exp_corr_{tag}", lambda: D.run_matrix("move_exp_nancorrmatrix", a, alpha=al), ob, [dict()], 3)
+            at = a.T.contiguous()
+            run(f"mat_static_cov_{tag}", lambda: D.run_matrix("nancovmatrix", at), no * nv * a.element_size(), sw, 3)
+            run(f"mat_static_corr_{tag}", lambda: D.run_matrix("nancorrmatrix", at), no * nv * a.element_size(), [dict()], 3)
+            del at
             del a
             torch.cuda.empty_cache()
     if "cfg3x" in args:

@@ -86,6 +86,15 @@ def test_long_observation_axis_segments(dtype):
             assert np.array_equal(np.isnan(got), np.isnan(exp)), f"{func}: NaN masks differ"
             _record(func + "(segments)", got, exp, 0.0, atol)
             np.testing.assert_allclose(got, exp, rtol=0, atol=atol, equal_nan=True)
+    # static forms: partial sums per segment of the observation axis, folded in order
+    vo = np.ascontiguousarray(np.swapaxes(ov, -1, -2))  # (batch, vars, obs)
+    for func in ("nancovmatrix", "nancorrmatrix"):
+        got = getattr(nb, func)(vo)
+        exp = getattr(oracle, func)(vo)
+        assert got.dtype == exp.dtype and got.shape == exp.shape
+        assert np.array_equal(np.isnan(got), np.isnan(exp)), f"{func}: NaN masks differ"
+        _record(func + "(segments)", got, exp, 0.0, atol)
+        np.testing.assert_allclose(got, exp, rtol=0, atol=atol, equal_nan=True)
     # the first segment runs the reference's recurrence from the start: bit-identical there
     got = nb.move_covmatrix(ov, window=64, min_count=8)
     same(got[:, :256], oracle.move_covmatrix(ov, window=64, min_count=8)[:, :256])
