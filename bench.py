@@ -133,6 +133,7 @@ WORKLOADS.update({
     "quant_quartiles_short": ("quantile", "nanquantile", "f64", 1_000_000, 1000, dict(quantiles=[0.25, 0.5, 0.75], axis=-1)),
     # matrix functions, (obs, vars) -> (obs, vars, vars); write-bound by construction
     "mat_move_cov": ("matrix", "move_covmatrix", "f64", 200_000, 32, dict(window=100, min_count=10)),
+    "mat_move_corr": ("matrix", "move_corrmatrix", "f64", 200_000, 32, dict(window=100, min_count=10)),
 })
 DEFAULT_WORKLOAD = "cfg2_group_nansum"
 TWO_INPUT = {"move_cov", "move_corr", "move_exp_nancov", "move_exp_nancorr"}

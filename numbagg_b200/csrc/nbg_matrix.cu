@@ -249,10 +249,10 @@ __device__ __forceinline__ void tri_pair(int k, int nv, int &i, int &j) {
 }
 
 // (tried: prefetch.global.L1 of the rows 8 steps ahead -- slower, 1.10 vs 0.81 ms on 200 000 x 32 float64)
-template <typename T, bool CORR, bool TABLE>
+template <typename T, bool CORR, bool TABLE, bool STAGE>
 __global__ void __launch_bounds__(kMatSegThreads) mat_move_seg_kernel(const T *__restrict__ a, T *__restrict__ out, i64 batch,
                                                                       i64 no, int nv, i64 window, i64 min_count, i64 seg_len,
-                                                                      int nseg, int blocks_per_seg) {
+                                                                      int nseg, int blocks_per_seg, int OB) {
     extern __shared__ double rc_tab[];  // rc_tab[c] = 1 / c
     if (TABLE) {
         for (int c = threadIdx.x; c <= (int)window; c += kMatSegThreads) rc_tab[c] = c ? 1.0 / (double)c : 0.0;
@@ -264,8 +264,10 @@ __global__ void __launch_bounds__(kMatSegThreads) mat_move_seg_kernel(const T *_
     const i64 sb = blockIdx.x / blocks_per_seg;
     const int seg = (int)(sb % nseg);
     const i64 bi = sb / nseg;
-    const int k = pb * kMatSegThreads + threadIdx.x;
-    if (k >= npairs || bi >= batch) return;
+    const int k0 = pb * kMatSegThreads + threadIdx.x;
+    const bool active = k0 < npairs;  // (bi < batch by construction of the grid)
+    if (!STAGE && !active) return;
+    const int k = active ? k0 : 0;    // idle threads of the staged form still load and synchronise
     int i, j;
     tri_pair(k, nv, i, j);
     const T *ab = a + bi * no * nv;
@@ -292,21 +294,10 @@ __global__ void __launch_bounds__(kMatSegThreads) mat_move_seg_kernel(const T *_
         }
     }
     const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-    const T *lead = ab + t0 * nv, *trail = ab + (t0 - window) * nv;  // trail is only dereferenced once t >= window
-    T *o = ob + t0 * q;
-    // the observations of step t + 1 are fetched while step t computes (the loads feed a NaN test at the
-    // top of a long dependent chain: without this the kernel sits in long_scoreboard half of the time)
-    const T kNaN = quiet_nan<T>();
-    T n_li = t0 < t1 ? lead[i] : kNaN, n_lj = t0 < t1 ? lead[j] : kNaN;
-    T n_ti = t0 >= window && t0 < t1 ? trail[i] : kNaN, n_tj = t0 >= window && t0 < t1 ? trail[j] : kNaN;
-    for (i64 t = t0; t < t1; t++, lead += nv, trail += nv, o += q) {
-        const T li = n_li, lj = n_lj, ti = n_ti, tj = n_tj;
-        if (t + 1 < t1) {
-            n_li = lead[nv + i], n_lj = lead[nv + j];
-            if (t + 1 >= window) n_ti = trail[nv + i], n_tj = trail[nv + j];
-        }
+    // one step of the reference's loop body: leaving pair (NaN before the window is full), entering
+    // pair, read-out, both stores
+    auto do_step = [&](T ti, T tj, T li, T lj, T *o) {
         {
-            // a step before the window is full has nothing leaving: ti / tj are NaN there
             const T vi = ti, vj = tj;
             if (!(is_nan(vi) || is_nan(vj))) {
                 si -= vi;
@@ -388,6 +379,74 @@ __global__ void __launch_bounds__(kMatSegThreads) mat_move_seg_kernel(const T *_
         }
         __stcs(o + oij, res);
         if (i != j) __stcs(o + oji, res);
+    };
+    const T kNaN = quiet_nan<T>();
+    T *o = ob + t0 * q;
+    if constexpr (STAGE) {
+        // The observation rows of a chunk of OB steps -- entering rows [tc, tc + OB) and leaving rows
+        // [tc - window, ...) -- are staged in shared memory by the whole CTA (all of its threads work on
+        // the same segment), double-buffered: the next chunk travels global -> registers while this one
+        // is consumed, registers -> shared memory at its end.  Without it every step starts with two
+        // L2 round trips (half of the stall samples of the unstaged form).
+        T *stg = reinterpret_cast<T *>(rc_tab + (TABLE ? (((int)window + 2) & ~1) : 0));
+        const int ce = OB * nv;  // elements per buffer and stream, <= 4 * kMatSegThreads
+        const i64 total = no * nv;
+        auto fetch = [&](i64 tc, int which, int e) -> T {
+            const i64 g = (which ? tc - window : tc) * nv + e;
+            return (g >= 0 && g < total) ? ab[g] : kNaN;
+        };
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = threadIdx.x + u * kMatSegThreads;
+            if (e < ce) {
+                stg[e] = fetch(t0, 0, e);
+                stg[ce + e] = fetch(t0, 1, e);
+            }
+        }
+        __syncthreads();
+        int b = 0;
+        for (i64 tc = t0; tc < t1; tc += OB, b ^= 1) {
+            T pl[4], pt[4];
+            const bool more = tc + OB < t1;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = threadIdx.x + u * kMatSegThreads;
+                    pl[u] = e < ce ? fetch(tc + OB, 0, e) : kNaN;
+                    pt[u] = e < ce ? fetch(tc + OB, 1, e) : kNaN;
+                }
+            }
+            if (active) {
+                const T *L = stg + (size_t)(2 * b) * ce, *R = L + ce;
+                const int ns = (int)(t1 - tc < OB ? t1 - tc : OB);
+                for (int st = 0; st < ns; st++, o += q) do_step(R[st * nv + i], R[st * nv + j], L[st * nv + i], L[st * nv + j], o);
+            }
+            if (more) {
+                T *W = stg + (size_t)(2 * (b ^ 1)) * ce;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = threadIdx.x + u * kMatSegThreads;
+                    if (e < ce) {
+                        W[e] = pl[u];
+                        W[ce + e] = pt[u];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        const T *lead = ab + t0 * nv, *trail = ab + (t0 - window) * nv;  // trail is only dereferenced once t >= window
+        // the observations of step t + 1 are fetched while step t computes
+        T n_li = t0 < t1 ? lead[i] : kNaN, n_lj = t0 < t1 ? lead[j] : kNaN;
+        T n_ti = t0 >= window && t0 < t1 ? trail[i] : kNaN, n_tj = t0 >= window && t0 < t1 ? trail[j] : kNaN;
+        for (i64 t = t0; t < t1; t++, lead += nv, trail += nv, o += q) {
+            const T li = n_li, lj = n_lj, ti = n_ti, tj = n_tj;
+            if (t + 1 < t1) {
+                n_li = lead[nv + i], n_lj = lead[nv + j];
+                if (t + 1 >= window) n_ti = trail[nv + i], n_tj = trail[nv + j];
+            }
+            do_step(ti, tj, li, lj, o);
+        }
     }
 }
 
@@ -739,24 +798,47 @@ int launch_matrix(int op, const void *a_, const void *alpha_, int alpha_per_item
             const i64 np = nv * (nv + 1) / 2;
             const int bps = (int)((np + kMatSegThreads - 1) / kMatSegThreads);
             const bool table = window <= kMatRcpMax;
-            const size_t smem = table ? (size_t)(window + 1) * sizeof(double) : 0;
-            const i64 resident = corr ? (table ? resident_ctas(mat_move_seg_kernel<T, true, true>, kMatSegThreads, smem)
-                                               : resident_ctas(mat_move_seg_kernel<T, true, false>, kMatSegThreads, smem))
-                                      : (table ? resident_ctas(mat_move_seg_kernel<T, false, true>, kMatSegThreads, smem)
-                                               : resident_ctas(mat_move_seg_kernel<T, false, false>, kMatSegThreads, smem));
+            // staged operands (NBG_MAT_STAGE=1, experiment): OB steps x nv variables per buffer, at most 1024
+            // elements (4 per thread).  Measured SLOWER than the register prefetch of the unstaged form
+            // (200 000 x 32 float64: 1.39 vs 0.81 ms): the chunk barrier makes every warp wait for the
+            // slowest one and each step now starts with an exposed shared-memory round trip.
+            int OB = (int)(1024 / nv);
+            if (OB > 32) OB = 32;
+            const bool stage = OB >= 8 && getenv("NBG_MAT_STAGE") != nullptr;
+            const size_t tab_bytes = table ? (size_t)(((int)window + 2) & ~1) * sizeof(double) : 0;
+            const size_t smem = tab_bytes + (stage ? (size_t)4 * OB * nv * sizeof(T) : 0);
+            i64 resident = kNumSMs;
+#define NBG_MAT_RES(C_, T_, S_)                                                                              \
+    do {                                                                                                     \
+        auto kern_ = mat_move_seg_kernel<T, C_, T_, S_>;                                                     \
+        if (smem > ((size_t)48 << 10)) {                                                                     \
+            const int rc_ = allow_big_smem(kern_, "nbg_matrix(move segments): cudaFuncSetAttribute");       \
+            if (rc_) return rc_;                                                                             \
+        }                                                                                                    \
+        resident = resident_ctas(kern_, kMatSegThreads, smem);                                               \
+    } while (0)
+#define NBG_MAT_PICK(MAC)                                                   \
+    do {                                                                    \
+        if (corr) {                                                         \
+            if (table) { if (stage) MAC(true, true, true); else MAC(true, true, false); }     \
+            else { if (stage) MAC(true, false, true); else MAC(true, false, false); }         \
+        } else {                                                            \
+            if (table) { if (stage) MAC(false, true, true); else MAC(false, true, false); }   \
+            else { if (stage) MAC(false, false, true); else MAC(false, false, false); }       \
+        }                                                                   \
+    } while (0)
+            NBG_MAT_PICK(NBG_MAT_RES);
             const MatSegs sg = mat_segments(batch * bps, resident, no, window);
             if (sg.nseg > 1) {
                 const i64 blocks = batch * sg.nseg * bps;
                 if (blocks > 0x7fffffff) return fail(NBG_ERR_BAD_ARG, "nbg_matrix: too many segments");
-#define NBG_MAT_SEG(C_, T_)                                                                                            \
-    mat_move_seg_kernel<T, C_, T_><<<(unsigned)blocks, kMatSegThreads, smem, stream>>>(a, out, batch, no, (int)nv, window, \
-                                                                                        min_count, sg.seg_len, sg.nseg, bps)
-                if (corr) {
-                    if (table) NBG_MAT_SEG(true, true); else NBG_MAT_SEG(true, false);
-                } else {
-                    if (table) NBG_MAT_SEG(false, true); else NBG_MAT_SEG(false, false);
-                }
+#define NBG_MAT_SEG(C_, T_, S_)                                                                                              \
+    mat_move_seg_kernel<T, C_, T_, S_><<<(unsigned)blocks, kMatSegThreads, smem, stream>>>(a, out, batch, no, (int)nv, window, \
+                                                                                            min_count, sg.seg_len, sg.nseg, bps, OB)
+                NBG_MAT_PICK(NBG_MAT_SEG);
 #undef NBG_MAT_SEG
+#undef NBG_MAT_RES
+#undef NBG_MAT_PICK
             } else if (corr) {
                 mat_move_kernel<T, true><<<grid, kMatThreads, 0, stream>>>(a, out, batch, no, (int)nv, window, min_count);
             } else {

@@ -1,44 +1,72 @@
-"""profiles/README.md from a bench_all.jsonl (scripts/run_all_benches.sh).  usage: make_profiles_readme.py <jsonl> <tag>"""
-import json, sys
-path, tag = sys.argv[1], sys.argv[2]
-rows = []
+"""profiles/README.md from profiles/r02_bench_all.jsonl (scripts/r02_profiles.sh) and round 1's table.
+usage: python scripts/make_profiles_readme.py"""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+
+
+def load(name):
+    rows = {}
+    try:
+        for line in open(os.path.join(P, name)):
+            try:
+                d = json.loads(line)
+            except Exception:
+                continue
+            if "config" in d:
+                rows[d["config"]["workload"]] = d
+    except FileNotFoundError:
+        pass
+    return rows
 
 
 def fmt(x):
     return f"{x:.1f}" if x >= 10 else f"{x:.3g}"
 
 
-for line in open(path):
-    try:
-        d = json.loads(line)
-    except Exception:
-        continue
-    if "config" in d:
-        rows.append(d)
-out = [f"# profiles — round {tag}", "",
-       "All numbers from one B200 (`gpurun`), device-resident inputs, CUDA events, >= 3 warm-up steps,",
-       "inputs larger than L2 (except cfg1).  `roofline` = algorithmic bytes / step time / measured copy",
-       "bandwidth (6447.8 GB/s, MEASURED_PEAKS.json).  `e2e` = public numpy API with pinned host buffers",
-       "(H2D + kernels + D2H inside the timed region; row blocks are pipelined on three streams).",
-       "`cpu` = oracle port (C, OpenMP over rows) on the box's 16 host cores; 1-D inputs use one core,",
-       "like the reference's gufunc.  The `red_*` rows (plain NaN reductions, SURVEY 8(f) rank 1) only READ",
-       "(8 bytes written per output), so they can exceed the measured COPY bandwidth used as `peak` (half",
-       "reads, half writes): `roofline` above 1.0 means faster than a device-to-device copy moves the same",
-       "bytes; ncu shows ~90 % of the DRAM peak for `nansum` float32.  The `quant_*` rows (nanquantile,",
-       "SURVEY 8(f) rank 3) are selection: 8 reads of the data by construction, `roofline` counts one.",
-       "cfg1 is launch-bound: its K steps are replayed from one CUDA graph (`config.launch`).  `mat_*` (matrix",
-       "functions, SURVEY 8(f) rank 2) is the first, bit-exact but sequential-per-pair kernel: 1024 threads.", "",
-       "| workload | shape | Gel/s | ms/step | roofline (of measured) | e2e Gel/s | cpu Gel/s (cores) | kernels/step |",
-       "|---|---|---:|---:|---:|---:|---:|---:|"]
-for d in rows:
+r1, r2 = load("r01_bench_all.jsonl"), load("r02_bench_all.jsonl")
+try:
+    traffic = json.load(open(os.path.join(P, "r02_traffic.json")))
+except Exception:
+    traffic = {}
+out = ["# profiles — round 2", "",
+       "All numbers from one B200 (`gpurun`), device-resident inputs, CUDA events on the launching stream, >= 3",
+       "warm-up steps, inputs larger than L2 (except cfg1).  `roofline` = algorithmic bytes / step time / measured copy",
+       "bandwidth (6447.8 GB/s, MEASURED_PEAKS.json); 0.87 of it = north_star's 70 % of 8 TB/s.  `r01` = the same",
+       "column one round ago.  `traffic` = ncu DRAM bytes of the dominant kernel / algorithmic bytes (this round's",
+       "`--set full` captures, `r02_traffic.json`).  `e2e` = public numpy API with pinned host buffers (H2D + kernels +",
+       "D2H inside the timed region; PCIe-bound by construction).  `cpu` = numbagg's own Numba path (`kind:",
+       "reference`, oracle/_ref) on the box's host cores, 1-D inputs on one core like the reference's gufunc.  `parity`",
+       "= the run's own output spot-checked against the oracle at full size.  The `red_*` rows only READ, so they can",
+       "exceed the COPY bandwidth used as `peak`.  cfg1 is launch-bound (K steps replayed from one CUDA graph).", "",
+       "| workload | shape | Gel/s | ms/step | roofline | r01 | traffic | e2e Gel/s | cpu Gel/s (kind, cores) | parity |",
+       "|---|---|---:|---:|---:|---:|---:|---:|---:|---|"]
+for wl, d in r2.items():
     c = d["config"]
-    out.append(f"| {c['workload']} ({c['func']}, {d['dtype']}) | {c['shape'][0]}x{c['shape'][1]}{' axis=' + str(c['axis']) if 'axis' in c else ''} | {fmt(d['value']/1e9)} | {d['ms_per_step']:.3f} | "
-               f"{d['roofline']['frac']:.3g} | {fmt(d['e2e']['value']/1e9)} | {fmt(d['cpu_baseline']['value']/1e9)} ({d['cpu_baseline']['cores']}) | {d['gpu_launches']/d['steps']:.0f} |")
-out += ["", "Files:", "",
-        "* `*_bench_all*.jsonl` — the raw bench.py JSON lines behind the table.",
-        "* `*_launches_default_bench*.csv` — ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`) of the default bench command; the row-bins kernel is ~99 % of each step.",
-        "* `*_ncu_*.txt` — per-kernel summaries of `ncu --set full` captures (scripts/ncu_summary.py): duration, DRAM bytes (= algorithmic bytes: no re-reads), pipe utilisation, stall reasons, top stalled SASS instructions.",
-        "* `*_launches_quant_median_long.csv` — ncu launch list of one `nanquantile` call on 2000 x 10^6 float64 (radix select: 8 x histogram + select + clear, then finish), captured before the compact target list: about 6 ms per histogram pass then, about 4 ms now.",
-        ""]
-open("profiles/README.md", "w").write("\n".join(out))
-print("\n".join(out[:40]))
+    e = (d.get("e2e") or {}).get("value")
+    cb = d.get("cpu_baseline") or {}
+    par = d.get("parity") or {}
+    ok = all(v.get("ok", False) for v in par.values() if isinstance(v, dict)) if par else None
+    tr = traffic.get(wl, {}).get("dram_bytes_per_launch")
+    alg = d["roofline"]["achieved"] * 1e9 * d["ms_per_step"] / 1e3
+    old = r1.get(wl, {}).get("roofline", {}).get("frac")
+    out.append(f"| {wl} ({c['func']}, {d['dtype']}) | {c['shape'][0]}x{c['shape'][1]}{' axis=' + str(c['axis']) if 'axis' in c else ''} | "
+               f"{fmt(d['value'] / 1e9)} | {d['ms_per_step']:.3f} | {d['roofline']['frac']:.3g} | {'' if old is None else format(old, '.3g')} | "
+               f"{'' if not tr else format(tr / alg, '.2f')} | {'' if not e else fmt(e / 1e9)} | "
+               f"{'' if not cb else fmt(cb['value'] / 1e9) + ' (' + str(cb.get('kind')) + ', ' + str(cb.get('cores')) + ')'} | "
+               f"{'' if ok is None else ('ok' if ok else 'FAIL')} |")
+out += ["", "Multi-GPU (strong scaling of the fixed configs + sharded forms over NCCL with in-run parity): DESIGN.md §5,",
+        "`r02_bench_n2.json`, `r02_bench_n4.json`, `r02_bench_n8*.json`.", "", "Files:", "",
+        "* `r02_bench_all.jsonl` — the raw bench.py JSON lines behind the table (`scripts/r02_profiles.sh`).",
+        "* `r02_launches_default_bench*.csv` — ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`) of the default bench command: the row-bins kernel is 98 % of a step, plan / histogram / init / finalize the rest.",
+        "* `r02_ncu_*.txt` — per-kernel summaries of `ncu --set full` captures (scripts/ncu_summary.py): duration, DRAM bytes, pipe utilisation, stall reasons, top stalled SASS instructions; `r02_traffic.json` is derived from them (scripts/collect_r02_profiles.py).",
+        "* `r02_sass_summary.txt` — `cuobjdump -sass` census per kernel family (UBLKCP / UBLKPF = TMA bulk copy / L2 prefetch, SYNCS = mbarrier, RED / ATOMG / ATOMS, F2F, MUFU, DADD / DMUL / DFMA, ...; scripts/sass_summary.py).  No UTMALDG / UTCHMMA: 1-D row tiles, no contraction anywhere on this path.",
+        "* `r02_parity_observed.json` — worst observed error per (function, dtype) over everything the GPU test session compared in the tolerance class, next to the bound.",
+        "* `r02_prefetch_sweep.jsonl` — L2 prefetch distance sweep of the one-tile-per-CTA kernels.",
+        "* `r02_launches_quant_median_long.csv` — launch list of one long-row `nanquantile` call (two histogram passes, compaction, candidate sort; the skipped tail passes take 4 µs each).",
+        "* `r02_pytest_gpu.log` — the `-m gpu` suite on the box.",
+        "* `r01_*` — round 1's evidence, kept for comparison.", ""]
+open(os.path.join(P, "README.md"), "w").write("\n".join(out))
+print("\n".join(out[:60]))

@@ -13,10 +13,11 @@ for w in cfg2_group_nansum cfg2_group_nanmean cfg2_group_nanstd cfg2_group_nanco
          cfg3_move_exp_nanmean cfg3_move_exp_nansum cfg3_move_exp_nancount cfg3_move_exp_nanvar cfg3_move_exp_nanstd cfg3_move_exp_nancov cfg3_move_exp_nancorr cfg3_move_exp_nanmean_f32 cfg3_ffill cfg3_bfill \
          cfg4_move_std cfg4_move_var cfg4_move_mean cfg4_move_cov cfg4_move_corr \
          cfg5_group_nansum1d cfg5_group_nanmean cfg5_group_nanargmax cfg5_group_nanfirst cfg5_group_nanvar; do
+  if [ -n "$NBG_SKIP_BENCH" ]; then break; fi
   steps=10; [ $w = cfg1_move_mean ] && steps=200
   timeout 600 python bench.py --workload $w --steps $steps --warmup 3 2>gpurun_out/r02_bench_err_$w.log | tail -1 >> gpurun_out/r02_bench_all.jsonl
 done
-for w in red_nansum_f32 red_nanmean_f32 red_nanvar_f32 red_nanmax_f32 red_nanargmax_f32 red_nansum_f64 red_nanstd_f64 red_nansum_f32_axis0 red_nanvar_f64_axis0 red_nanmean_f32_short red_nansum_f64_all quant_median_long quant_quartiles_short mat_move_cov; do
+for w in red_nansum_f32 red_nanmean_f32 red_nanvar_f32 red_nanmax_f32 red_nanargmax_f32 red_nansum_f64 red_nanstd_f64 red_nansum_f32_axis0 red_nanvar_f64_axis0 red_nanmean_f32_short red_nansum_f64_all quant_median_long quant_quartiles_short mat_move_cov mat_move_corr; do
   timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --no-e2e --no-cpu --no-parity 2>gpurun_out/r02_bench_err_$w.log | tail -1 >> gpurun_out/r02_bench_all.jsonl
 done
 python - <<'PY'
@@ -29,18 +30,19 @@ for line in open("gpurun_out/r02_bench_all.jsonl"):
     ok = all(v.get("ok", False) for v in par.values() if isinstance(v, dict)) if par else None
     print(f"{d['config']['workload']:28s} {d['value']/1e9:9.1f} Gel/s {d['ms_per_step']:9.3f} ms  roofline {d['roofline']['frac']:.3f}  e2e {e/1e9:7.2f}  cpu {c/1e9:6.2f}  parity {ok}")
 PY
-# ---- launch list of the default bench command (shares, not absolutes)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_default_bench_raw.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-parity > gpurun_out/r02_bench_under_ncu.log 2>&1
+# ---- launch list of the default bench command (shares, not absolutes): our kernels only (the first
+# 400 launches of the process are torch's input generators)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"nbg|group_|scan_|move_|red_" -c 200 --csv --log-file gpurun_out/r02_launches_default_bench_raw.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-parity > gpurun_out/r02_bench_under_ncu.log 2>&1
 python scripts/summarise_launches.py gpurun_out/r02_launches_default_bench_raw.csv gpurun_out/r02_launches_default_bench.csv; cat gpurun_out/r02_launches_default_bench.csv
-# ---- one `ncu --set full` capture per dominant kernel
+# ---- one `ncu --set full` capture per dominant kernel (NBG_NCU_ONLY="a b c" restricts the list)
 for spec in "cfg2_group_nansum group_rowbins2" "cfg2_group_nanmean group_rowbins_kernel" "cfg2_group_nanstd group_rowbins_kernel" "cfg2_group_nanargmax group_rowbins_kernel" \
             "cfg3_ffill scan_rowtile" "cfg3_move_exp_nanmean scan_rowtile" "cfg3_move_exp_nanvar scan_rowtile" "cfg3_move_exp_nancorr scan_rowtile" "cfg3_move_exp_nanmean_f32 scan_rowtile" \
             "cfg1s_move_mean move_rowtile" "cfg4_move_std move_prefix" "cfg4_move_cov move_prefix" "cfg4_move_corr move_rowtile" "cfg4_move_var move_rowtile" \
-            "cfg5_group_nansum1d group_atomic" "cfg5_group_nanvar group_atomic" "cfg5_group_nanargmax group_atomic" "cfg5_group_nanfirst group_atomic"; do
+            "cfg5_group_nansum1d group_atomic" "cfg5_group_nanvar group_atomic" "cfg5_group_nanargmax group_atomic" "cfg5_group_nanfirst group_atomic" \
+            "quant_median_long quant_hist" "quant_quartiles_short quant_warp_sort" "mat_move_cov mat_move_seg"; do
   set -- $spec
+  if [ -n "$NBG_NCU_ONLY" ] && ! echo " $NBG_NCU_ONLY " | grep -q " $1 "; then continue; fi
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s 2 -c 1 -o /tmp/r02_$1 python scripts/prof_workload.py $1 > /dev/null 2>&1
   python scripts/ncu_summary.py /tmp/r02_$1.ncu-rep 14 > gpurun_out/r02_ncu_$1.txt 2>&1
   head -3 gpurun_out/r02_ncu_$1.txt
 done
-# ---- L2 prefetch distance of the one-tile-per-CTA kernels
-timeout 300 python scripts/r02_quick.py pfsweep > gpurun_out/r02_prefetch_sweep.jsonl 2>&1; cat gpurun_out/r02_prefetch_sweep.jsonl

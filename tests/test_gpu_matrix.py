@@ -76,6 +76,13 @@ def test_long_observation_axis_segments(dtype):
         assert np.array_equal(np.isnan(got), np.isnan(exp)), f"{func}: NaN masks differ"
         _record(func + "(segments)", got, exp, 0.0, atol)
         np.testing.assert_allclose(got, exp, rtol=0, atol=atol, equal_nan=True)
+    # other pair counts: 40 and 130 variables
+    for nvars in (40, 130):
+        ow = _data((1, 8500, nvars), dtype, seed=7)
+        got = nb.move_covmatrix(ow, window=30, min_count=3)
+        exp = oracle.move_covmatrix(ow, window=30, min_count=3)
+        assert np.array_equal(np.isnan(got), np.isnan(exp))
+        np.testing.assert_allclose(got, exp, rtol=0, atol=atol, equal_nan=True)
     # exponential weights: segments carry their state as an affine map (two passes)
     al = (np.random.RandomState(6).rand(20_000) * 0.2 + 0.005).astype(dtype)
     for alpha in (dtype(0.02), al):
