@@ -477,14 +477,14 @@ def parity_checks(torch, nb, D, oracle, wl, tensors, labels, out, step_on, lo_el
 
 
 # ------------------------------------------------------------------------------ sharded block
-def sharded_block(torch, dist, nd, D, device, rank, world, steps=5):
+def sharded_block(torch, dist, nd, D, device, rank, world, steps=10):
     """Core-axis / element-sharded forms of BASELINE configs 3-5 over NCCL, at
     full size: every rank regenerates the whole input (same seeds), computes the UNSHARDED result on
     its own GPU, runs the sharded form on its contiguous shard and compares its whole shard."""
     results = {}
 
     def timed(fn):
-        for _ in range(3):  # NCCL sets collectives / p2p channels up lazily: first calls are not representative
+        for _ in range(5):  # NCCL sets collectives / p2p channels up lazily: first calls are not representative
             fn()
         torch.cuda.synchronize()
         dist.barrier()
