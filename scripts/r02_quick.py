@@ -195,6 +195,15 @@ def main():
         run("cfg2_group_nanstd", lambda: D.run_group("group_nanstd", a, labels, K, 1), ab, [dict(NBG_RB2_OFF=1), dict(NBG_RB2_NC=3), dict(NBG_RB2_NC=4), dict(NBG_RB2_NC=6)], steps)
         del a
         torch.cuda.empty_cache()
+    if "cfg2nw" in args:
+        rows, n, K = 10_000, 1_000_000, 1000
+        a = gen((rows, n), torch.float32, 0.1)
+        labels = torch.from_numpy(np.random.RandomState(0).randint(0, K, size=n)).to(dev)
+        ab = rows * n * 4 + n * 8 + rows * K * 4
+        sets = [dict(NBG_RB2_NW=w) for w in (16, 8, 12, 24)] + [dict(NBG_RB2_NW=12, NBG_RB2_PD=2), dict(NBG_RB2_NW=16, NBG_RB2_PD=2), dict(NBG_RB2_NW=8, NBG_RB2_S=3), dict(NBG_RB2_NW=12, NBG_RB2_S=3)]
+        run("cfg2_group_nansum", lambda: D.run_group("group_nansum", a, labels, K, 1), ab, sets, steps)
+        del a
+        torch.cuda.empty_cache()
     if "cfg1s" in args:
         rows, n = 2000, 100_000
         a = gen((rows, n), torch.float64, 0.1)
