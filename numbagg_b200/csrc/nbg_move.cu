@@ -524,10 +524,17 @@ struct TileCfg<double> {
     static constexpr int THREADS = 512, E = 9;
 };
 
-template <typename T, class Op, bool RCP>
+// Small problems (fewer than ~2 waves of the 512-thread tiles: BASELINE config 1 is 300 of them on 296
+// slots, i.e. one full wave and a 4-CTA tail) take 128-thread tiles instead: four times as many CTAs, all
+// resident at once, each with a shorter load -> compute -> store chain.
+template <typename T, class Op, bool RCP, int THREADS = TileCfg<T>::THREADS>
 static int launch_rowtile(MoveParams p, int64_t outer, int64_t n, cudaStream_t stream) {
-    constexpr int THREADS = TileCfg<T>::THREADS, E = TileCfg<T>::E;
+    constexpr int E = TileCfg<T>::E;
     using SM = MoveSmem<T, Op::NIN, Op::NCH, THREADS, E, RCP>;
+    if constexpr (THREADS == TileCfg<T>::THREADS) {
+        const int64_t big_tiles = ((n + SM::TILE - 1) / SM::TILE) * outer;
+        if (big_tiles < 4 * (int64_t)kNumSMs && !getenv("NBG_MOVE_BIG_TILES")) return launch_rowtile<T, Op, RCP, 128>(p, outer, n, stream);
+    }
     const int64_t tpr = (n + SM::TILE - 1) / SM::TILE;
     if (tpr * outer > INT32_MAX) return fail(NBG_ERR_UNSUPPORTED, "nbg_move: more than 2^31 tiles");
     p.tiles_per_row = (int)tpr;
