@@ -109,6 +109,32 @@ __device__ __forceinline__ bool rcp_ok(double b) {
 // instructions) next to ours for every element (seen in the SASS of the exp scans: two Newton chains
 // per quotient).
 static __device__ __noinline__ double ieee_div(double a, double b) { return a / b; }
+static __device__ __noinline__ double ieee_sqrt(double v) { return sqrt(v); }
+static __device__ __noinline__ double ieee_rsqrt(double v) { return rsqrt(v); }
+
+
+// sqrt through the float reciprocal-sqrt seed (MUFU.RSQ, ~2^-22 relative error), two Newton
+// steps on y ~ 1/sqrt(v) and one correction of r = v*y: <= 1 ulp.  Values outside
+// (1e-35, 1e35) -- including 0, negatives, inf and NaN -- take the IEEE sqrt path.
+__device__ __forceinline__ double rsqrt_seed(double v) {
+    return (double)rsqrtf((float)v);  // MUFU.RSQ on the float image of v (callers bound v)
+}
+__device__ __forceinline__ double fast_rsqrt(double v) {
+    // callers guarantee 2^-120 < v < 2^120 or handle the specials themselves
+    double y = rsqrt_seed(v);                 // ~2^-22
+    double h = 0.5 * v;
+    y = y * fma(-h * y, y, 1.5);              // ~2^-43
+    y = y * fma(-h * y, y, 1.5);              // ~2^-86 -> rounding-limited
+    return y;
+}
+__device__ __forceinline__ double fast_sqrt(double v) {
+    const bool tiny_or_huge = !(v > 1e-35 && v < 1e35);
+    if (tiny_or_huge) return ieee_sqrt(v);  // rare (also NaN / negative / 0 / inf): IEEE path, out of line
+    const double y = fast_rsqrt(v);
+    double r = v * y;
+    r = fma(fma(-r, r, v), 0.5 * y, r);
+    return r;
+}
 // a / b given y = fast_rcp(b)
 __device__ __forceinline__ double qdiv(double a, double b, double y) {
     const double q = a * y;

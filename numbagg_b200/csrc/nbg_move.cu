@@ -35,28 +35,7 @@ namespace nbg {
 constexpr int kDirectMax = 32;
 constexpr int kRcpMax = 4096;  // windows up to this size use the shared reciprocal table
 
-// sqrt through the float reciprocal-sqrt seed (MUFU.RSQ, ~2^-22 relative error), two Newton
-// steps on y ~ 1/sqrt(v) and one correction of r = v*y: <= 1 ulp.  Values outside
-// (1e-35, 1e35) -- including 0, negatives, inf and NaN -- take the IEEE sqrt path.
-__device__ __forceinline__ double rsqrt_seed(double v) {
-    return (double)rsqrtf((float)v);  // MUFU.RSQ on the float image of v (callers bound v)
-}
-__device__ __forceinline__ double fast_rsqrt(double v) {
-    // callers guarantee 2^-120 < v < 2^120 or handle the specials themselves
-    double y = rsqrt_seed(v);                 // ~2^-22
-    double h = 0.5 * v;
-    y = y * fma(-h * y, y, 1.5);              // ~2^-43
-    y = y * fma(-h * y, y, 1.5);              // ~2^-86 -> rounding-limited
-    return y;
-}
-__device__ __forceinline__ double fast_sqrt(double v) {
-    const bool tiny_or_huge = !(v > 1e-35 && v < 1e35);
-    if (tiny_or_huge) return sqrt(v);  // rare (also NaN / negative / 0 / inf): IEEE path
-    const double y = fast_rsqrt(v);
-    double r = v * y;
-    r = fma(fma(-r, r, v), 0.5 * y, r);
-    return r;
-}
+// (fast_rsqrt / fast_sqrt: nbg_common.cuh)
 // ------------------------------------------------------------------------------------ ops
 // Each op lists its channels (running double sums), how one observation contributes, the
 // order of add/remove (moving.py differs between move_sum and the others) and the output.
@@ -109,7 +88,7 @@ struct OpVar {
                 asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)v));
                 return r;
             }
-            return (T)sqrt(v);
+            return (T)ieee_sqrt(v);
         }
         return (T)(SQRT ? fast_sqrt(v) : v);
     }
@@ -178,7 +157,9 @@ struct OpCorr {
         if constexpr (std::is_same<T, float>::value) {
             if (vv > 1e-30 && vv < 1e30) return __fmul_rn((float)cov, rsqrtf((float)vv));  // ~2e-7 relative
         }
-        return vv > 0 ? (T)dmul(cov, (vv > 1e-35 && vv < 1e35) ? fast_rsqrt(vv) : rsqrt(vv)) : quiet_nan<T>();
+        if (!(vv > 0)) return quiet_nan<T>();
+        if (vv > 1e-35 && vv < 1e35) return (T)dmul(cov, fast_rsqrt(vv));
+        return (T)dmul(cov, ieee_rsqrt(vv));
     }
     __device__ static __forceinline__ T finalize_pfx(const double *s, double rc, double rc1, bool &suspect) {
         if constexpr (std::is_same<T, float>::value) {

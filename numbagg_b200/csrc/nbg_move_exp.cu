@@ -134,7 +134,7 @@ struct ExpVar {  // moving_exp.py:106-224  channels: sum_x_2, sum_x, sum_weight,
         } else {
             v = exp_var_ieee(s[0], s[1], s[2], s[3]);
         }
-        return (T)(SQRT ? sqrt(v) : v);
+        return (T)(SQRT ? sqrt(v) : v);  // (the seed + Newton root is not faster here: 7.71 vs 7.64 ms)
     }
 };
 template <typename T, bool GATE = true>
@@ -193,10 +193,15 @@ struct ExpCorr {  // moving_exp.py:276-335  + sum_x1_2, sum_x2_2  (the weight, w
         double v;
         if (rcp_ok(s[3]) && rcp_ok(sw2) && fabs(a) + fabs(b) + fabs(c) + fabs(t) < kExpInf) {
             if (!(bias > 0)) return quiet_nan<T>();
-            const double den = sqrt(dmul(var1, var2));
-            if (!(den > 0)) return quiet_nan<T>();
-            v = qd(cov, den, fast_rcp(den));
-            if (!(rcp_ok(den) && fabs(v) < kExpInf)) v = ieee_div(cov, den);
+            const double vv = dmul(var1, var2);
+            if (!(vv > 0)) return quiet_nan<T>();  // the reference's gate is sqrt(vv) > 0: the same set
+            if (vv > 1e-35 && vv < 1e35) {
+                v = dmul(cov, fast_rsqrt(vv));  // <= 2 ulp from cov / sqrt(vv)
+            } else {
+                const double den = ieee_sqrt(vv);
+                if (!(den > 0)) return quiet_nan<T>();
+                v = ieee_div(cov, den);
+            }
         } else {
             v = exp_corr_ieee(s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
         }
