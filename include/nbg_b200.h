@@ -274,8 +274,13 @@ int nbg_quantile(const void *a, const void *q, void *out, int64_t rows, int64_t 
  * n_vars); `window`, `min_count` for the moving ops; for the exponential ops `alpha` holds one
  * decay weight per observation in the dtype of `a` -- (n_obs) shared by all batch items
  * (alpha_per_item = 0) or (batch, n_obs) -- and `min_weight` gates the output.
- * dtype: NBG_F32 | NBG_F64.  Results are bit-identical to numbagg (same operations, same
- * order, running sums in the input dtype).
+ * dtype: NBG_F32 | NBG_F64.  With n_obs < 8192 results are bit-identical to numbagg (same
+ * operations, same order, running sums in the input dtype).  Longer observation axes are cut
+ * into segments that run in parallel (windows rebuilt from the preceding observations,
+ * exponential states carried as affine maps, static sums folded in order): results then agree
+ * with numbagg to the rounding of its running sums, NaN masks exactly.  The exponential and the
+ * static forms take their carry / partial-sum workspace from the device's stream-ordered memory
+ * pool (cudaMallocAsync on `stream`).
  */
 typedef enum {
     NBG_MAT_NANCORR = 0,
