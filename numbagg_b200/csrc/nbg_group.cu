@@ -36,6 +36,7 @@
 #include "nbg_common.cuh"
 #include "nbg_group_rowbins.cuh"
 #include "nbg_group_rowbins2.cuh"
+#include "nbg_group_partition.cuh"
 
 namespace nbg {
 
@@ -552,7 +553,18 @@ static int launch_atomic(const V *values, const L *labels, int labels_per_row, G
     int rc;
     constexpr bool kMean = OP == NBG_GROUP_NANMEAN, kVar = OP == NBG_GROUP_NANVAR || OP == NBG_GROUP_NANSTD;
     if ((kMean || kVar) && lay.planar) {
-        // table too large for L2: one pass per channel plane, that plane pinned
+        // table too large for L2.  One row of floating-point values: partition by label range, shared-memory
+        // bins per range (nbg_group_partition.cuh) -- no global atomics on the table
+        if constexpr (VTraits<V>::is_float) {
+            if (rows == 1) {
+                bool handled = false;
+                rc = launch_partition<V, L, kVar ? 2 : 1>(values, labels, n, K, reinterpret_cast<double *>(ws.ch[0]),
+                                                         reinterpret_cast<double *>(ws.ch[1]),
+                                                         reinterpret_cast<long long *>(ws.ch[2]), stream, &handled);
+                if (rc || handled) return rc;
+            }
+        }
+        // otherwise: one pass per channel plane, that plane pinned
         rc = pass(group_atomic_kernel<V, L, OP, 0, 1>, ws.ch[0], plane_bytes, "nbg_group(atomic, sum plane)");
         if (rc) return rc;
         if (kVar) {

@@ -204,6 +204,17 @@ def main():
         run("cfg2_group_nansum", lambda: D.run_group("group_nansum", a, labels, K, 1), ab, sets, steps)
         del a
         torch.cuda.empty_cache()
+    if "cfg5p" in args:
+        n, K = 2_000_000_000, 10_000_000
+        a = gen((n,), torch.float64, 0.1)
+        g = torch.Generator(device=dev).manual_seed(1)
+        labels = torch.randint(0, K, (n,), generator=g, device=dev, dtype=torch.int64)
+        ab = n * 16 + K * 8
+        v2 = a.view(1, -1)
+        for f in ("group_nanvar", "group_nanmean", "group_nanstd"):
+            run("cfg5_" + f, lambda: D.run_group(f, v2, labels, K, 1), ab, [dict(NBG_GROUP_PARTITION=0), dict(NBG_GROUP_PARTITION=1)], 3)
+        del a, labels, v2
+        torch.cuda.empty_cache()
     if "cfg1s" in args:
         rows, n = 2000, 100_000
         a = gen((rows, n), torch.float64, 0.1)

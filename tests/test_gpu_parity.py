@@ -404,6 +404,28 @@ def test_group_high_cardinality_1d(nb):
         _group_check(nb, f, v, labels, num_labels=K)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_group_partition_path(nb, dtype, monkeypatch):
+    """Per-element labels, a table too large for L2, one row of floating-point values: mean / var / std
+    can partition the elements by label range and reduce in shared-memory bins (nbg_group_partition.cuh;
+    an experiment, enabled with NBG_GROUP_PARTITION=1 -- the C library reads it per call).  Labels out of
+    range, NaN values, empty labels and an empty tail bucket are all present.  The default path (one
+    atomic pass per channel plane) runs on the same input first."""
+    _partition_case(nb, dtype)
+    monkeypatch.setenv("NBG_GROUP_PARTITION", "1")
+    _partition_case(nb, dtype)
+
+
+def _partition_case(nb, dtype):
+    n, K = 12_000_000, 6_600_000
+    rs = np.random.RandomState(21)
+    v = (rs.standard_normal(n) * 3 + 1).astype(dtype)
+    v[rs.rand(n) < 0.1] = np.nan
+    labels = rs.randint(-2, K - 20_000, size=n)  # some negative (ignored), the last labels never occur
+    for f in ("group_nanmean", "group_nanvar", "group_nanstd"):
+        _group_check(nb, f, v, labels, num_labels=K)
+
+
 # ---------------------------------------------------------------------------- properties
 def test_properties_large_fill(nb):
     import torch
