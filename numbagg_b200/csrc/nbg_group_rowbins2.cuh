@@ -784,7 +784,7 @@ static Rb2Geometry rb2_geometry(int64_t rows, int64_t n, int64_t K) {
     g.aux_bytes = ((size_t)NCLS * K + (size_t)NCLS * 65 + 64) * 4;
     // consumer warps: 16.  31 (+ producer = 1024 threads) was measured SLOWER on config 2 (10.2 vs 8.6 ms):
     // half-sized ranges double the padding and the per-tile overhead (+28 % instructions); 8 / 12 / 24 warps
-    // measured 8.69 / 8.35 / 9.25 ms against 8.43 (gpurun_out/exp29_cfg2.jsonl): a plateau
+    // measured 8.69 / 8.35 / 9.25 ms against 8.43 (profiles/experiments/r02_exp29_cfg2.jsonl): a plateau
     g.NW = 16;
     if (const char *e = getenv("NBG_RB2_NW")) g.NW = atoi(e) == 31 ? 31 : 16;
     g.ok = true;

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kQThreads) quant_sort_kernel(const double *__r
 // selects per pair), larger distances are one shuffle pair per key.  No shared memory, no barriers:
 // at n = 1000 the CTA-per-row kernels below spend their time in ~130 CTA-wide barriers per row (31 ms
 // on 10^6 x 1000); this one issues ~10 000 instructions per lane and row whatever the number of
-// quantiles and runs at the limit of the integer pipe (17.6 ms; ncu `gpurun_out/exp27_ncu_quant_short.txt`).
+// quantiles and runs at the limit of the integer pipe (17.6 ms; ncu `profiles/r02_ncu_quant_quartiles_short.txt`).
 // Only the exchanges inside a lane need compile-time register indices; the block loop (kk) and the
 // cross-lane distances (lj) are RUNTIME loops -- fully unrolled the network is 10 000 instructions
 // (160 KB of code) and the four warps of a scheduler, each somewhere else in it, stalled on

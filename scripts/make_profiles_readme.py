@@ -67,6 +67,7 @@ out += ["", "Multi-GPU (strong scaling of the fixed configs + sharded forms over
         "* `r02_prefetch_sweep.jsonl` — L2 prefetch distance sweep of the one-tile-per-CTA kernels.",
         "* `r02_launches_quant_median_long.csv` — launch list of one long-row `nanquantile` call (two histogram passes, compaction, candidate sort; the skipped tail passes take 4 µs each).",
         "* `r02_pytest_gpu.log` — the `-m gpu` suite on the box.",
-        "* `r01_*` — round 1's evidence, kept for comparison.", ""]
+        "* `r01_*` — round 1's evidence, kept for comparison.",
+        "* `experiments/` — raw A/B timings behind statements in DESIGN.md: config-4 prefix geometry (`r02_exp18_cfg4g`), matrix segments (`r02_exp20_mat`, `r02_final2_mat`), exp read-outs (`r02_exp22_cfg3`), rb2 label split and warp sweep (`r02_exp24_cfg2`, `r02_exp29_cfg2`, `r02_exp7_cfg2`), config-5 L2 policies and the partition experiment (`r02_exp3_cfg5`, `r02_exp32_cfg5`, `r02_exp33_part_raw.csv`), sharded call breakdown (`r02_exp16_breakdown.txt`).", ""]
 open(os.path.join(P, "README.md"), "w").write("\n".join(out))
 print("\n".join(out[:60]))
