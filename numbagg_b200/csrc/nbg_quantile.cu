@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(kQThreads) quant_hist_kernel(const double *__r
             if (pass == 0) {
                 local_valid += (in && x == x) ? 1 : 0;
                 // sign and exponent: a handful of distinct digits per warp -> warp-aggregated update
+                // (tried: per-thread register counts for the two most recent digits -- divergent, 4.7 vs 4.4 ms)
                 warp_hist_add(h, digit, in);
             } else {
                 const u64 head = key >> hshift;
