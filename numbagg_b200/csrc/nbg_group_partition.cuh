@@ -214,8 +214,11 @@ static int launch_partition(const V *values, const L *labels, int64_t n, int64_t
     // 7 TB/s (2.3 ms) and the reduce pass takes 10.5 ms, but the scatter pass takes 110 ms -- its per-element
     // RETURNING shared-memory atomic (the rank inside the bucket) is resolved one lane at a time (~490 cycles
     // per warp instruction with 32 distinct addresses; ncu: issue slots 3 % busy, short_scoreboard 181 cycles
-    // per issue), where the non-returning adds of the histogram kernel cost nothing.  A scatter that ranks
-    // with warp-level multi-split (match / ballot) instead is the missing piece.
+    // per issue), where the non-returning adds of the histogram kernel cost nothing.  Ranking with warp-private
+    // cursors and match.any instead (no atomics at all, 592 warp slices) was tried too: 135 ms -- so the pass is
+    // really bound by its 4e9 single-element store transactions (32 distinct sectors per warp instruction:
+    // ~36 G transactions/s); the missing piece is write-combining in shared memory (one 32-byte run per
+    // bucket and CTA before anything is stored).
     const char *pe = getenv("NBG_GROUP_PARTITION");
     if (!pe || atoi(pe) == 0) return NBG_OK;
     const int nb = (int)nb64;
